@@ -1,0 +1,409 @@
+// flash_tc.cu — single-head (d = 256) flash attention on tcgen05 for SAM 2 memory attention.
+//
+//   out[b] = softmax(scale * q[b] k[b]^T) v[b]     q [B,Lq,256]  k [B,Lk,256]  v [B,Lk,DV]  (bf16)
+//
+// One CTA owns NQ query tiles of 128 rows of one object and streams the keys once for all of them.
+//   warp 0           : TMA producer — Q tiles once (4 boxes of 128x64 each), then rings of K tiles
+//                      (BN keys x 256, K-major) and V tiles (BN keys x DV, MN-major), 128B swizzle.
+//                      K slots are released as soon as Q·K^T of that tile retires, V slots after P·V.
+//   warp 1           : TMEM allocator + MMA issuer
+//                        S_h,j = Q_h K_j^T     tcgen05.mma SS, M=128 N=BN, 16 K-steps -> S[h][j&1]
+//                        O_h  += P_h,j V_j     tcgen05.mma TS (A = P in TMEM),  M=128 N=DV
+//                      S is double-buffered per query tile so Q·K^T of tile j+1 overlaps softmax j.
+//   warps 2..2+4*NQ  : softmax, one warpgroup per query tile, one thread per query row (TMEM lane):
+//                      tcgen05.ld S row, running max with lazy rescaling (threshold 2^8), ex2, row
+//                      sum, bf16 P written over S with tcgen05.st; conditional O rescale; final
+//                      O / l epilogue and global store.
+// TMEM columns: S[h][i] at (2h+i)*BN, O[h] at 2*NQ*BN + h*DV  (<= 512).
+// DV = 64 is the cross-attention case: the 64->256 value projection is applied AFTER P·V by the
+// caller (softmax rows sum to one), which cuts P·V work and V traffic 4x; NQ = 2 halves the K
+// traffic per FLOP (K tiles come out of L2, which is the binding bandwidth here).
+#include <math.h>
+
+#include "common.h"
+#include "tc05.cuh"
+
+namespace ds2 {
+
+constexpr int kHD = 256;
+constexpr int kQM = 128;
+
+struct FlashParams {
+  int B, Lq, Lk;
+  float scale_log2;
+  __nv_bfloat16* out;
+  long long ldo, bso;
+};
+
+template <int DV, int BN, int NQ, int KS, int VS>
+struct FlashCfg {
+  static constexpr int kThreads = 64 + 128 * NQ;
+  static constexpr int kQBytes = kQM * kHD * 2;  // 64 KB per query tile
+  static constexpr int kKBytes = BN * kHD * 2;
+  static constexpr int kVBytes = BN * DV * 2;
+  static constexpr int kSmemData = NQ * kQBytes + KS * kKBytes + VS * kVBytes;
+  static constexpr int kSmem = kSmemData + 1024 + 512;
+  static constexpr int kTmemCols = 2 * NQ * BN + NQ * DV;
+  static_assert(kTmemCols <= 512, "TMEM budget");
+  static_assert(kSmem <= 232448, "shared memory budget");
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int DV, int BN, int NQ, int KS, int VS>
+__global__ void __launch_bounds__(64 + 128 * NQ, 1)
+flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                          const __grid_constant__ CUtensorMap tmap_k,
+                          const __grid_constant__ CUtensorMap tmap_v, const FlashParams p) {
+  using Cfg = FlashCfg<DV, BN, NQ, KS, VS>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sq = smem_base;
+  const uint32_t sk0 = sq + NQ * Cfg::kQBytes;
+  const uint32_t sv0 = sk0 + KS * Cfg::kKBytes;
+  const uint32_t bar_base = sv0 + VS * Cfg::kVBytes;
+  int nb = 0;
+  const int o_q = nb;        nb += NQ;
+  const int o_kfull = nb;    nb += KS;
+  const int o_kempty = nb;   nb += KS;
+  const int o_vfull = nb;    nb += VS;
+  const int o_vempty = nb;   nb += VS;
+  const int o_sfull = nb;    nb += 2 * NQ;
+  const int o_pfull = nb;    nb += 2 * NQ;
+  const int o_odone = nb;    nb += NQ;
+  auto bar = [&](int off, int i) { return bar_base + 8u * static_cast<uint32_t>(off + i); };
+  const uint32_t tmem_slot = bar_base + 8u * static_cast<uint32_t>(nb);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (kQM * NQ);
+  const int b = blockIdx.y;
+  const int n_tiles = (p.Lk + BN - 1) / BN;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmap_q);
+    tc::prefetch_tmap(&tmap_k);
+    tc::prefetch_tmap(&tmap_v);
+    for (int i = 0; i < NQ; ++i) tc::mbar_init(bar(o_q, i), 1);
+    for (int i = 0; i < KS; ++i) {
+      tc::mbar_init(bar(o_kfull, i), 1);
+      tc::mbar_init(bar(o_kempty, i), 1);
+    }
+    for (int i = 0; i < VS; ++i) {
+      tc::mbar_init(bar(o_vfull, i), 1);
+      tc::mbar_init(bar(o_vempty, i), 1);
+    }
+    for (int i = 0; i < 2 * NQ; ++i) {
+      tc::mbar_init(bar(o_sfull, i), 1);
+      tc::mbar_init(bar(o_pfull, i), 4);
+    }
+    for (int i = 0; i < NQ; ++i) tc::mbar_init(bar(o_odone, i), 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, 512);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  auto tmem_s = [&](int h, int i) { return tmem_base + static_cast<uint32_t>((2 * h + i) * BN); };
+  auto tmem_o = [&](int h) { return tmem_base + static_cast<uint32_t>(2 * NQ * BN + h * DV); };
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    for (int h = 0; h < NQ; ++h) {
+      tc::mbar_expect_tx(bar(o_q, h), Cfg::kQBytes);
+      for (int kk = 0; kk < kHD / 64; ++kk)
+        tc::tma_load_3d(sq + h * Cfg::kQBytes + kk * (kQM * 128), &tmap_q, bar(o_q, h), kk * 64,
+                        q0 + h * kQM, b);
+    }
+    for (int j = 0; j < n_tiles; ++j) {
+      {
+        const int s = j % KS;
+        tc::mbar_wait(bar(o_kempty, s), ((j / KS) & 1) ^ 1);
+        tc::mbar_expect_tx(bar(o_kfull, s), Cfg::kKBytes);
+        const uint32_t sk = sk0 + s * Cfg::kKBytes;
+        for (int kk = 0; kk < kHD / 64; ++kk)
+          tc::tma_load_3d(sk + kk * (BN * 128), &tmap_k, bar(o_kfull, s), kk * 64, j * BN, b);
+      }
+      {
+        const int s = j % VS;
+        tc::mbar_wait(bar(o_vempty, s), ((j / VS) & 1) ^ 1);
+        tc::mbar_expect_tx(bar(o_vfull, s), Cfg::kVBytes);
+        const uint32_t sv = sv0 + s * Cfg::kVBytes;
+        for (int nn = 0; nn < DV / 64; ++nn)
+          tc::tma_load_3d(sv + nn * (BN * 128), &tmap_v, bar(o_vfull, s), nn * 64, j * BN, b);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------ MMA issuer ------------------------------
+    const uint32_t idesc_qk = tc::make_idesc_bf16(kQM, BN, 0, 0);
+    const uint32_t idesc_pv = tc::make_idesc_bf16(kQM, DV, 0, 1);
+    auto issue_qk = [&](int j) {
+      const int s = j % KS;
+      tc::mbar_wait(bar(o_kfull, s), (j / KS) & 1);
+      tc::tc_fence_after();
+      const uint32_t sk = sk0 + s * Cfg::kKBytes;
+#pragma unroll
+      for (int h = 0; h < NQ; ++h) {
+        const uint32_t d = tmem_s(h, j & 1);
+        const uint32_t sqh = sq + h * Cfg::kQBytes;
+#pragma unroll
+        for (int k = 0; k < kHD / 16; ++k) {
+          const uint64_t da = tc::make_desc_sw128(sqh + (k >> 2) * (kQM * 128) + (k & 3) * 32, 16, 1024);
+          const uint64_t db = tc::make_desc_sw128(sk + (k >> 2) * (BN * 128) + (k & 3) * 32, 16, 1024);
+          tc::umma_ss(d, da, db, idesc_qk, k != 0 ? 1u : 0u);
+        }
+        tc::umma_commit(bar(o_sfull, 2 * h + (j & 1)));
+      }
+      tc::umma_commit(bar(o_kempty, s));
+    };
+    for (int h = 0; h < NQ; ++h) tc::mbar_wait(bar(o_q, h), 0);
+    issue_qk(0);
+    for (int j = 0; j < n_tiles; ++j) {
+      if (j + 1 < n_tiles) issue_qk(j + 1);
+      const int s = j % VS;
+      tc::mbar_wait(bar(o_vfull, s), (j / VS) & 1);
+      const uint32_t sv = sv0 + s * Cfg::kVBytes;
+#pragma unroll
+      for (int h = 0; h < NQ; ++h) {
+        tc::mbar_wait(bar(o_pfull, 2 * h + (j & 1)), (j >> 1) & 1);
+        tc::tc_fence_after();
+        const uint32_t pa = tmem_s(h, j & 1);
+#pragma unroll
+        for (int k = 0; k < BN / 16; ++k) {
+          // V tile is MN-major: 64-channel blocks BN*128 B apart (LBO), 8-key groups 1024 B apart (SBO)
+          const uint64_t db = tc::make_desc_sw128(sv + k * 2048, BN * 128, 1024);
+          tc::umma_ts(tmem_o(h), pa + k * 8, db, idesc_pv, (j | k) != 0 ? 1u : 0u);
+        }
+        tc::umma_commit(bar(o_odone, h));
+      }
+      tc::umma_commit(bar(o_vempty, s));
+    }
+  } else if (warp >= 2) {
+    // ------------------------------ softmax / epilogue ------------------------------
+    const int h = (warp - 2) >> 2;  // query tile of this warpgroup
+    const int lq = warp & 3;        // TMEM lane quarter this warp may access
+    const uint32_t lane_off = static_cast<uint32_t>(lq * 32) << 16;
+    const int row = q0 + h * kQM + lq * 32 + lane;
+    const uint32_t to = tmem_o(h) + lane_off;
+    float m_ref = -INFINITY;
+    float l = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      tc::mbar_wait(bar(o_sfull, 2 * h + (j & 1)), (j >> 1) & 1);
+      tc::tc_fence_after();
+      const uint32_t ts = tmem_s(h, j & 1) + lane_off;
+      uint32_t sraw[BN];
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sraw[c * 32]);
+        tc::tmem_ld32(ts + c * 32, chunk);
+      }
+      tc::tmem_ld_wait();
+      const int valid = p.Lk - j * BN;  // keys >= valid are TMA zero fill -> mask
+      float mt = -INFINITY;
+      if (valid >= BN) {
+#pragma unroll
+        for (int i = 0; i < BN; ++i) mt = fmaxf(mt, __uint_as_float(sraw[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < BN; ++i) {
+          if (i >= valid) sraw[i] = 0xff800000u;  // -inf
+          mt = fmaxf(mt, __uint_as_float(sraw[i]));
+        }
+      }
+      float alpha = 1.f;
+      bool resc = false;
+      if (j == 0) {
+        m_ref = mt;
+      } else if ((mt - m_ref) * p.scale_log2 > 8.0f) {
+        alpha = ex2_approx((m_ref - mt) * p.scale_log2);
+        m_ref = mt;
+        resc = true;
+      }
+      const float moff = m_ref * p.scale_log2;
+      float sum = 0.f;
+      uint32_t pk[BN / 2];
+#pragma unroll
+      for (int i = 0; i < BN / 2; ++i) {
+        const float e0 = ex2_approx(fmaf(__uint_as_float(sraw[2 * i]), p.scale_log2, -moff));
+        const float e1 = ex2_approx(fmaf(__uint_as_float(sraw[2 * i + 1]), p.scale_log2, -moff));
+        sum += e0 + e1;
+        pk[i] = tc::pack_bf16(e0, e1);
+      }
+      l = l * alpha + sum;
+#pragma unroll
+      for (int c = 0; c < BN / 64; ++c) {
+        const uint32_t(&chunk)[32] = *reinterpret_cast<const uint32_t(*)[32]>(&pk[c * 32]);
+        tc::tmem_st32(ts + c * 32, chunk);
+      }
+      // Consume every phase of `odone` (P·V of tile j-1 complete) so this waiter is never more than
+      // one phase behind the barrier — parity waits alias otherwise.  By now that MMA has long retired.
+      if (j > 0) tc::mbar_wait(bar(o_odone, h), (j - 1) & 1);
+      if (__any_sync(0xffffffffu, resc)) {
+        // O is stable here: P·V of tile j-1 is complete and P·V of tile j is not yet issued
+        tc::tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < DV / 32; ++c) {
+          uint32_t o[32];
+          tc::tmem_ld32(to + c * 32, o);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tc::tmem_st32(to + c * 32, o);
+        }
+      }
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(bar(o_pfull, 2 * h + (j & 1)));
+    }
+    // epilogue: O / l -> bf16 -> global
+    tc::mbar_wait(bar(o_odone, h), (n_tiles - 1) & 1);
+    tc::tc_fence_after();
+    const float inv = 1.0f / l;
+    __nv_bfloat16* orow = p.out + static_cast<long long>(b) * p.bso + static_cast<long long>(row) * p.ldo;
+#pragma unroll
+    for (int c = 0; c < DV / 32; ++c) {
+      uint32_t o[32];
+      tc::tmem_ld32(to + c * 32, o);
+      tc::tmem_ld_wait();
+      if (row < p.Lq) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 t;
+          t.x = tc::pack_bf16(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+          t.y = tc::pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+          t.z = tc::pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+          t.w = tc::pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+          reinterpret_cast<uint4*>(orow + c * 32)[i] = t;
+        }
+      }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SIMT debug kernel (impl == 1): one warp per query row, f32 math.  Bring-up cross-check only.
+// ---------------------------------------------------------------------------------------------
+__global__ void flash_simt_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                                  const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out,
+                                  long long ldq, long long ldk, long long ldv, long long ldo,
+                                  long long bsq, long long bsk, long long bsv, long long bso, int Lq,
+                                  int Lk, int DV, float scale) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  if (warp >= Lq) return;
+  const __nv_bfloat16* qr = q + b * bsq + warp * ldq;
+  float qv[8];
+  for (int i = 0; i < 8; ++i) qv[i] = __bfloat162float(qr[lane * 8 + i]);
+  float m = -INFINITY, l = 0.f;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // DV/32 values per lane (<= 8)
+  const int per = DV / 32;
+  for (int t = 0; t < Lk; ++t) {
+    const __nv_bfloat16* kr = k + b * bsk + t * ldk;
+    float d = 0.f;
+    for (int i = 0; i < 8; ++i) d += qv[i] * __bfloat162float(kr[lane * 8 + i]);
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    d *= scale;
+    const float mn = fmaxf(m, d);
+    const float a = __expf(m - mn), e = __expf(d - mn);
+    l = l * a + e;
+    const __nv_bfloat16* vr = v + b * bsv + t * ldv;
+    for (int i = 0; i < per; ++i) acc[i] = acc[i] * a + e * __bfloat162float(vr[lane * per + i]);
+    m = mn;
+  }
+  __nv_bfloat16* orow = out + b * bso + warp * ldo;
+  for (int i = 0; i < per; ++i) orow[lane * per + i] = __float2bfloat16(acc[i] / l);
+}
+
+template <int DV, int BN, int NQ, int KS, int VS>
+static int launch_flash(const ds2_flash_args* a, cudaStream_t st) {
+  using Cfg = FlashCfg<DV, BN, NQ, KS, VS>;
+  CUtensorMap tq, tk, tv;
+  {
+    const uint64_t dims[3] = {256, static_cast<uint64_t>(a->Lq), static_cast<uint64_t>(a->B)};
+    const uint64_t str[2] = {static_cast<uint64_t>(a->ldq) * 2, static_cast<uint64_t>(a->bsq) * 2};
+    const uint32_t box[3] = {64, kQM, 1};
+    int rc = make_tmap_bf16(&tq, a->q, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {256, static_cast<uint64_t>(a->Lk), static_cast<uint64_t>(a->B)};
+    const uint64_t str[2] = {static_cast<uint64_t>(a->ldk) * 2, static_cast<uint64_t>(a->bsk) * 2};
+    const uint32_t box[3] = {64, BN, 1};
+    int rc = make_tmap_bf16(&tk, a->k, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(DV), static_cast<uint64_t>(a->Lk),
+                              static_cast<uint64_t>(a->B)};
+    const uint64_t str[2] = {static_cast<uint64_t>(a->ldv) * 2, static_cast<uint64_t>(a->bsv) * 2};
+    const uint32_t box[3] = {64, BN, 1};
+    int rc = make_tmap_bf16(&tv, a->v, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(flash_d256_tcgen05_kernel<DV, BN, NQ, KS, VS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    DS2_REQUIRE(e == cudaSuccess, static_cast<int>(e), "ds2_flash_attn: cudaFuncSetAttribute: %s",
+                cudaGetErrorString(e));
+    attr_set = true;
+  }
+  FlashParams p;
+  p.B = a->B;
+  p.Lq = a->Lq;
+  p.Lk = a->Lk;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  p.ldo = a->ldo;
+  p.bso = a->bso;
+  dim3 grid((a->Lq + kQM * NQ - 1) / (kQM * NQ), a->B);
+  flash_d256_tcgen05_kernel<DV, BN, NQ, KS, VS><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(tq, tk, tv, p);
+  return post_launch("flash_d256_tcgen05_kernel");
+}
+
+}  // namespace ds2
+
+extern "C" int ds2_flash_attn(const ds2_flash_args* a, void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(a != nullptr, DS2_E_ARG, "ds2_flash_attn: null args");
+  DS2_REQUIRE(a->B > 0 && a->Lq > 0 && a->Lk > 0, DS2_E_ARG, "ds2_flash_attn: bad shape");
+  DS2_REQUIRE(a->DV == 64 || a->DV == 256, DS2_E_ARG, "ds2_flash_attn: DV must be 64 or 256 (got %d)",
+              a->DV);
+  DS2_REQUIRE(a->q && a->k && a->v && a->out, DS2_E_ARG, "ds2_flash_attn: null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (a->impl == 1) {
+    dim3 grid((a->Lq * 32 + 255) / 256, a->B);
+    flash_simt_kernel<<<grid, 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(a->q), reinterpret_cast<const __nv_bfloat16*>(a->k),
+        reinterpret_cast<const __nv_bfloat16*>(a->v), reinterpret_cast<__nv_bfloat16*>(a->out), a->ldq,
+        a->ldk, a->ldv, a->ldo, a->bsq, a->bsk, a->bsv, a->bso, a->Lq, a->Lk, a->DV, a->scale);
+    return post_launch("flash_simt_kernel");
+  }
+  DS2_REQUIRE((a->ldq % 8) == 0 && (a->ldk % 8) == 0 && (a->ldv % 8) == 0 && (a->ldo % 8) == 0 &&
+                  (a->bsq % 8) == 0 && (a->bsk % 8) == 0 && (a->bsv % 8) == 0 && (a->bso % 8) == 0,
+              DS2_E_ALIGN, "ds2_flash_attn: pitches must be multiples of 8 elements");
+  // impl: 0 = default (one query tile, 128-key tiles), 3 = two query tiles per CTA / 64-key tiles
+  if (a->DV == 64) {
+    if (a->impl == 3) return launch_flash<64, 64, 2, 2, 3>(a, st);
+    return launch_flash<64, 128, 1, 2, 2>(a, st);
+  }
+  return launch_flash<256, 64, 1, 2, 2>(a, st);
+}

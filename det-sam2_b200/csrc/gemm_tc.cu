@@ -1,0 +1,434 @@
+// gemm_tc.cu — persistent, warp-specialised bf16 GEMM on tcgen05 tensor cores (sm_100a).
+//
+//   out[M,N] = epilogue( A[M,K] · W[N,K]^T )         A, W bf16 K-major; f32 accumulate in TMEM
+//
+// CTA = 256 threads, one CTA per SM, static round-robin over 128 x BN output tiles.
+//   warp 0      : TMA producer   (cp.async.bulk.tensor 2-D, 128B swizzle, 4-stage ring)
+//   warp 1      : MMA issuer     (tcgen05.mma cta_group::1, M=128, N=BN, K=16 per instruction)
+//   warp 2      : TMEM allocator (512 columns = 2 accumulator stages of <=256 columns)
+//   warps 4..7  : epilogue       (tcgen05.ld 32x32b -> bias/act/gamma/rotary/residual -> global)
+// The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of
+// tile i+1.  BN is a run-time multiple of 16 (<=256) chosen so that it divides N where possible
+// (Hiera widths 144/288/576/1152 are not powers of two).
+#include <math.h>
+
+#include "common.h"
+#include "tc05.cuh"
+
+namespace ds2 {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kStages = 4;
+constexpr int kABytes = kBM * kBK * 2;        // 16 KB
+constexpr int kBBytesMax = 256 * kBK * 2;     // 32 KB
+constexpr int kStageBytes = kABytes + kBBytesMax;
+constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kGemmThreads = 256;
+
+struct GemmParams {
+  int M, N, K, BN;
+  int tiles_m, tiles_n;
+  const float* bias;
+  const float* gamma;
+  const float* residual;
+  long long ldr;
+  int res_row_mod;
+  int act;
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  long long ldc, ldc_bf16;
+  const float* rope_cs;
+  int rope_col0, rope_col1, rope_period, rope_rows_per_batch, rope_row_limit;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// Epilogue for NC (16 or 32) consecutive columns of one row held in registers.
+template <int NC>
+__device__ __forceinline__ void epilogue_cols(const GemmParams& p, const uint32_t* acc, int row,
+                                              int col0) {
+  float v[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(acc[i]);
+  const bool full = (col0 + NC <= p.N);
+  if (p.bias) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+      if (full || col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
+  }
+  if (p.act == 1) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] = fmaxf(v[i], 0.0f);
+  } else if (p.act == 2) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] = gelu_erf(v[i]);
+  }
+  if (p.gamma) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+      if (full || col0 + i < p.N) v[i] *= __ldg(p.gamma + col0 + i);
+  }
+  if (p.rope_cs && col0 >= p.rope_col0 && col0 < p.rope_col1) {
+    const int rb = row % p.rope_rows_per_batch;
+    if (rb < p.rope_row_limit) {
+      const int pos = rb % p.rope_period;
+      const float2* cs = reinterpret_cast<const float2*>(p.rope_cs) + static_cast<size_t>(pos) * 128 +
+                         (((col0 - p.rope_col0) & 255) >> 1);
+#pragma unroll
+      for (int i = 0; i < NC / 2; ++i) {
+        const float2 c = __ldg(cs + i);
+        const float a = v[2 * i], b = v[2 * i + 1];
+        v[2 * i] = a * c.x - b * c.y;
+        v[2 * i + 1] = a * c.y + b * c.x;
+      }
+    }
+  }
+  if (p.residual) {
+    const long long rr = p.res_row_mod > 0 ? (row % p.res_row_mod) : row;
+    const float* r = p.residual + rr * p.ldr + col0;
+    if (full && ((p.ldr & 3) == 0)) {
+#pragma unroll
+      for (int i = 0; i < NC / 4; ++i) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(r) + i);
+        v[4 * i] += t.x;
+        v[4 * i + 1] += t.y;
+        v[4 * i + 2] += t.z;
+        v[4 * i + 3] += t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+        if (col0 + i < p.N) v[i] += __ldg(r + i);
+    }
+  }
+  if (p.out_f32) {
+    float* o = p.out_f32 + static_cast<long long>(row) * p.ldc + col0;
+    if (full && ((p.ldc & 3) == 0)) {
+#pragma unroll
+      for (int i = 0; i < NC / 4; ++i)
+        reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+        if (col0 + i < p.N) o[i] = v[i];
+    }
+  }
+  if (p.out_bf16) {
+    __nv_bfloat16* o = p.out_bf16 + static_cast<long long>(row) * p.ldc_bf16 + col0;
+    if (full && ((p.ldc_bf16 & 7) == 0)) {
+#pragma unroll
+      for (int i = 0; i < NC / 8; ++i) {
+        uint4 t;
+        t.x = tc::pack_bf16(v[8 * i], v[8 * i + 1]);
+        t.y = tc::pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+        t.z = tc::pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+        t.w = tc::pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+        reinterpret_cast<uint4*>(o)[i] = t;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+        if (col0 + i < p.N) o[i] = __float2bfloat16(v[i]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                         const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  // barrier layout: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmap_a);
+    tc::prefetch_tmap(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      tc::mbar_init(full_bar(s), 1);
+      tc::mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(tfull_bar(s), 1);
+      tc::mbar_init(tempty_bar(s), 4);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) {
+    tc::tmem_alloc(tmem_slot, 512);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int k_blocks = (p.K + kBK - 1) / kBK;
+  const uint32_t stage_tx = kABytes + static_cast<uint32_t>(p.BN) * kBK * 2;
+
+  if (warp == 0 && lane == 0) {
+    // ---------------- TMA producer ----------------
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_blk = t / p.tiles_n, n_blk = t % p.tiles_n;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        tc::mbar_wait(empty_bar(stage), phase ^ 1);
+        tc::mbar_expect_tx(full_bar(stage), stage_tx);
+        const uint32_t sa = smem_base + stage * kStageBytes;
+        tc::tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBK, m_blk * kBM);
+        tc::tma_load_2d(sa + kABytes, &tmap_w, full_bar(stage), kb * kBK, n_blk * p.BN);
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------- MMA issuer ----------------
+    const uint32_t idesc = tc::make_idesc_bf16(kBM, p.BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      tc::mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tc::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        tc::mbar_wait(full_bar(stage), phase);
+        tc::tc_fence_after();
+        const uint32_t sa = smem_base + stage * kStageBytes;
+        const uint32_t sb = sa + kABytes;
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          const uint64_t da = tc::make_desc_sw128(sa + k * 32, 16, 1024);
+          const uint64_t db = tc::make_desc_sw128(sb + k * 32, 16, 1024);
+          tc::umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        tc::umma_commit(empty_bar(stage));
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      tc::umma_commit(tfull_bar(acc));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue ----------------
+    const int ew = warp - 4;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_blk = t / p.tiles_n, n_blk = t % p.tiles_n;
+      tc::mbar_wait(tfull_bar(acc), acc_phase);
+      tc::tc_fence_after();
+      const int row = m_blk * kBM + ew * 32 + lane;
+      const uint32_t t_addr =
+          tmem_base + static_cast<uint32_t>(acc) * 256u + (static_cast<uint32_t>(ew * 32) << 16);
+      const int n0 = n_blk * p.BN;
+      for (int c = 0; c < p.BN; c += 32) {
+        if (p.BN - c >= 32) {
+          uint32_t r[32];
+          tc::tmem_ld32(t_addr + c, r);
+          tc::tmem_ld_wait();
+          if (row < p.M && n0 + c < p.N) epilogue_cols<32>(p, r, row, n0 + c);
+        } else {
+          uint32_t r[16];
+          tc::tmem_ld16(t_addr + c, r);
+          tc::tmem_ld_wait();
+          if (row < p.M && n0 + c < p.N) epilogue_cols<16>(p, r, row, n0 + c);
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SIMT debug kernel (bring-up cross-check only; selected with args->impl == 1)
+// ---------------------------------------------------------------------------------------------
+__global__ void gemm_bf16_simt_kernel(const __nv_bfloat16* __restrict__ A, long long lda,
+                                      const __nv_bfloat16* __restrict__ W, long long ldw,
+                                      const GemmParams p) {
+  __shared__ float sa[16][17];
+  __shared__ float sb[16][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int row = blockIdx.y * 16 + ty;
+  const int col = blockIdx.x * 16 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < p.K; k0 += 16) {
+    sa[ty][tx] = (row < p.M && k0 + tx < p.K) ? __bfloat162float(A[row * lda + k0 + tx]) : 0.f;
+    const int wr = blockIdx.x * 16 + ty;
+    sb[ty][tx] = (wr < p.N && k0 + tx < p.K) ? __bfloat162float(W[wr * ldw + k0 + tx]) : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += sa[ty][k] * sb[tx][k];
+    __syncthreads();
+  }
+  // epilogue on column pairs so the rotary path matches the tensor-core kernel
+  __shared__ float sc[16][17];
+  sc[ty][tx] = acc;
+  __syncthreads();
+  if ((tx & 1) == 0 && row < p.M && col < p.N) {
+    float v[2] = {sc[ty][tx], sc[ty][tx + 1]};
+    for (int i = 0; i < 2; ++i) {
+      const int c = col + i;
+      if (c >= p.N) continue;
+      if (p.bias) v[i] += p.bias[c];
+      if (p.act == 1) v[i] = fmaxf(v[i], 0.f);
+      if (p.act == 2) v[i] = gelu_erf(v[i]);
+      if (p.gamma) v[i] *= p.gamma[c];
+    }
+    if (p.rope_cs && col >= p.rope_col0 && col < p.rope_col1) {
+      const int rb = row % p.rope_rows_per_batch;
+      if (rb < p.rope_row_limit) {
+        const int pos = rb % p.rope_period;
+        const float2 c = reinterpret_cast<const float2*>(p.rope_cs)[static_cast<size_t>(pos) * 128 +
+                                                                   (((col - p.rope_col0) & 255) >> 1)];
+        const float a = v[0], b = v[1];
+        v[0] = a * c.x - b * c.y;
+        v[1] = a * c.y + b * c.x;
+      }
+    }
+    for (int i = 0; i < 2; ++i) {
+      const int c = col + i;
+      if (c >= p.N) continue;
+      if (p.residual) {
+        const long long rr = p.res_row_mod > 0 ? (row % p.res_row_mod) : row;
+        v[i] += p.residual[rr * p.ldr + c];
+      }
+      if (p.out_f32) p.out_f32[static_cast<long long>(row) * p.ldc + c] = v[i];
+      if (p.out_bf16) p.out_bf16[static_cast<long long>(row) * p.ldc_bf16 + c] = __float2bfloat16(v[i]);
+    }
+  }
+}
+
+static int choose_bn(int N) {
+  if (N % 16 == 0) {
+    for (int bn = 256; bn >= 96; bn -= 16)
+      if (N % bn == 0) return bn;
+    if (N <= 256) return N;
+  }
+  if (N <= 16) return 16;
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  return 128;
+}
+
+}  // namespace ds2
+
+extern "C" int ds2_gemm(const ds2_gemm_args* a, void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(a != nullptr, DS2_E_ARG, "ds2_gemm: null args");
+  DS2_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, DS2_E_ARG, "ds2_gemm: bad shape %d %d %d", a->M, a->N,
+              a->K);
+  DS2_REQUIRE(a->A && a->W, DS2_E_ARG, "ds2_gemm: null operand");
+  DS2_REQUIRE(a->out_f32 || a->out_bf16, DS2_E_ARG, "ds2_gemm: no output");
+  DS2_REQUIRE(a->lda >= a->K && a->ldw >= a->K, DS2_E_ARG, "ds2_gemm: leading dim < K");
+  if (a->rope_cs) {
+    DS2_REQUIRE(a->rope_period > 0 && a->rope_rows_per_batch > 0 && (a->rope_col0 % 32) == 0 &&
+                    (a->rope_col1 % 32) == 0,
+                DS2_E_ARG, "ds2_gemm: bad rotary spec");
+  }
+  GemmParams p;
+  p.M = a->M;
+  p.N = a->N;
+  p.K = a->K;
+  p.bias = a->bias;
+  p.gamma = a->gamma;
+  p.residual = a->residual;
+  p.ldr = a->ldr;
+  p.res_row_mod = a->res_row_mod;
+  p.act = a->act;
+  p.out_f32 = a->out_f32;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
+  p.ldc = a->ldc;
+  p.ldc_bf16 = a->ldc_bf16;
+  p.rope_cs = a->rope_cs;
+  p.rope_col0 = a->rope_col0;
+  p.rope_col1 = a->rope_col1;
+  p.rope_period = a->rope_period;
+  p.rope_rows_per_batch = a->rope_rows_per_batch;
+  p.rope_row_limit = a->rope_row_limit;
+  cudaStream_t st = as_stream(stream);
+
+  if (a->impl == 1) {
+    p.BN = 16;
+    p.tiles_m = p.tiles_n = 0;
+    dim3 grid((a->N + 15) / 16, (a->M + 15) / 16), block(16, 16);
+    gemm_bf16_simt_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a->A), a->lda,
+                                                  reinterpret_cast<const __nv_bfloat16*>(a->W), a->ldw,
+                                                  p);
+    return post_launch("gemm_bf16_simt_kernel");
+  }
+
+  DS2_REQUIRE((a->lda % 8) == 0 && (a->ldw % 8) == 0, DS2_E_ALIGN,
+              "ds2_gemm: lda/ldw must be multiples of 8 elements (got %lld, %lld)",
+              static_cast<long long>(a->lda), static_cast<long long>(a->ldw));
+  p.BN = choose_bn(a->N);
+  p.tiles_m = (a->M + kBM - 1) / kBM;
+  p.tiles_n = (a->N + p.BN - 1) / p.BN;
+
+  CUtensorMap ta, tw;
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->M)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(a->lda) * 2};
+    const uint32_t box[2] = {static_cast<uint32_t>(kBK), static_cast<uint32_t>(kBM)};
+    int rc = make_tmap_bf16(&ta, a->A, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->N)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(a->ldw) * 2};
+    const uint32_t box[2] = {static_cast<uint32_t>(kBK), static_cast<uint32_t>(p.BN)};
+    int rc = make_tmap_bf16(&tw, a->W, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+    DS2_REQUIRE(e == cudaSuccess, static_cast<int>(e), "ds2_gemm: cudaFuncSetAttribute: %s",
+                cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int sms = sm_count();
+  DS2_REQUIRE(sms > 0, DS2_E_NODEVICE, "ds2_gemm: no CUDA device");
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < sms ? tiles : sms;
+  gemm_bf16_tcgen05_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(ta, tw, p);
+  return post_launch("gemm_bf16_tcgen05_kernel");
+}

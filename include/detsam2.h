@@ -1,0 +1,220 @@
+/* detsam2.h — C ABI of libdetsam2.so, the sm_100a kernel library behind the Det-SAM2 / SAM 2.1
+ * video-predictor hot path (Hiera encoder -> memory attention -> mask decoder -> memory encoder
+ * -> post-processing).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every function returns 0 on success, a negative DS2_E_* code on a bad argument, or a
+ *     positive cudaError_t when a launch fails.  No exceptions cross the ABI;
+ *   - activations are token-major ("channels last"): [batch, H*W, C];
+ *   - bf16 buffers are passed as void*; f32 as float*.
+ *
+ * The reference has exactly one FFI on this path (pybind11
+ * `sam2._C.get_connected_componnets`, /root/reference/sam2/csrc/connected_components.cu:213-289);
+ * `ds2_connected_components` replaces it one-for-one.  Every other entry point replaces a torch
+ * library call made by the reference's Python modules; the file:line each one stands in for is
+ * cited next to it.
+ */
+#ifndef DETSAM2_H
+#define DETSAM2_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DS2_OK 0
+#define DS2_E_ARG (-1)      /* invalid argument / unsupported shape */
+#define DS2_E_ALIGN (-2)    /* pointer or leading dimension not aligned as required */
+#define DS2_E_DRIVER (-3)   /* cuTensorMapEncodeTiled unavailable or failed */
+#define DS2_E_NODEVICE (-4) /* no CUDA device */
+
+/* ---- library / device ---------------------------------------------------------------------- */
+int ds2_version(void);
+/* number of kernels launched by this library since load (bench.py `gpu_launches`) */
+int64_t ds2_launch_count(void);
+const char* ds2_last_error(void);
+int ds2_device_sm_count(void);
+
+/* ---- GEMM: out = epilogue(A[M,K] @ W[N,K]^T) -------------------------------------------------
+ * replaces nn.Linear / 1x1 nn.Conv2d / im2col'd convs everywhere on the path
+ * (e.g. sam2/modeling/backbones/hieradet.py:49-50,75-80, memory_attention.py:47-48,
+ *  sam/transformer.py:232-238, memory_encoder.py:98-101).
+ * epilogue, in order:  v = acc + bias[n];  v = act(v);  v *= gamma[n];
+ *                      rotary on column pairs (2i,2i+1) inside [rope_col0, rope_col1);
+ *                      v += residual[row or row % res_row_mod][n];  store f32 and/or bf16.      */
+typedef struct ds2_gemm_args {
+  const void* A;   /* bf16 [M, K], row pitch lda elements (lda % 8 == 0, 16-byte aligned base) */
+  const void* W;   /* bf16 [N, K], row pitch ldw elements */
+  int64_t lda, ldw;
+  int32_t M, N, K;
+  const float* bias;     /* [N] or NULL */
+  const float* gamma;    /* [N] or NULL */
+  const float* residual; /* f32, row pitch ldr, or NULL */
+  int64_t ldr;
+  int32_t res_row_mod;   /* 0: residual row = row;  >0: row % res_row_mod (broadcast over batch) */
+  int32_t act;           /* 0 none, 1 ReLU, 2 GELU(erf) */
+  float* out_f32;        /* row pitch ldc, or NULL */
+  void* out_bf16;        /* row pitch ldc_bf16, or NULL */
+  int64_t ldc, ldc_bf16;
+  /* rotary epilogue (RoPEAttention, sam/transformer.py:311-363; position_encoding.py:193-220) */
+  const float* rope_cs;  /* [rope_period][128][2] (cos, sin) or NULL */
+  int32_t rope_col0, rope_col1;   /* rotate columns c in [col0, col1); pair = ((c-col0) % 256)/2 */
+  int32_t rope_period;            /* table rows; position = (row % rope_rows_per_batch) % period */
+  int32_t rope_rows_per_batch;    /* rows per batch item */
+  int32_t rope_row_limit;         /* rotate only rows with (row % rows_per_batch) < limit */
+  int32_t impl;                   /* 0 = tcgen05 (product path), 1 = SIMT debug kernel */
+} ds2_gemm_args;
+int ds2_gemm(const ds2_gemm_args* args, void* stream);
+
+/* ---- flash attention, one 256-wide head (memory attention) -----------------------------------
+ * replaces F.scaled_dot_product_attention in RoPEAttention.forward
+ * (sam2/modeling/sam/transformer.py:343-361) for MemoryAttentionLayer self- and cross-attention
+ * (memory_attention.py:58-81).   out[b] = softmax(scale * q[b] k[b]^T) v[b]
+ * q [B, Lq, 256], k [B, Lk, 256], v [B, Lk, DV], out [B, Lq, DV], DV in {64, 256}, all bf16.
+ * ld*: row pitch in elements; bs*: batch pitch in elements.                                     */
+typedef struct ds2_flash_args {
+  const void* q; const void* k; const void* v; void* out;
+  int64_t ldq, ldk, ldv, ldo;
+  int64_t bsq, bsk, bsv, bso;
+  int32_t B, Lq, Lk, DV;
+  float scale;
+  int32_t impl; /* 0 = tcgen05, 1 = SIMT debug kernel */
+} ds2_flash_args;
+int ds2_flash_attn(const ds2_flash_args* args, void* stream);
+
+/* ---- generic multi-head attention with optional window addressing (Hiera, mask decoder) ------
+ * replaces F.scaled_dot_product_attention in MultiScaleAttention.forward
+ * (backbones/hieradet.py:57-82, window_partition/unpartition backbones/utils.py:16-63) and in
+ * sam/transformer.py:214-284 (Attention).  See ds2_mha_args in the kernel section below.        */
+typedef struct ds2_mha_args {
+  const void* q; const void* k; const void* v; void* out;  /* bf16 */
+  int64_t q_tok_stride, k_tok_stride, v_tok_stride, o_tok_stride; /* elements between tokens */
+  int64_t q_bs, k_bs, v_bs, o_bs;                                  /* elements between batches */
+  int32_t B, H, D;       /* batch, heads, head_dim (<= 128); head h at column offset h*D */
+  int32_t Lq, Lk;        /* tokens per batch item when window == 0 */
+  /* window mode (window > 0): tokens live on a [Hm, Wm] raster per batch item; attention is
+   * restricted to window x window tiles (zero padding participates, hieradet.py:145-148).  With
+   * q_pool = 1 the query of each 2x2 cell is the element-wise max over the cell
+   * (hieradet.py:65-68) and out has (Hm/2)*(Wm/2) tokens.                                       */
+  int32_t window, Hm, Wm, q_pool;
+  int32_t Lk_valid;      /* keys >= Lk_valid are masked (0 = all valid) */
+  float scale;
+} ds2_mha_args;
+int ds2_mha(const ds2_mha_args* args, void* stream);
+
+/* ---- normalisation / elementwise ------------------------------------------------------------- */
+/* LayerNorm over the last dim (nn.LayerNorm; LayerNorm2d sam2_utils.py:150-162 is the same maths
+ * on channels-last data).  y = LN(x)*w + b; optional GELU; optional second output y + pos.      */
+typedef struct ds2_ln_args {
+  const float* x; int64_t ldx; int32_t rows, C;
+  const float* w; const float* b; float eps;
+  int32_t act;               /* 0 none, 2 GELU */
+  float* out_f32; void* out_bf16; int64_t ldo;
+  const float* pos; int32_t pos_row_mod; /* second output = y + pos[row % pos_row_mod] */
+  void* out2_bf16;
+  const void* x_bf16;        /* alternative bf16 input (x == NULL) */
+} ds2_ln_args;
+int ds2_layernorm(const ds2_ln_args* args, void* stream);
+
+/* y = a*alpha + b*beta (b row-broadcast with modulo), to f32 and/or bf16 */
+int ds2_axpby(const float* a, const float* b, int64_t rows, int32_t C, int32_t b_row_mod,
+              float alpha, float beta, float* out_f32, void* out_bf16, void* stream);
+int ds2_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
+int ds2_cast_bf16_f32(const void* x, float* y, int64_t n, void* stream);
+/* 2x2 max-pool on a token-major [B, Hm, Wm, C] f32 map (hieradet.py:14-29 do_pool) */
+int ds2_maxpool2x2(const float* x, float* y, int32_t B, int32_t Hm, int32_t Wm, int32_t C,
+                   void* stream);
+/* y[b, 2i+di, 2j+dj, :] = top[b, i, j, :] + lat[b, 2i+di, 2j+dj, :]  (FpnNeck top-down,
+ * backbones/image_encoder.py:116-127, nearest) */
+int ds2_upsample2x_add(const float* top, const float* lat, float* y, int32_t B, int32_t Hm,
+                       int32_t Wm, int32_t C, void* stream);
+
+/* ---- convolution helpers ---------------------------------------------------------------------- */
+/* im2col for the patch embedding: fp16 NCHW frame [3, S, S] -> bf16 [ (S/4)^2, Kpad ] rows with
+ * (c, ky, kx) ordering, k7 s4 p3 (backbones/utils.py:66-96). */
+int ds2_im2col_patch(const void* frame_f16, void* out_bf16, int32_t S, int32_t Kpad, void* stream);
+/* im2col k3 s2 p1 on channels-last bf16 [B, Hi, Wi, C] -> [B*Ho*Wo, 9*C] ((ky,kx,c) ordering) */
+int ds2_im2col_k3s2(const void* x_bf16, void* out_bf16, int32_t B, int32_t Hi, int32_t Wi,
+                    int32_t C, void* stream);
+/* depth-wise 7x7 pad 3 on channels-last f32 [B, Hm, Wm, C] (memory_encoder.py:76-82) */
+int ds2_dwconv7(const float* x, const float* w /*[C,49]*/, const float* bias, float* y, int32_t B,
+                int32_t Hm, int32_t Wm, int32_t C, void* stream);
+
+/* ---- memory-encoder mask path (memory_encoder.py:17-58, sam2_base.py:692-743) ------------------
+ * stage 1: low-res logits [B, Sl, Sl] -> (bilinear x4, sigmoid or >0, *scale + bias) -> conv3x3 s2
+ *          (1->4) -> LN2d -> GELU -> bf16 [B, 2Sl, 2Sl, 4].  Never materialises the 4Sl x 4Sl mask. */
+int ds2_maskds_stage1(const float* lowres, int32_t B, int32_t Sl, int32_t binarize, float scale,
+                      float bias, const float* w /*[4,1,3,3]*/, const float* b, const float* ln_w,
+                      const float* ln_b, void* out_bf16, void* stream);
+/* stage 2: direct conv3x3 s2 Cin->Cout + LN2d + GELU on channels-last bf16 */
+int ds2_maskds_conv(const void* x_bf16, int32_t B, int32_t Hi, int32_t Wi, int32_t Cin,
+                    int32_t Cout, const float* w /*[Cout,Cin,3,3]*/, const float* b,
+                    const float* ln_w, const float* ln_b, void* out_bf16, void* stream);
+
+/* ---- mask decoder pieces (sam/mask_decoder.py:163-247, sam2_base.py:342-397) ------------------ */
+/* pixel-shuffle of a ConvTranspose2d(k2,s2) GEMM result + skip + LN2d + GELU:
+ * g [B*Hm*Wm, 4*C] (col = (dy*2+dx)*C + c) -> y bf16 [B, 2Hm, 2Wm, C];  skip f32 [(2Hm*2Wm), C]  */
+int ds2_upscale1(const float* g, const float* bias, const float* skip, const float* ln_w,
+                 const float* ln_b, void* y_bf16, int32_t B, int32_t Hm, int32_t Wm, int32_t C,
+                 void* stream);
+/* second ConvT result g [B*Hm*Wm, 4*C] + skip -> GELU -> dot with hyper[B, M, C] ->
+ * masks f32 [B, M, 2Hm, 2Wm] */
+int ds2_upscale2_masks(const float* g, const float* bias, const float* skip, const float* hyper,
+                       float* masks, int32_t B, int32_t Hm, int32_t Wm, int32_t C, int32_t M,
+                       void* stream);
+/* batched 3-layer MLP on small inputs: y[i] = W3 act(W2 act(W1 x[idx[i]] + b1) + b2) + b3
+ * (hypernetwork / IoU / object-score / obj_ptr heads, sam2_utils.py:121-145).
+ * nmlp independent weight sets laid out back to back; item i uses weight set i % nmlp.         */
+typedef struct ds2_mlp3_args {
+  const float* x; int64_t ldx; const int32_t* gather; /* optional row indices */
+  int32_t rows, nmlp, din, dh, dout;
+  const float* w1; const float* b1; const float* w2; const float* b2; const float* w3;
+  const float* b3;
+  int32_t sigmoid_out;
+  float* y; int64_t ldy;
+} ds2_mlp3_args;
+int ds2_mlp3(const ds2_mlp3_args* args, void* stream);
+
+/* SAM-head selection epilogue (sam2_base.py:342-397, mask_decoder.py:143-158,249-296):
+ * from all_masks [B,4,S,S], ious [B,4], object score [B], tokens [B,4,C] choose the output mask
+ * (multimask: argmax IoU over masks 1..3; single: mask 0 with the stability fallback), apply the
+ * NO_OBJ_SCORE gate, and emit low_res [B,S,S], best index [B], chosen token [B,C].              */
+int ds2_sam_select(const float* all_masks, const float* ious, const float* obj_score,
+                   const float* mask_tokens, int32_t B, int32_t S, int32_t C, int32_t multimask,
+                   float stab_delta, float stab_thresh, float* low_res, float* iou_out,
+                   int32_t* best_idx, float* token_out, void* stream);
+/* obj_ptr = lambda*ptr + (1-lambda)*no_obj_ptr, lambda = [score > 0] (sam2_base.py:376-387) */
+int ds2_objptr_mix(float* ptr, const float* obj_score, const float* no_obj_ptr, int32_t B,
+                   int32_t C, void* stream);
+
+/* ---- memory bank (sam2_base.py:564-648) -------------------------------------------------------
+ * gathers one memory frame into the step's key-input / value buffers:
+ *   kin[b, row0 + t, :] = bf16(mem[b, t, :] + pos[t, :] + tpos[:]),  val[b, row0+t, :] = mem[b,t,:] */
+int ds2_bank_gather(const void* mem_bf16, const float* pos, const float* tpos, void* kin_bf16,
+                    void* val_bf16, int32_t B, int32_t T, int32_t C, int64_t dst_bs, int32_t row0,
+                    void* stream);
+/* object-pointer tokens: ptr f32 [B, 256] -> 4 tokens of 64; kin = bf16(ptr + tpos), val = bf16(ptr) */
+int ds2_bank_ptr(const float* ptr, const float* tpos, void* kin_bf16, void* val_bf16, int32_t B,
+                 int64_t dst_bs, int32_t row0, void* stream);
+
+/* ---- post-processing --------------------------------------------------------------------------
+ * drop-in for sam2._C.get_connected_componnets (csrc/connected_components.cu:213-282):
+ * 8-connected components of a uint8 [N,1,H,W] mask; labels/counts int32 [N,1,H,W].              */
+int ds2_connected_components(const uint8_t* mask, int32_t* labels, int32_t* counts, int32_t N,
+                             int32_t H, int32_t W, void* stream);
+/* fill_holes_in_mask_scores (sam2/utils/misc.py:365-393), fused: in-place on f32 [N,H,W] */
+int ds2_fill_holes(float* scores, int32_t* labels_ws, int32_t* counts_ws, int32_t N, int32_t H,
+                   int32_t W, int32_t max_area, void* stream);
+/* F.interpolate(bilinear, align_corners=False) on f32 [N, Hi, Wi] -> [N, Ho, Wo]
+ * (sam2_video_predictor.py:630-635, sam2_base.py:355-360) */
+int ds2_resize_bilinear(const float* x, float* y, int32_t N, int32_t Hi, int32_t Wi, int32_t Ho,
+                        int32_t Wo, void* stream);
+/* (x > 0) bit-packed, 8 pixels per byte, little-endian bit order (det_sam2_RT.py:396-399) */
+int ds2_threshold_pack(const float* x, uint8_t* bits, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DETSAM2_H */
