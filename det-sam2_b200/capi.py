@@ -53,6 +53,7 @@ class MhaArgs(C.Structure):
         ("window", C.c_int32), ("Hm", C.c_int32), ("Wm", C.c_int32), ("q_pool", C.c_int32),
         ("Lk_valid", C.c_int32),
         ("scale", C.c_float),
+        ("pad_q", C.c_void_p), ("pad_k", C.c_void_p), ("pad_v", C.c_void_p),
     ]
 
 

@@ -1,0 +1,251 @@
+// conv.cu — convolution front-ends: im2col producers for the tcgen05 GEMM (patch embedding,
+// 3x3/s2 mask-downsampler stages), the depth-wise 7x7 of the ConvNeXt fuser, and the fused first
+// stages of the mask down-sampler (bilinear x4 + sigmoid + conv + LayerNorm2d + GELU in one pass,
+// so the 1024^2 high-resolution mask is never written to HBM).
+#include <math.h>
+
+#include "common.h"
+
+namespace ds2 {
+
+__device__ __forceinline__ float gelu_erf_c(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// ---- patch embedding im2col: fp16 [3,S,S] -> bf16 [(S/4)^2, Kpad], k = c*49 + ky*7 + kx ----------
+__global__ void im2col_patch_kernel(const __half* __restrict__ img, __nv_bfloat16* __restrict__ out, int S,
+                                    int Kpad) {
+  const int So = S / 4;
+  const int K8 = Kpad / 8;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(So) * So * K8) return;
+  const int k8 = static_cast<int>(i % K8);
+  const int pix = static_cast<int>(i / K8);
+  const int oy = pix / So, ox = pix % So;
+  uint4 o;
+  __nv_bfloat16* oe = reinterpret_cast<__nv_bfloat16*>(&o);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = k8 * 8 + e;
+    float v = 0.f;
+    if (k < 147) {
+      const int c = k / 49, r = k % 49, ky = r / 7, kx = r % 7;
+      const int iy = oy * 4 - 3 + ky, ix = ox * 4 - 3 + kx;
+      if (iy >= 0 && iy < S && ix >= 0 && ix < S) v = __half2float(img[(static_cast<long long>(c) * S + iy) * S + ix]);
+    }
+    oe[e] = __float2bfloat16(v);
+  }
+  *reinterpret_cast<uint4*>(out + static_cast<long long>(pix) * Kpad + k8 * 8) = o;
+}
+
+// ---- im2col k3 s2 p1, channels-last bf16: [B,Hi,Wi,C] -> [B*Ho*Wo, 9*C], k = (ky*3+kx)*C + c ----
+__global__ void im2col_k3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int B,
+                                   int Hi, int Wi, int C) {
+  const int Ho = Hi / 2, Wo = Wi / 2, C8 = C / 8;
+  const long long n = static_cast<long long>(B) * Ho * Wo * 9 * C8;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c8 = static_cast<int>(i % C8);
+  long long r = i / C8;
+  const int tap = static_cast<int>(r % 9);
+  r /= 9;
+  const int ox = static_cast<int>(r % Wo);
+  r /= Wo;
+  const int oy = static_cast<int>(r % Ho);
+  const int b = static_cast<int>(r / Ho);
+  const int iy = oy * 2 - 1 + tap / 3, ix = ox * 2 - 1 + tap % 3;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (iy >= 0 && iy < Hi && ix >= 0 && ix < Wi)
+    v = *reinterpret_cast<const uint4*>(x + ((static_cast<long long>(b) * Hi + iy) * Wi + ix) * C + c8 * 8);
+  const long long row = (static_cast<long long>(b) * Ho + oy) * Wo + ox;
+  *reinterpret_cast<uint4*>(out + row * (9LL * C) + tap * C + c8 * 8) = v;
+}
+
+// ---- depth-wise 7x7, pad 3, channels-last f32 ---------------------------------------------------
+__global__ void dwconv7_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                               const float* __restrict__ bias, float* __restrict__ y, int B, int Hm, int Wm,
+                               int C) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n = static_cast<long long>(B) * Hm * Wm * C;
+  if (i >= n) return;
+  const int c = static_cast<int>(i % C);
+  long long r = i / C;
+  const int px = static_cast<int>(r % Wm);
+  r /= Wm;
+  const int py = static_cast<int>(r % Hm);
+  const int b = static_cast<int>(r / Hm);
+  float acc = bias ? bias[c] : 0.f;
+  const float* wc = w + c * 49;
+#pragma unroll
+  for (int ky = 0; ky < 7; ++ky) {
+    const int iy = py - 3 + ky;
+    if (iy < 0 || iy >= Hm) continue;
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) {
+      const int ix = px - 3 + kx;
+      if (ix < 0 || ix >= Wm) continue;
+      acc = fmaf(x[((static_cast<long long>(b) * Hm + iy) * Wm + ix) * C + c], wc[ky * 7 + kx], acc);
+    }
+  }
+  y[i] = acc;
+}
+
+// ---- mask down-sampler stage 1 (fused) -----------------------------------------------------------
+// PyTorch bilinear (align_corners=False) source index / weights for scale 1/4.
+__device__ __forceinline__ float hires_mask_value(const float* __restrict__ lr, int Sl, int Y, int X) {
+  const float sy = fmaxf(0.25f * (Y + 0.5f) - 0.5f, 0.f);
+  const float sx = fmaxf(0.25f * (X + 0.5f) - 0.5f, 0.f);
+  const int y0 = min(static_cast<int>(sy), Sl - 1), x0 = min(static_cast<int>(sx), Sl - 1);
+  const int y1 = y0 + (y0 < Sl - 1 ? 1 : 0), x1 = x0 + (x0 < Sl - 1 ? 1 : 0);
+  const float ly = fminf(fmaxf(sy - y0, 0.f), 1.f), lx = fminf(fmaxf(sx - x0, 0.f), 1.f);
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  return hy * (hx * lr[y0 * Sl + x0] + lx * lr[y0 * Sl + x1]) + ly * (hx * lr[y1 * Sl + x0] + lx * lr[y1 * Sl + x1]);
+}
+
+__global__ void maskds_stage1_kernel(const float* __restrict__ lowres, int B, int Sl, int binarize, float scale,
+                                     float bias, const float* __restrict__ w, const float* __restrict__ cb,
+                                     const float* __restrict__ lnw, const float* __restrict__ lnb,
+                                     __nv_bfloat16* __restrict__ out) {
+  const int So = Sl * 2, Sh = Sl * 4;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(B) * So * So) return;
+  const int ox = static_cast<int>(i % So);
+  const int oy = static_cast<int>((i / So) % So);
+  const int b = static_cast<int>(i / (static_cast<long long>(So) * So));
+  const float* lr = lowres + static_cast<long long>(b) * Sl * Sl;
+  float acc[4] = {cb[0], cb[1], cb[2], cb[3]};
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int Y = oy * 2 - 1 + ky;
+    if (Y < 0 || Y >= Sh) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int X = ox * 2 - 1 + kx;
+      if (X < 0 || X >= Sh) continue;
+      const float hv = hires_mask_value(lr, Sl, Y, X);
+      const float m = (binarize ? (hv > 0.f ? 1.f : 0.f) : 1.f / (1.f + expf(-hv))) * scale + bias;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[c] = fmaf(m, w[c * 9 + ky * 3 + kx], acc[c]);
+    }
+  }
+  const float u = 0.25f * (acc[0] + acc[1] + acc[2] + acc[3]);
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) s += (acc[c] - u) * (acc[c] - u);
+  const float rstd = rsqrtf(0.25f * s + 1e-6f);
+  uint2 o;
+  __nv_bfloat16* oe = reinterpret_cast<__nv_bfloat16*>(&o);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) oe[c] = __float2bfloat16(gelu_erf_c((acc[c] - u) * rstd * lnw[c] + lnb[c]));
+  *reinterpret_cast<uint2*>(out + i * 4) = o;
+}
+
+// ---- direct conv3x3 s2 p1 (small Cin, Cout <= 16) + LN2d + GELU, channels-last bf16 ----------------
+template <int CIN, int COUT>
+__global__ void maskds_conv_kernel(const __nv_bfloat16* __restrict__ x, int B, int Hi, int Wi,
+                                   const float* __restrict__ w, const float* __restrict__ cb,
+                                   const float* __restrict__ lnw, const float* __restrict__ lnb,
+                                   __nv_bfloat16* __restrict__ out) {
+  __shared__ float sw[COUT * CIN * 9];
+  for (int i = threadIdx.x; i < COUT * CIN * 9; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int Ho = Hi / 2, Wo = Wi / 2;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(B) * Ho * Wo) return;
+  const int ox = static_cast<int>(i % Wo);
+  const int oy = static_cast<int>((i / Wo) % Ho);
+  const int b = static_cast<int>(i / (static_cast<long long>(Wo) * Ho));
+  float acc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) acc[o] = cb[o];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * 2 - 1 + ky;
+    if (iy < 0 || iy >= Hi) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * 2 - 1 + kx;
+      if (ix < 0 || ix >= Wi) continue;
+      const __nv_bfloat16* px = x + ((static_cast<long long>(b) * Hi + iy) * Wi + ix) * CIN;
+      float xv[CIN];
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) xv[c] = __bfloat162float(px[c]);
+#pragma unroll
+      for (int o = 0; o < COUT; ++o)
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) acc[o] = fmaf(xv[c], sw[(o * CIN + c) * 9 + ky * 3 + kx], acc[o]);
+    }
+  }
+  float u = 0.f;
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) u += acc[o];
+  u /= COUT;
+  float s = 0.f;
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) s += (acc[o] - u) * (acc[o] - u);
+  const float rstd = rsqrtf(s / COUT + 1e-6f);
+  __nv_bfloat16* po = out + i * COUT;
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) po[o] = __float2bfloat16(gelu_erf_c((acc[o] - u) * rstd * lnw[o] + lnb[o]));
+}
+
+}  // namespace ds2
+
+extern "C" {
+
+int ds2_im2col_patch(const void* frame_f16, void* out_bf16, int32_t S, int32_t Kpad, void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(frame_f16 && out_bf16 && S > 0 && (S % 4) == 0 && Kpad >= 147 && (Kpad % 8) == 0, DS2_E_ARG,
+              "ds2_im2col_patch: bad args");
+  const long long n = static_cast<long long>(S / 4) * (S / 4) * (Kpad / 8);
+  im2col_patch_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __half*>(frame_f16), reinterpret_cast<__nv_bfloat16*>(out_bf16), S, Kpad);
+  return post_launch("im2col_patch_kernel");
+}
+
+int ds2_im2col_k3s2(const void* x_bf16, void* out_bf16, int32_t B, int32_t Hi, int32_t Wi, int32_t C, void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(x_bf16 && out_bf16 && B > 0 && (Hi % 2) == 0 && (Wi % 2) == 0 && (C % 8) == 0, DS2_E_ARG,
+              "ds2_im2col_k3s2: bad args");
+  const long long n = static_cast<long long>(B) * (Hi / 2) * (Wi / 2) * 9 * (C / 8);
+  im2col_k3s2_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16), B, Hi, Wi, C);
+  return post_launch("im2col_k3s2_kernel");
+}
+
+int ds2_dwconv7(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Hm, int32_t Wm,
+                int32_t C, void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(x && w && y && B > 0 && Hm > 0 && Wm > 0 && C > 0, DS2_E_ARG, "ds2_dwconv7: bad args");
+  const long long n = static_cast<long long>(B) * Hm * Wm * C;
+  dwconv7_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(x, w, bias, y, B, Hm, Wm, C);
+  return post_launch("dwconv7_kernel");
+}
+
+int ds2_maskds_stage1(const float* lowres, int32_t B, int32_t Sl, int32_t binarize, float scale, float bias,
+                      const float* w, const float* b, const float* ln_w, const float* ln_b, void* out_bf16,
+                      void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(lowres && w && b && ln_w && ln_b && out_bf16 && B > 0 && Sl > 0, DS2_E_ARG,
+              "ds2_maskds_stage1: bad args");
+  const long long n = static_cast<long long>(B) * Sl * 2 * Sl * 2;
+  maskds_stage1_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+      lowres, B, Sl, binarize, scale, bias, w, b, ln_w, ln_b, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  return post_launch("maskds_stage1_kernel");
+}
+
+int ds2_maskds_conv(const void* x_bf16, int32_t B, int32_t Hi, int32_t Wi, int32_t Cin, int32_t Cout,
+                    const float* w, const float* b, const float* ln_w, const float* ln_b, void* out_bf16,
+                    void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(x_bf16 && w && b && ln_w && ln_b && out_bf16 && B > 0, DS2_E_ARG, "ds2_maskds_conv: bad args");
+  DS2_REQUIRE(Cin == 4 && Cout == 16, DS2_E_ARG, "ds2_maskds_conv: only 4->16 is instantiated (got %d->%d)", Cin,
+              Cout);
+  const long long n = static_cast<long long>(B) * (Hi / 2) * (Wi / 2);
+  maskds_conv_kernel<4, 16><<<static_cast<unsigned>((n + 127) / 128), 128, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x_bf16), B, Hi, Wi, w, b, ln_w, ln_b,
+      reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  return post_launch("maskds_conv_kernel");
+}
+
+}  // extern "C"

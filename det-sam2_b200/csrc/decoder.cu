@@ -1,0 +1,292 @@
+// decoder.cu — SAM mask-decoder tail: transposed-conv pixel shuffles fused with skip / LayerNorm2d /
+// GELU, the hypernetwork mask product (the 32-channel up-scaled embedding is consumed on the fly and
+// never written to HBM), small batched 3-layer MLP heads, and the mask / token selection epilogue.
+#include <math.h>
+
+#include "common.h"
+
+namespace ds2 {
+
+__device__ __forceinline__ float gelu_erf_d(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float warp_sum_d(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// one warp per OUTPUT pixel; C == 64 (2 channels per lane)
+__global__ void __launch_bounds__(256) upscale1_kernel(const float* __restrict__ g, const float* __restrict__ bias,
+                                                       const float* __restrict__ skip,
+                                                       const float* __restrict__ lnw,
+                                                       const float* __restrict__ lnb,
+                                                       __nv_bfloat16* __restrict__ y, int B, int Hm, int Wm, int C) {
+  const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int Ho = Hm * 2, Wo = Wm * 2;
+  if (wid >= static_cast<long long>(B) * Ho * Wo) return;
+  const int X = static_cast<int>(wid % Wo);
+  const int Y = static_cast<int>((wid / Wo) % Ho);
+  const int b = static_cast<int>(wid / (static_cast<long long>(Wo) * Ho));
+  const long long grow = (static_cast<long long>(b) * Hm + Y / 2) * Wm + X / 2;
+  const int sub = (Y & 1) * 2 + (X & 1);
+  const float* gp = g + grow * (4LL * C) + sub * C;
+  const float* sp = skip + (static_cast<long long>(Y) * Wo + X) * C;
+  float v[2];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = lane + i * 32;
+    v[i] = gp[c] + bias[c] + sp[c];
+    s += v[i];
+  }
+  const float mean = warp_sum_d(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) q += (v[i] - mean) * (v[i] - mean);
+  const float rstd = rsqrtf(warp_sum_d(q) / C + 1e-6f);
+  __nv_bfloat16* yp = y + wid * C;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = lane + i * 32;
+    yp[c] = __float2bfloat16(gelu_erf_d((v[i] - mean) * rstd * lnw[c] + lnb[c]));
+  }
+}
+
+// one thread per OUTPUT pixel; C == 32; M <= 4 hyper vectors per object held in shared memory
+__global__ void __launch_bounds__(256) upscale2_masks_kernel(const float* __restrict__ g,
+                                                             const float* __restrict__ bias,
+                                                             const float* __restrict__ skip,
+                                                             const float* __restrict__ hyper,
+                                                             float* __restrict__ masks, int B, int Hm, int Wm,
+                                                             int M) {
+  constexpr int C = 32;
+  __shared__ float sh[4 * C + C];
+  const int Ho = Hm * 2, Wo = Wm * 2;
+  const long long per_obj = static_cast<long long>(Ho) * Wo;
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < M * C; i += blockDim.x) sh[i] = hyper[static_cast<long long>(b) * M * C + i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sh[4 * C + i] = bias[i];
+  __syncthreads();
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pix >= per_obj) return;
+  const int X = static_cast<int>(pix % Wo), Y = static_cast<int>(pix / Wo);
+  const long long grow = (static_cast<long long>(b) * Hm + Y / 2) * Wm + X / 2;
+  const int sub = (Y & 1) * 2 + (X & 1);
+  const float4* gp = reinterpret_cast<const float4*>(g + grow * (4LL * C) + sub * C);
+  const float4* sp = reinterpret_cast<const float4*>(skip + pix * C);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < C / 4; ++i) {
+    const float4 a = gp[i], s = sp[i];
+    float u[4] = {a.x + s.x + sh[4 * C + 4 * i], a.y + s.y + sh[4 * C + 4 * i + 1],
+                  a.z + s.z + sh[4 * C + 4 * i + 2], a.w + s.w + sh[4 * C + 4 * i + 3]};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float t = gelu_erf_d(u[e]);
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+        if (m < M) acc[m] = fmaf(t, sh[m * C + 4 * i + e], acc[m]);
+    }
+  }
+  for (int m = 0; m < M; ++m) masks[(static_cast<long long>(b) * M + m) * per_obj + pix] = acc[m];
+}
+
+// batched 3-layer MLP, one CTA (256 threads) per row item
+struct Mlp3Params {
+  const float* x;
+  long long ldx;
+  const int* gather;
+  int rows, nmlp, din, dh, dout;
+  const float *w1, *b1, *w2, *b2, *w3, *b3;
+  int sigmoid_out;
+  float* y;
+  long long ldy;
+};
+__global__ void __launch_bounds__(256) mlp3_kernel(const Mlp3Params p) {
+  extern __shared__ float sm[];
+  float* xin = sm;             // din
+  float* h1 = xin + p.din;     // dh
+  float* h2 = h1 + p.dh;       // dh
+  const int item = blockIdx.x;
+  const int set = item % p.nmlp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long src = p.gather ? p.gather[item] : item;
+  for (int i = threadIdx.x; i < p.din; i += blockDim.x) xin[i] = p.x[src * p.ldx + i];
+  __syncthreads();
+  const float* w1 = p.w1 + static_cast<long long>(set) * p.dh * p.din;
+  const float* w2 = p.w2 + static_cast<long long>(set) * p.dh * p.dh;
+  const float* w3 = p.w3 + static_cast<long long>(set) * p.dout * p.dh;
+  for (int o = warp; o < p.dh; o += 8) {
+    float a = 0.f;
+    for (int k = lane; k < p.din; k += 32) a = fmaf(w1[static_cast<long long>(o) * p.din + k], xin[k], a);
+    a = warp_sum_d(a);
+    if (lane == 0) h1[o] = fmaxf(a + p.b1[set * p.dh + o], 0.f);
+  }
+  __syncthreads();
+  for (int o = warp; o < p.dh; o += 8) {
+    float a = 0.f;
+    for (int k = lane; k < p.dh; k += 32) a = fmaf(w2[static_cast<long long>(o) * p.dh + k], h1[k], a);
+    a = warp_sum_d(a);
+    if (lane == 0) h2[o] = fmaxf(a + p.b2[set * p.dh + o], 0.f);
+  }
+  __syncthreads();
+  for (int o = warp; o < p.dout; o += 8) {
+    float a = 0.f;
+    for (int k = lane; k < p.dh; k += 32) a = fmaf(w3[static_cast<long long>(o) * p.dh + k], h2[k], a);
+    a = warp_sum_d(a);
+    if (lane == 0) {
+      a += p.b3[set * p.dout + o];
+      if (p.sigmoid_out) a = 1.f / (1.f + expf(-a));
+      p.y[static_cast<long long>(item) * p.ldy + o] = a;
+    }
+  }
+}
+
+// mask / token selection: one CTA per object
+__global__ void __launch_bounds__(256) sam_select_kernel(const float* __restrict__ all_masks,
+                                                         const float* __restrict__ ious,
+                                                         const float* __restrict__ obj_score,
+                                                         const float* __restrict__ mask_tokens, int B, int S, int C,
+                                                         int multimask, float delta, float thresh,
+                                                         float* __restrict__ low_res, float* __restrict__ iou_out,
+                                                         int* __restrict__ best_idx, float* __restrict__ token_out) {
+  __shared__ int s_i, s_u, s_idx;
+  const int b = blockIdx.x;
+  const long long n = static_cast<long long>(S) * S;
+  if (threadIdx.x == 0) {
+    s_i = 0;
+    s_u = 0;
+  }
+  __syncthreads();
+  const float* io = ious + b * 4;
+  int best_multi = 1;
+  {
+    float bv = io[1];
+    if (io[2] > bv) { bv = io[2]; best_multi = 2; }
+    if (io[3] > bv) { bv = io[3]; best_multi = 3; }
+  }
+  if (!multimask) {
+    const float* m0 = all_masks + static_cast<long long>(b) * 4 * n;
+    int ci = 0, cu = 0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+      const float v = m0[i];
+      ci += v > delta;
+      cu += v > -delta;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      ci += __shfl_xor_sync(0xffffffffu, ci, o);
+      cu += __shfl_xor_sync(0xffffffffu, cu, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&s_i, ci);
+      atomicAdd(&s_u, cu);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int idx;
+    if (multimask) {
+      idx = best_multi;
+    } else {
+      const float stab = s_u > 0 ? static_cast<float>(s_i) / static_cast<float>(s_u) : 1.0f;
+      idx = (stab >= thresh) ? 0 : best_multi;
+    }
+    s_idx = idx;
+    best_idx[b] = idx;
+    iou_out[b] = io[idx];
+  }
+  __syncthreads();
+  const int idx = s_idx;
+  const bool present = obj_score[b] > 0.f;
+  const float* src = all_masks + (static_cast<long long>(b) * 4 + idx) * n;
+  float* dst = low_res + static_cast<long long>(b) * n;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) dst[i] = present ? src[i] : -1024.0f;
+  // object-pointer token: the matching multimask token, or token 0 in single-mask mode
+  const int tok = multimask ? idx : 0;
+  for (int i = threadIdx.x; i < C; i += blockDim.x)
+    token_out[static_cast<long long>(b) * C + i] = mask_tokens[(static_cast<long long>(b) * 4 + tok) * C + i];
+}
+
+__global__ void objptr_mix_kernel(float* __restrict__ ptr, const float* __restrict__ obj_score,
+                                  const float* __restrict__ no_obj_ptr, int B, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const float lam = obj_score[i / C] > 0.f ? 1.f : 0.f;
+  ptr[i] = lam * ptr[i] + (1.f - lam) * no_obj_ptr[i % C];
+}
+
+}  // namespace ds2
+
+extern "C" {
+
+int ds2_upscale1(const float* g, const float* bias, const float* skip, const float* ln_w, const float* ln_b,
+                 void* y_bf16, int32_t B, int32_t Hm, int32_t Wm, int32_t C, void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(g && bias && skip && ln_w && ln_b && y_bf16 && B > 0, DS2_E_ARG, "ds2_upscale1: bad args");
+  DS2_REQUIRE(C == 64, DS2_E_ARG, "ds2_upscale1: C must be 64 (got %d)", C);
+  const long long warps = static_cast<long long>(B) * Hm * 2 * Wm * 2;
+  upscale1_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(
+      g, bias, skip, ln_w, ln_b, reinterpret_cast<__nv_bfloat16*>(y_bf16), B, Hm, Wm, C);
+  return post_launch("upscale1_kernel");
+}
+
+int ds2_upscale2_masks(const float* g, const float* bias, const float* skip, const float* hyper, float* masks,
+                       int32_t B, int32_t Hm, int32_t Wm, int32_t C, int32_t M, void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(g && bias && skip && hyper && masks && B > 0, DS2_E_ARG, "ds2_upscale2_masks: bad args");
+  DS2_REQUIRE(C == 32 && M >= 1 && M <= 4, DS2_E_ARG, "ds2_upscale2_masks: C must be 32 and M <= 4");
+  const long long per_obj = static_cast<long long>(Hm) * 2 * Wm * 2;
+  dim3 grid(static_cast<unsigned>((per_obj + 255) / 256), B);
+  upscale2_masks_kernel<<<grid, 256, 0, as_stream(stream)>>>(g, bias, skip, hyper, masks, B, Hm, Wm, M);
+  return post_launch("upscale2_masks_kernel");
+}
+
+int ds2_mlp3(const ds2_mlp3_args* a, void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(a && a->x && a->w1 && a->b1 && a->w2 && a->b2 && a->w3 && a->b3 && a->y, DS2_E_ARG,
+              "ds2_mlp3: null pointer");
+  DS2_REQUIRE(a->rows > 0 && a->nmlp > 0 && a->din > 0 && a->dh > 0 && a->dout > 0, DS2_E_ARG, "ds2_mlp3: bad dims");
+  Mlp3Params p;
+  p.x = a->x;
+  p.ldx = a->ldx;
+  p.gather = a->gather;
+  p.rows = a->rows;
+  p.nmlp = a->nmlp;
+  p.din = a->din;
+  p.dh = a->dh;
+  p.dout = a->dout;
+  p.w1 = a->w1;
+  p.b1 = a->b1;
+  p.w2 = a->w2;
+  p.b2 = a->b2;
+  p.w3 = a->w3;
+  p.b3 = a->b3;
+  p.sigmoid_out = a->sigmoid_out;
+  p.y = a->y;
+  p.ldy = a->ldy;
+  const int smem = (a->din + 2 * a->dh) * 4;
+  mlp3_kernel<<<a->rows, 256, smem, as_stream(stream)>>>(p);
+  return post_launch("mlp3_kernel");
+}
+
+int ds2_sam_select(const float* all_masks, const float* ious, const float* obj_score, const float* mask_tokens,
+                   int32_t B, int32_t S, int32_t C, int32_t multimask, float stab_delta, float stab_thresh,
+                   float* low_res, float* iou_out, int32_t* best_idx, float* token_out, void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(all_masks && ious && obj_score && mask_tokens && low_res && iou_out && best_idx && token_out && B > 0,
+              DS2_E_ARG, "ds2_sam_select: bad args");
+  sam_select_kernel<<<B, 256, 0, as_stream(stream)>>>(all_masks, ious, obj_score, mask_tokens, B, S, C, multimask,
+                                                     stab_delta, stab_thresh, low_res, iou_out, best_idx, token_out);
+  return post_launch("sam_select_kernel");
+}
+
+int ds2_objptr_mix(float* ptr, const float* obj_score, const float* no_obj_ptr, int32_t B, int32_t C, void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(ptr && obj_score && no_obj_ptr && B > 0 && C > 0, DS2_E_ARG, "ds2_objptr_mix: bad args");
+  objptr_mix_kernel<<<(B * C + 255) / 256, 256, 0, as_stream(stream)>>>(ptr, obj_score, no_obj_ptr, B, C);
+  return post_launch("objptr_mix_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,354 @@
+// mha.cu — generic multi-head flash attention for the small / oddly-shaped attentions of the path:
+// Hiera window + global attention (head_dim 72/56/96, windows 4..16, 2x2 query max-pool, zero-pad
+// windows) and the two-way mask-decoder attentions (head_dim 16/32, 7-9 tokens x 4096 pixels).
+//
+// CTA = 4 warps = 64 query rows of one (batch x window, head); keys are streamed through shared
+// memory in chunks of 64; S = Q K^T and O += P V on mma.sync.m16n8k16 (bf16 in, f32 accumulate) with
+// the head dim zero-padded to a multiple of 16; online softmax in registers with quad shuffles.
+// (These are <2 % of the frame's FLOPs; the d=256 memory attention uses the tcgen05 kernel in
+// flash_tc.cu.)
+#include <math.h>
+
+#include "common.h"
+
+namespace ds2 {
+
+struct MhaParams {
+  const __nv_bfloat16* q;
+  const __nv_bfloat16* k;
+  const __nv_bfloat16* v;
+  __nv_bfloat16* out;
+  long long q_tok, k_tok, v_tok, o_tok;
+  long long q_bs, k_bs, v_bs, o_bs;
+  int B, H, D;
+  int Lq, Lk;
+  int window, Hm, Wm, q_pool;
+  int nwy, nwx;
+  int Lk_valid;
+  float scale_log2;
+  const __nv_bfloat16* pad_q;
+  const __nv_bfloat16* pad_k;
+  const __nv_bfloat16* pad_v;
+};
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                               uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ float ex2f_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+
+// Address of token (row index inside the sequence) for q / k / v, or nullptr for a padded token.
+struct SeqGeom {
+  int b, wy, wx;
+  int Lq, Lk;
+};
+
+template <int DP>
+__global__ void __launch_bounds__(128) mha_kernel(const MhaParams p) {
+  constexpr int QS = DP + 8;   // smem row stride (elements) for Q / K tiles
+  constexpr int VS = 64 + 8;   // smem row stride for V^T
+  extern __shared__ __align__(16) uint8_t smem_mha[];
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_mha);
+  __nv_bfloat16* Ks = Qs + 64 * QS;
+  __nv_bfloat16* Vt = Ks + 64 * QS;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int h = blockIdx.y;
+  const int w = p.window;
+  int b, wy = 0, wx = 0, Lq, Lk;
+  if (w > 0) {
+    const int per = p.nwy * p.nwx;
+    b = blockIdx.x / per;
+    const int wi = blockIdx.x % per;
+    wy = wi / p.nwx;
+    wx = wi % p.nwx;
+    Lk = w * w;
+    Lq = p.q_pool ? (w / 2) * (w / 2) : Lk;
+  } else {
+    b = blockIdx.x;
+    Lq = p.Lq;
+    Lk = p.Lk;
+  }
+  const int q0 = blockIdx.z * 64;
+  if (q0 >= Lq) return;
+  const int Lk_valid = (p.Lk_valid > 0 && w == 0) ? p.Lk_valid : Lk;
+  const int DV8 = p.D / 8;  // 16-byte vectors per head row
+
+  auto tok_ptr = [&](const __nv_bfloat16* base, long long bs, long long ts, const __nv_bfloat16* pad,
+                     int r) -> const __nv_bfloat16* {
+    if (w == 0) return base + b * bs + static_cast<long long>(r) * ts + h * p.D;
+    const int gy = wy * w + r / w, gx = wx * w + r % w;
+    if (gy < p.Hm && gx < p.Wm) return base + b * bs + (static_cast<long long>(gy) * p.Wm + gx) * ts + h * p.D;
+    return pad ? pad + h * p.D : nullptr;
+  };
+
+  // ---- stage Q tile (rows >= Lq and dims >= D are zero) ----
+  for (int i = tid; i < 64 * (DP / 8); i += 128) {
+    const int r = i / (DP / 8), c = i % (DP / 8);
+    uint4 val = make_uint4(0, 0, 0, 0);
+    const int qr = q0 + r;
+    if (qr < Lq && c < DV8) {
+      if (w > 0 && p.q_pool) {
+        const int hw = w / 2;
+        const int py = qr / hw, px = qr % hw;
+        bool first = true;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const __nv_bfloat16* src = tok_ptr(p.q, p.q_bs, p.q_tok, p.pad_q, (2 * py + dy) * w + 2 * px + dx);
+            uint4 x = make_uint4(0, 0, 0, 0);
+            if (src) x = *reinterpret_cast<const uint4*>(src + c * 8);
+            val = first ? x : bf16x8_max(val, x);
+            first = false;
+          }
+      } else {
+        const __nv_bfloat16* src = tok_ptr(p.q, p.q_bs, p.q_tok, p.pad_q, qr);
+        if (src) val = *reinterpret_cast<const uint4*>(src + c * 8);
+      }
+    }
+    *reinterpret_cast<uint4*>(Qs + r * QS + c * 8) = val;
+  }
+  __syncthreads();
+
+  // ---- Q fragments ----
+  uint32_t qa[DP / 16][4];
+  {
+    const __nv_bfloat16* qrow0 = Qs + (warp * 16 + g) * QS;
+    const __nv_bfloat16* qrow1 = qrow0 + 8 * QS;
+#pragma unroll
+    for (int kk = 0; kk < DP / 16; ++kk) {
+      qa[kk][0] = *reinterpret_cast<const uint32_t*>(qrow0 + kk * 16 + 2 * t);
+      qa[kk][1] = *reinterpret_cast<const uint32_t*>(qrow1 + kk * 16 + 2 * t);
+      qa[kk][2] = *reinterpret_cast<const uint32_t*>(qrow0 + kk * 16 + 8 + 2 * t);
+      qa[kk][3] = *reinterpret_cast<const uint32_t*>(qrow1 + kk * 16 + 8 + 2 * t);
+    }
+  }
+  float o[DP / 8][4];
+#pragma unroll
+  for (int i = 0; i < DP / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const bool warp_active = (q0 + warp * 16) < Lq;
+
+  for (int k0 = 0; k0 < Lk; k0 += 64) {
+    __syncthreads();
+    // ---- stage K chunk [64][DP] and V^T chunk [DP][64] ----
+    for (int i = tid; i < 64 * (DP / 8); i += 128) {
+      const int r = i / (DP / 8), c = i % (DP / 8);
+      const int kr = k0 + r;
+      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+      if (kr < Lk && c < DV8) {
+        const __nv_bfloat16* ks = tok_ptr(p.k, p.k_bs, p.k_tok, p.pad_k, kr);
+        const __nv_bfloat16* vs = tok_ptr(p.v, p.v_bs, p.v_tok, p.pad_v, kr);
+        if (ks) kv = *reinterpret_cast<const uint4*>(ks + c * 8);
+        if (vs) vv = *reinterpret_cast<const uint4*>(vs + c * 8);
+      }
+      *reinterpret_cast<uint4*>(Ks + r * QS + c * 8) = kv;
+      const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) Vt[(c * 8 + e) * VS + r] = ve[e];
+    }
+    __syncthreads();
+    if (!warp_active) continue;
+
+    // ---- S = Q K^T for this warp's 16 rows x 64 keys ----
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      const __nv_bfloat16* krow = Ks + (nt * 8 + g) * QS;
+#pragma unroll
+      for (int kk = 0; kk < DP / 16; ++kk) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + kk * 16 + 2 * t);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + kk * 16 + 8 + 2 * t);
+        mma_bf16_16816(s[nt], qa[kk], b0, b1);
+      }
+    }
+    // ---- mask + online softmax (rows g and g+8) ----
+    const int lim = Lk_valid - k0;  // keys >= lim masked
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int c0 = nt * 8 + 2 * t;
+      if (c0 >= lim) s[nt][0] = s[nt][2] = -INFINITY;
+      if (c0 + 1 >= lim) s[nt][1] = s[nt][3] = -INFINITY;
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float a0 = (m0 == -INFINITY) ? 0.f : ex2f_fast((m0 - mn0) * p.scale_log2);
+    const float a1 = (m1 == -INFINITY) ? 0.f : ex2f_fast((m1 - mn1) * p.scale_log2);
+    m0 = mn0;
+    m1 = mn1;
+    const float off0 = (mn0 == -INFINITY) ? 0.f : mn0 * p.scale_log2;
+    const float off1 = (mn1 == -INFINITY) ? 0.f : mn1 * p.scale_log2;
+    float sum0 = 0.f, sum1 = 0.f;
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float e0 = ex2f_fast(fmaf(s[nt][0], p.scale_log2, -off0));
+      const float e1 = ex2f_fast(fmaf(s[nt][1], p.scale_log2, -off0));
+      const float e2 = ex2f_fast(fmaf(s[nt][2], p.scale_log2, -off1));
+      const float e3 = ex2f_fast(fmaf(s[nt][3], p.scale_log2, -off1));
+      sum0 += e0 + e1;
+      sum1 += e2 + e3;
+      __nv_bfloat162 p01 = __floats2bfloat162_rn(e0, e1);
+      __nv_bfloat162 p23 = __floats2bfloat162_rn(e2, e3);
+      pa[nt >> 1][(nt & 1) * 2 + 0] = *reinterpret_cast<uint32_t*>(&p01);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&p23);
+    }
+    l0 = l0 * a0 + sum0;
+    l1 = l1 * a1 + sum1;
+#pragma unroll
+    for (int i = 0; i < DP / 8; ++i) {
+      o[i][0] *= a0;
+      o[i][1] *= a0;
+      o[i][2] *= a1;
+      o[i][3] *= a1;
+    }
+    // ---- O += P V ----
+#pragma unroll
+    for (int i = 0; i < DP / 8; ++i) {
+      const __nv_bfloat16* vrow = Vt + (i * 8 + g) * VS;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vrow + kk * 16 + 2 * t);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vrow + kk * 16 + 8 + 2 * t);
+        mma_bf16_16816(o[i], pa[kk], b0, b1);
+      }
+    }
+  }
+  if (!warp_active) return;
+  // ---- finalize: quad-reduce row sums, normalise, store ----
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  auto out_ptr = [&](int r) -> __nv_bfloat16* {
+    if (r >= Lq) return nullptr;
+    if (w == 0) return p.out + b * p.o_bs + static_cast<long long>(r) * p.o_tok + h * p.D;
+    const int ww = p.q_pool ? w / 2 : w;
+    const int Ho = p.q_pool ? p.Hm / 2 : p.Hm, Wo = p.q_pool ? p.Wm / 2 : p.Wm;
+    const int gy = wy * ww + r / ww, gx = wx * ww + r % ww;
+    if (gy >= Ho || gx >= Wo) return nullptr;
+    return p.out + b * p.o_bs + (static_cast<long long>(gy) * Wo + gx) * p.o_tok + h * p.D;
+  };
+  __nv_bfloat16* o0 = out_ptr(q0 + warp * 16 + g);
+  __nv_bfloat16* o1 = out_ptr(q0 + warp * 16 + g + 8);
+#pragma unroll
+  for (int i = 0; i < DP / 8; ++i) {
+    const int c = i * 8 + 2 * t;
+    if (c < p.D) {
+      if (o0) *reinterpret_cast<__nv_bfloat162*>(o0 + c) = __floats2bfloat162_rn(o[i][0] * i0, o[i][1] * i0);
+      if (o1) *reinterpret_cast<__nv_bfloat162*>(o1 + c) = __floats2bfloat162_rn(o[i][2] * i1, o[i][3] * i1);
+    }
+  }
+}
+
+template <int DP>
+static int launch_mha(const MhaParams& p, dim3 grid, cudaStream_t st) {
+  const int smem = (2 * 64 * (DP + 8) + DP * 72) * 2;
+  if (smem > 48 * 1024) {
+    static bool set = false;
+    if (!set) {
+      cudaFuncSetAttribute(mha_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      set = true;
+    }
+  }
+  mha_kernel<DP><<<grid, 128, smem, st>>>(p);
+  return post_launch("mha_kernel");
+}
+
+}  // namespace ds2
+
+extern "C" int ds2_mha(const ds2_mha_args* a, void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(a != nullptr, DS2_E_ARG, "ds2_mha: null args");
+  DS2_REQUIRE(a->q && a->k && a->v && a->out, DS2_E_ARG, "ds2_mha: null pointer");
+  DS2_REQUIRE(a->B > 0 && a->H > 0 && a->D > 0 && a->D <= 128 && (a->D % 8) == 0, DS2_E_ARG,
+              "ds2_mha: bad head spec B=%d H=%d D=%d", a->B, a->H, a->D);
+  DS2_REQUIRE((a->q_tok_stride % 8) == 0 && (a->k_tok_stride % 8) == 0 && (a->v_tok_stride % 8) == 0 &&
+                  (a->o_tok_stride % 2) == 0,
+              DS2_E_ALIGN, "ds2_mha: token strides must be multiples of 8 elements");
+  MhaParams p;
+  p.q = reinterpret_cast<const __nv_bfloat16*>(a->q);
+  p.k = reinterpret_cast<const __nv_bfloat16*>(a->k);
+  p.v = reinterpret_cast<const __nv_bfloat16*>(a->v);
+  p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  p.q_tok = a->q_tok_stride;
+  p.k_tok = a->k_tok_stride;
+  p.v_tok = a->v_tok_stride;
+  p.o_tok = a->o_tok_stride;
+  p.q_bs = a->q_bs;
+  p.k_bs = a->k_bs;
+  p.v_bs = a->v_bs;
+  p.o_bs = a->o_bs;
+  p.B = a->B;
+  p.H = a->H;
+  p.D = a->D;
+  p.Lq = a->Lq;
+  p.Lk = a->Lk;
+  p.window = a->window;
+  p.Hm = a->Hm;
+  p.Wm = a->Wm;
+  p.q_pool = a->q_pool;
+  p.Lk_valid = a->Lk_valid;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.pad_q = reinterpret_cast<const __nv_bfloat16*>(a->pad_q);
+  p.pad_k = reinterpret_cast<const __nv_bfloat16*>(a->pad_k);
+  p.pad_v = reinterpret_cast<const __nv_bfloat16*>(a->pad_v);
+  p.nwy = p.nwx = 1;
+  int Lq, nseq;
+  if (a->window > 0) {
+    DS2_REQUIRE(a->Hm > 0 && a->Wm > 0, DS2_E_ARG, "ds2_mha: window mode needs Hm, Wm");
+    DS2_REQUIRE(!a->q_pool || ((a->window % 2) == 0 && (a->Hm % 2) == 0 && (a->Wm % 2) == 0), DS2_E_ARG,
+                "ds2_mha: q_pool needs even window and map");
+    p.nwy = (a->Hm + a->window - 1) / a->window;
+    p.nwx = (a->Wm + a->window - 1) / a->window;
+    const bool padded = (a->Hm % a->window) != 0 || (a->Wm % a->window) != 0;
+    DS2_REQUIRE(!padded || (a->pad_q && a->pad_k && a->pad_v), DS2_E_ARG,
+                "ds2_mha: padded windows need pad_q/pad_k/pad_v");
+    Lq = a->q_pool ? (a->window / 2) * (a->window / 2) : a->window * a->window;
+    nseq = a->B * p.nwy * p.nwx;
+  } else {
+    DS2_REQUIRE(a->Lq > 0 && a->Lk > 0, DS2_E_ARG, "ds2_mha: bad Lq/Lk");
+    Lq = a->Lq;
+    nseq = a->B;
+  }
+  DS2_REQUIRE((Lq + 63) / 64 <= 65535 && a->H <= 65535, DS2_E_ARG, "ds2_mha: grid too large");
+  dim3 grid(nseq, a->H, (Lq + 63) / 64);
+  cudaStream_t st = as_stream(stream);
+  const int D = a->D;
+  if (D <= 16) return launch_mha<16>(p, grid, st);
+  if (D <= 32) return launch_mha<32>(p, grid, st);
+  if (D <= 64) return launch_mha<64>(p, grid, st);
+  if (D <= 80) return launch_mha<80>(p, grid, st);
+  if (D <= 96) return launch_mha<96>(p, grid, st);
+  return launch_mha<128>(p, grid, st);
+}

@@ -1,0 +1,216 @@
+// post.cu — post-processing of mask logits: 8-connected component labelling (lock-free union-find
+// with atomicMin), hole filling, bilinear resize to video resolution, threshold + bit-pack.
+// Integer / byte work, HBM- and latency-bound; grids cover all objects of a frame in one launch
+// (the reference launches 6 kernels per object, csrc/connected_components.cu:245-276).
+#include <limits.h>
+
+#include "common.h"
+
+namespace ds2 {
+
+__device__ __forceinline__ int uf_find(const int* parent, int n) {
+  int p = parent[n];
+  while (p != n) {
+    n = p;
+    p = parent[n];
+  }
+  return n;
+}
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a > b) {
+      const int t = a;
+      a = b;
+      b = t;
+    }
+    // a < b : hang b under a if b is still a root
+    const int old = atomicMin(parent + b, a);
+    if (old == b) return;
+    b = old;
+  }
+}
+
+// fg(p): foreground predicate source is either a uint8 mask (!=0) or f32 scores (<= 0)
+__device__ __forceinline__ bool is_fg(const uint8_t* m8, const float* sc, long long i) {
+  return m8 ? (m8[i] != 0) : (sc[i] <= 0.f);
+}
+
+__global__ void cc_init_kernel(const uint8_t* __restrict__ m8, const float* __restrict__ sc, int* __restrict__ parent,
+                               int* __restrict__ area, int* __restrict__ minblk, long long total, int HW) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  parent[i] = is_fg(m8, sc, i) ? static_cast<int>(i % HW) : -1;
+  area[i] = 0;
+  if (minblk) minblk[i] = INT_MAX;
+}
+
+__global__ void cc_merge_kernel(int* __restrict__ parent, long long total, int H, int W) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int HW = H * W;
+  const int p = static_cast<int>(i % HW);
+  int* par = parent + (i - p);
+  if (par[p] < 0) return;
+  const int y = p / W, x = p % W;
+  if (x > 0 && par[p - 1] >= 0) uf_union(par, p, p - 1);
+  if (y > 0) {
+    if (par[p - W] >= 0) uf_union(par, p, p - W);
+    if (x > 0 && par[p - W - 1] >= 0) uf_union(par, p, p - W - 1);
+    if (x + 1 < W && par[p - W + 1] >= 0) uf_union(par, p, p - W + 1);
+  }
+}
+
+__global__ void cc_count_kernel(const int* __restrict__ parent, int* __restrict__ area, int* __restrict__ minblk,
+                                long long total, int H, int W) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int HW = H * W;
+  const int p = static_cast<int>(i % HW);
+  const long long base = i - p;
+  if (parent[i] < 0) return;
+  const int root = uf_find(parent + base, p);
+  atomicAdd(area + base + root, 1);
+  if (minblk) {
+    const int y = p / W, x = p % W;
+    atomicMin(minblk + base + root, (y & ~1) * W + (x & ~1));
+  }
+}
+
+__global__ void cc_emit_kernel(const int* __restrict__ parent, const int* __restrict__ minblk,
+                               int* __restrict__ labels, int* __restrict__ counts, long long total, int HW) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int p = static_cast<int>(i % HW);
+  const long long base = i - p;
+  if (parent[i] < 0) {
+    labels[i] = 0;
+    counts[i] = 0;
+    return;
+  }
+  const int root = uf_find(parent + base, p);
+  labels[i] = minblk[base + root] + 1;
+  counts[i] = counts[base + root];  // roots keep their own value; non-roots are never read as roots
+}
+
+__global__ void fill_holes_kernel(float* __restrict__ scores, const int* __restrict__ parent,
+                                  const int* __restrict__ area, long long total, int HW, int max_area) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  if (parent[i] < 0) return;
+  const int p = static_cast<int>(i % HW);
+  const long long base = i - p;
+  const int root = uf_find(parent + base, p);
+  if (area[base + root] <= max_area) scores[i] = 0.1f;
+}
+
+// PyTorch upsample_bilinear2d, align_corners=False, antialias=False
+__global__ void resize_bilinear_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int Hi, int Wi,
+                                       int Ho, int Wo, float sh, float sw) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(N) * Ho * Wo;
+  if (i >= total) return;
+  const int ox = static_cast<int>(i % Wo);
+  const int oy = static_cast<int>((i / Wo) % Ho);
+  const int n = static_cast<int>(i / (static_cast<long long>(Wo) * Ho));
+  const float sy = fmaxf(sh * (oy + 0.5f) - 0.5f, 0.f);
+  const float sx = fmaxf(sw * (ox + 0.5f) - 0.5f, 0.f);
+  const int y0 = min(static_cast<int>(sy), Hi - 1), x0 = min(static_cast<int>(sx), Wi - 1);
+  const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
+  const float ly = fminf(fmaxf(sy - y0, 0.f), 1.f), lx = fminf(fmaxf(sx - x0, 0.f), 1.f);
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const float* src = x + static_cast<long long>(n) * Hi * Wi;
+  y[i] = hy * (hx * src[y0 * Wi + x0] + lx * src[y0 * Wi + x1]) + ly * (hx * src[y1 * Wi + x0] + lx * src[y1 * Wi + x1]);
+}
+
+__global__ void threshold_pack_kernel(const float* __restrict__ x, uint8_t* __restrict__ bits, long long n) {
+  const long long byte = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long i0 = byte * 8;
+  if (i0 >= n) return;
+  unsigned v = 0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    if (i0 + e < n && x[i0 + e] > 0.f) v |= 1u << e;
+  bits[byte] = static_cast<uint8_t>(v);
+}
+
+static inline unsigned nblocks(long long n, int bs) { return static_cast<unsigned>((n + bs - 1) / bs); }
+
+}  // namespace ds2
+
+extern "C" {
+
+int ds2_connected_components(const uint8_t* mask, int32_t* labels, int32_t* counts, int32_t N, int32_t H, int32_t W,
+                             void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(mask && labels && counts && N > 0 && H > 0 && W > 0, DS2_E_ARG, "ds2_connected_components: bad args");
+  // the reference asserts even H and W (csrc/connected_components.cu:229-232)
+  DS2_REQUIRE((H % 2) == 0 && (W % 2) == 0, DS2_E_ARG, "ds2_connected_components: height and width must be even");
+  cudaStream_t st = as_stream(stream);
+  const long long total = static_cast<long long>(N) * H * W;
+  int* tmp = nullptr;
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&tmp), static_cast<size_t>(total) * 2 * sizeof(int), st);
+  DS2_REQUIRE(e == cudaSuccess, static_cast<int>(e), "ds2_connected_components: cudaMallocAsync: %s",
+              cudaGetErrorString(e));
+  int* parent = tmp;
+  int* minblk = tmp + total;
+  const int HW = H * W;
+  cc_init_kernel<<<nblocks(total, 256), 256, 0, st>>>(mask, nullptr, parent, counts, minblk, total, HW);
+  int rc = post_launch("cc_init_kernel");
+  if (!rc) {
+    cc_merge_kernel<<<nblocks(total, 256), 256, 0, st>>>(parent, total, H, W);
+    rc = post_launch("cc_merge_kernel");
+  }
+  if (!rc) {
+    cc_count_kernel<<<nblocks(total, 256), 256, 0, st>>>(parent, counts, minblk, total, H, W);
+    rc = post_launch("cc_count_kernel");
+  }
+  if (!rc) {
+    cc_emit_kernel<<<nblocks(total, 256), 256, 0, st>>>(parent, minblk, labels, counts, total, HW);
+    rc = post_launch("cc_emit_kernel");
+  }
+  cudaFreeAsync(tmp, st);
+  return rc;
+}
+
+int ds2_fill_holes(float* scores, int32_t* labels_ws, int32_t* counts_ws, int32_t N, int32_t H, int32_t W,
+                   int32_t max_area, void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(scores && labels_ws && counts_ws && N > 0 && H > 0 && W > 0 && max_area > 0, DS2_E_ARG,
+              "ds2_fill_holes: bad args");
+  cudaStream_t st = as_stream(stream);
+  const long long total = static_cast<long long>(N) * H * W;
+  const int HW = H * W;
+  cc_init_kernel<<<nblocks(total, 256), 256, 0, st>>>(nullptr, scores, labels_ws, counts_ws, nullptr, total, HW);
+  int rc = post_launch("cc_init_kernel");
+  if (rc) return rc;
+  cc_merge_kernel<<<nblocks(total, 256), 256, 0, st>>>(labels_ws, total, H, W);
+  rc = post_launch("cc_merge_kernel");
+  if (rc) return rc;
+  cc_count_kernel<<<nblocks(total, 256), 256, 0, st>>>(labels_ws, counts_ws, nullptr, total, H, W);
+  rc = post_launch("cc_count_kernel");
+  if (rc) return rc;
+  fill_holes_kernel<<<nblocks(total, 256), 256, 0, st>>>(scores, labels_ws, counts_ws, total, HW, max_area);
+  return post_launch("fill_holes_kernel");
+}
+
+int ds2_resize_bilinear(const float* x, float* y, int32_t N, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo,
+                        void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(x && y && N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, DS2_E_ARG, "ds2_resize_bilinear: bad args");
+  const long long total = static_cast<long long>(N) * Ho * Wo;
+  resize_bilinear_kernel<<<nblocks(total, 256), 256, 0, as_stream(stream)>>>(
+      x, y, N, Hi, Wi, Ho, Wo, static_cast<float>(Hi) / Ho, static_cast<float>(Wi) / Wo);
+  return post_launch("resize_bilinear_kernel");
+}
+
+int ds2_threshold_pack(const float* x, uint8_t* bits, int64_t n, void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(x && bits && n > 0, DS2_E_ARG, "ds2_threshold_pack: bad args");
+  threshold_pack_kernel<<<nblocks((n + 7) / 8, 256), 256, 0, as_stream(stream)>>>(x, bits, n);
+  return post_launch("threshold_pack_kernel");
+}
+
+}  // extern "C"

@@ -101,6 +101,9 @@ typedef struct ds2_mha_args {
   int32_t window, Hm, Wm, q_pool;
   int32_t Lk_valid;      /* keys >= Lk_valid are masked (0 = all valid) */
   float scale;
+  /* bf16 [H*D] rows substituted for zero-padded window tokens: a padded token is x = 0 after
+   * norm1, so its q/k/v are the qkv bias (hieradet.py:145-148, backbones/utils.py:28-32)        */
+  const void* pad_q; const void* pad_k; const void* pad_v;
 } ds2_mha_args;
 int ds2_mha(const ds2_mha_args* args, void* stream);
 
