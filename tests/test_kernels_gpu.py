@@ -233,8 +233,9 @@ def test_elementwise(ops):
     ob = torch.empty(512, 256, device=DEV, dtype=torch.bfloat16)
     ops.axpby(a, b, 1.0, 0.1, b_row_mod=64, out_f32=of, out_bf16=ob)
     ref = a + 0.1 * b.repeat(8, 1)
-    assert torch.equal(of, ref)
-    assert torch.equal(ob, bf(ref))
+    # the kernel contracts a*alpha + b*beta into FMAs: equal to torch up to one rounding of 0.1*b
+    assert (of - ref).abs().max().item() < 1e-6
+    assert (ob.float() - ref).abs().max().item() < 2e-2
     y = torch.empty(1001, device=DEV, dtype=torch.bfloat16)
     x = torch.randn(1001, device=DEV)
     ops.cast_f32_bf16(x, y)
