@@ -181,7 +181,7 @@ def param_shapes(cfg: ModelConfig) -> "OrderedDict[str, tuple]":
     return s
 
 
-def synthetic_state_dict(cfg: ModelConfig, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+def synthetic_state_dict(cfg: ModelConfig, seed: int = 0, obj_score_bias: float = 4.0) -> "OrderedDict[str, torch.Tensor]":
     """Seeded random weights (fp32, CPU).  Scales are chosen so that activations stay O(1) through
     the 48-block trunk and mask logits are O(1..10): weights ~ N(0, 1/fan_in), norm scales ~ 1,
     biases / embeddings small, layer-scale gamma O(0.1) so the ConvNeXt branch matters."""
@@ -216,6 +216,9 @@ def synthetic_state_dict(cfg: ModelConfig, seed: int = 0) -> "OrderedDict[str, t
             t = 0.5 * torch.randn(shape, generator=g) if ("token" in name or "point_embeddings" in name) \
                 else 0.1 * torch.randn(shape, generator=g)
         sd[name] = t.float().contiguous()
+    # random heads put the object score near 0, where the `score > 0` gate (sam2_base.py:342-350)
+    # flips on rounding noise; a trained checkpoint is decisively positive on visible objects
+    sd["sam_mask_decoder.pred_obj_score_head.layers.2.bias"] += obj_score_bias
     return sd
 
 
