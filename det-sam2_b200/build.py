@@ -22,6 +22,7 @@ SOURCES = [
     "conv.cu",
     "decoder.cu",
     "post.cu",
+    "prompt.cu",
 ]
 
 NVCC_FLAGS = [

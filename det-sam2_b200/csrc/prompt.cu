@@ -1,0 +1,148 @@
+// prompt.cu — small latency-bound pieces around the mask decoder and the memory bank:
+//   * prompt encoder (random-Fourier point embedding + label embeddings) fused with the assembly of
+//     the decoder's token matrix,
+//   * object-pointer bank tokens with the temporal positional encoding computed in-kernel,
+//   * memory-encoder tail (no-object embedding + bf16 store).
+#include <math.h>
+
+#include "common.h"
+
+namespace ds2 {
+
+// tokens[b, t, :]:  t < n_out -> out_tokens[t];  t >= n_out -> sparse embedding of point t - n_out
+// (point P is the padding point (0,0,label -1) appended when no box is given,
+//  sam/prompt_encoder.py:73-95).  One CTA (128 threads) per (b, t); C = 256 = 2 * 128.
+__global__ void __launch_bounds__(128) prompt_tokens_kernel(const float* __restrict__ coords,
+                                                            const int* __restrict__ labels, int B, int P,
+                                                            const float* __restrict__ gauss,      // [2,128]
+                                                            const float* __restrict__ point_emb,  // [4,256]
+                                                            const float* __restrict__ not_a_point,  // [256]
+                                                            const float* __restrict__ out_tokens,   // [n_out,256]
+                                                            int n_out, float image_size,
+                                                            float* __restrict__ tokens) {
+  const int nt = n_out + P + 1;
+  const int b = blockIdx.x / nt, t = blockIdx.x % nt;
+  const int j = threadIdx.x;  // frequency index 0..127
+  float* dst = tokens + (static_cast<long long>(b) * nt + t) * 256;
+  if (t < n_out) {
+    dst[j] = out_tokens[t * 256 + j];
+    dst[j + 128] = out_tokens[t * 256 + 128 + j];
+    return;
+  }
+  const int pidx = t - n_out;
+  float x = 0.f, y = 0.f;
+  int lab = -1;
+  if (pidx < P) {
+    x = coords[(static_cast<long long>(b) * P + pidx) * 2 + 0];
+    y = coords[(static_cast<long long>(b) * P + pidx) * 2 + 1];
+    lab = labels[static_cast<long long>(b) * P + pidx];
+  }
+  float s = 0.f, c = 0.f;
+  if (lab != -1) {
+    // (p + 0.5) / S -> [0,1] -> 2u - 1 -> @ G -> * 2 pi   (position_encoding.py:131-158)
+    const float u = 2.f * ((x + 0.5f) / image_size) - 1.f;
+    const float v = 2.f * ((y + 0.5f) / image_size) - 1.f;
+    const float a = 6.283185307179586f * (u * gauss[j] + v * gauss[128 + j]);
+    sincosf(a, &s, &c);
+  }
+  float e0 = s, e1 = c;
+  if (lab == -1) {
+    e0 = not_a_point[j];
+    e1 = not_a_point[128 + j];
+  } else if (lab >= 0 && lab < 4) {
+    e0 += point_emb[lab * 256 + j];
+    e1 += point_emb[lab * 256 + 128 + j];
+  }
+  dst[j] = e0;
+  dst[j + 128] = e1;
+}
+
+// Object-pointer tokens of one stored frame (sam2_base.py:588-648): ptr f32 [B,256] -> 4 tokens of 64;
+//   tpos = W[64,256] . sine1d(dist / t_diff_max, 256) + bias     (get_1d_sine_pe sam2_utils.py:69-79)
+//   kin = bf16(ptr + tpos),  val = bf16(ptr).   grid = B, block = 256.
+__global__ void __launch_bounds__(256) bank_ptr_pe_kernel(const float* __restrict__ ptr, float dist_norm,
+                                                          const float* __restrict__ w,     // [64,256]
+                                                          const float* __restrict__ bias,  // [64]
+                                                          __nv_bfloat16* __restrict__ kin,
+                                                          __nv_bfloat16* __restrict__ val, long long dst_bs,
+                                                          int row0) {
+  __shared__ float pe[256];
+  __shared__ float tp[64];
+  const int t = threadIdx.x;
+  {
+    // pe_dim = 128; dim_t[i] = 10000^(2*(i/2)/128); [sin(pos/dim_t) | cos(pos/dim_t)]
+    const int i = t & 127;
+    const float dim_t = powf(10000.f, static_cast<float>(2 * (i / 2)) / 128.f);
+    const float a = dist_norm / dim_t;
+    pe[t] = (t < 128) ? sinf(a) : cosf(a);
+  }
+  __syncthreads();
+  {
+    // 4 threads per output channel
+    const int c = t >> 2, part = t & 3;
+    float acc = 0.f;
+    for (int k = part * 64; k < part * 64 + 64; ++k) acc = fmaf(w[c * 256 + k], pe[k], acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (part == 0) tp[c] = acc + bias[c];
+  }
+  __syncthreads();
+  const int b = blockIdx.x;
+  const float pv = ptr[static_cast<long long>(b) * 256 + t];
+  const long long dst = static_cast<long long>(b) * dst_bs + static_cast<long long>(row0 + t / 64) * 64 + (t % 64);
+  kin[dst] = __float2bfloat16(pv + tp[t % 64]);
+  val[dst] = __float2bfloat16(pv);
+}
+
+// maskmem = bf16(x + (1 - [score > 0]) * no_obj_embed)      (sam2_base.py:733-741, svp:1337)
+__global__ void memenc_finish_kernel(const float* __restrict__ x, const float* __restrict__ score,
+                                     const float* __restrict__ no_obj, __nv_bfloat16* __restrict__ out, int B,
+                                     int T, int C) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n = static_cast<long long>(B) * T * C;
+  if (i >= n) return;
+  const int c = static_cast<int>(i % C);
+  const int b = static_cast<int>(i / (static_cast<long long>(T) * C));
+  const float add = score[b] > 0.f ? 0.f : no_obj[c];
+  out[i] = __float2bfloat16(x[i] + add);
+}
+
+}  // namespace ds2
+
+extern "C" {
+
+int ds2_prompt_tokens(const float* coords, const int32_t* labels, int32_t B, int32_t P, const float* gauss,
+                      const float* point_emb, const float* not_a_point, const float* out_tokens, int32_t n_out,
+                      float image_size, float* tokens, void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(gauss && point_emb && not_a_point && out_tokens && tokens && B > 0 && P >= 0 && n_out > 0, DS2_E_ARG,
+              "ds2_prompt_tokens: bad args");
+  DS2_REQUIRE(P == 0 || (coords && labels), DS2_E_ARG, "ds2_prompt_tokens: P > 0 needs coords and labels");
+  const int nt = n_out + P + 1;
+  prompt_tokens_kernel<<<B * nt, 128, 0, as_stream(stream)>>>(coords, labels, B, P, gauss, point_emb, not_a_point,
+                                                           out_tokens, n_out, image_size, tokens);
+  return post_launch("prompt_tokens_kernel");
+}
+
+int ds2_bank_ptr_pe(const float* ptr, float dist_norm, const float* w, const float* bias, void* kin_bf16,
+                    void* val_bf16, int32_t B, int64_t dst_bs, int32_t row0, void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(ptr && w && bias && kin_bf16 && val_bf16 && B > 0, DS2_E_ARG, "ds2_bank_ptr_pe: bad args");
+  bank_ptr_pe_kernel<<<B, 256, 0, as_stream(stream)>>>(ptr, dist_norm, w, bias,
+                                                     reinterpret_cast<__nv_bfloat16*>(kin_bf16),
+                                                     reinterpret_cast<__nv_bfloat16*>(val_bf16), dst_bs, row0);
+  return post_launch("bank_ptr_pe_kernel");
+}
+
+int ds2_memenc_finish(const float* x, const float* score, const float* no_obj_embed, void* out_bf16, int32_t B,
+                      int32_t T, int32_t C, void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(x && score && no_obj_embed && out_bf16 && B > 0 && T > 0 && C > 0, DS2_E_ARG,
+              "ds2_memenc_finish: bad args");
+  const long long n = static_cast<long long>(B) * T * C;
+  memenc_finish_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+      x, score, no_obj_embed, reinterpret_cast<__nv_bfloat16*>(out_bf16), B, T, C);
+  return post_launch("memenc_finish_kernel");
+}
+
+}  // extern "C"

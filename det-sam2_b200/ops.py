@@ -211,6 +211,22 @@ def bank_ptr(ptr, tpos, kin, val, B, dst_bs, row0):
     _chk(_lib().ds2_bank_ptr(_p(ptr), _p(tpos), _p(kin), _p(val), B, dst_bs, row0, _stream()), "ds2_bank_ptr")
 
 
+def prompt_tokens(coords, labels, B, P, gauss, point_emb, not_a_point, out_tokens, image_size, tokens):
+    _chk(_lib().ds2_prompt_tokens(_p(coords), _p(labels), B, P, _p(gauss), _p(point_emb), _p(not_a_point),
+                                  _p(out_tokens), out_tokens.shape[0], float(image_size), _p(tokens), _stream()),
+         "ds2_prompt_tokens")
+
+
+def bank_ptr_pe(ptr, dist_norm, w, bias, kin, val, B, dst_bs, row0):
+    _chk(_lib().ds2_bank_ptr_pe(_p(ptr), float(dist_norm), _p(w), _p(bias), _p(kin), _p(val), B, dst_bs, row0,
+                                _stream()), "ds2_bank_ptr_pe")
+
+
+def memenc_finish(x, score, no_obj_embed, out, B, T, Cc):
+    _chk(_lib().ds2_memenc_finish(_p(x), _p(score), _p(no_obj_embed), _p(out), B, T, Cc, _stream()),
+         "ds2_memenc_finish")
+
+
 def connected_components(mask_u8):
     """Drop-in for sam2._C.get_connected_componnets: uint8 [N,1,H,W] cuda -> (labels, counts) int32."""
     if not mask_u8.is_cuda or mask_u8.dtype != torch.uint8 or mask_u8.dim() != 4 or mask_u8.shape[1] != 1:

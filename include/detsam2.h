@@ -202,6 +202,22 @@ int ds2_bank_gather(const void* mem_bf16, const float* pos, const float* tpos, v
 int ds2_bank_ptr(const float* ptr, const float* tpos, void* kin_bf16, void* val_bf16, int32_t B,
                  int64_t dst_bs, int32_t row0, void* stream);
 
+/* ---- prompt encoder / token assembly (sam/prompt_encoder.py:73-95,134-171; mask_decoder.py:163-186)
+ * tokens f32 [B, n_out + P + 1, 256] = [out_tokens (obj-score, IoU, mask tokens) ; point embeddings ;
+ * padding point].  coords f32 [B,P,2] in model pixels, labels int32 [B,P] (-1 pad, 0/1 clicks, 2/3 box). */
+int ds2_prompt_tokens(const float* coords, const int32_t* labels, int32_t B, int32_t P,
+                      const float* gauss /*[2,128]*/, const float* point_emb /*[4,256]*/,
+                      const float* not_a_point /*[256]*/, const float* out_tokens /*[n_out,256]*/,
+                      int32_t n_out, float image_size, float* tokens, void* stream);
+/* object-pointer bank tokens with the temporal PE computed in-kernel (sam2_base.py:588-648,
+ * sam2_utils.py:69-79): tpos = W[64,256] . sine1d(dist_norm, 256) + bias                        */
+int ds2_bank_ptr_pe(const float* ptr, float dist_norm, const float* w, const float* bias, void* kin_bf16,
+                    void* val_bf16, int32_t B, int64_t dst_bs, int32_t row0, void* stream);
+/* memory-encoder tail (sam2_base.py:733-741, sam2_video_predictor.py:1337):
+ * out bf16 [B,T,C] = x + (1 - [score_b > 0]) * no_obj_embed                                      */
+int ds2_memenc_finish(const float* x, const float* score, const float* no_obj_embed, void* out_bf16,
+                      int32_t B, int32_t T, int32_t C, void* stream);
+
 /* ---- post-processing --------------------------------------------------------------------------
  * drop-in for sam2._C.get_connected_componnets (csrc/connected_components.cu:213-282):
  * 8-connected components of a uint8 [N,1,H,W] mask; labels/counts int32 [N,1,H,W].              */

@@ -594,7 +594,7 @@ class OracleEngine:
         o = forward_sam_heads(self.sd, self.cfg, pix_feat, point_coords, point_labels, mask_inputs, hr,
                               multimask_output)
         return {"pred_masks": o["low_res_masks"], "ious": o["ious"], "obj_ptr": o["obj_ptr"],
-                "object_score_logits": o["object_score_logits"]}
+                "object_score_logits": o["object_score_logits"], "_multimasks": o["low_res_multimasks"]}
 
     def mask_as_output(self, feats, mask_inputs):
         B = mask_inputs.shape[0]
