@@ -88,6 +88,8 @@ class CudaEngine:
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self._ws = {}
+        # bench.py sets this to a list to collect (tag, start_event, end_event, meta) of the dominant kernel
+        self.kernel_timers = None
         self._pack(state_dict)
 
     # ---------------------------------------------------------------------------------------------
@@ -438,7 +440,14 @@ class CudaEngine:
             ops.gemm(t16, p[w + "ca_q.w"], bias=p[w + "ca_q.b"], out_bf16=q16.view(B * T, D), rope=(rope, 0, D, T, T))
             ops.gemm(kin.view(B * N, M), p[w + "ca_k.w"], bias=p[w + "ca_k.b"], out_bf16=k16.view(B * N, D),
                      rope=(rope, 0, D, N, N - n_ptr_tok))
-            ops.flash_attn(q16, k16, val, o64, scale)
+            if self.kernel_timers is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                ops.flash_attn(q16, k16, val, o64, scale)
+                ev1.record()
+                self.kernel_timers.append(("flash_cross", ev0, ev1, {"N": N, "B": B}))
+            else:
+                ops.flash_attn(q16, k16, val, o64, scale)
             ops.gemm(o64.view(B * T, M), p[w + "ca_ov.w"], bias=p[w + "ca_ov.b"], residual=x2, out_f32=x2)
             ops.layernorm(x2, p[w + "n3.w"], p[w + "n3.b"], 1e-5, out_bf16=t16)
             ops.gemm(t16, p[w + "ff1.w"], bias=p[w + "ff1.b"], act=1, out_bf16=hff)
