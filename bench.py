@@ -170,11 +170,16 @@ def run_ours(args):
         l0 = ops.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        prof = args.cuda_profiler and mode == "device"
+        if prof:
+            torch.cuda.profiler.start()  # ncu --profile-from-start off: only the timed device steps
         e0.record()
         for _ in range(K):
             step()
         e1.record()
         barrier()
+        if prof:
+            torch.cuda.profiler.stop()
         ms = e0.elapsed_time(e1)
         if mode == "device":
             clocks = sampler.stop()
@@ -333,6 +338,7 @@ def main():
     ap.add_argument("--objects", type=int, default=16)
     ap.add_argument("--prefill", type=int, default=16, help="tracked frames before warm-up so the bank is at steady state")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-profiler", action="store_true", help="bracket the timed device steps with cudaProfilerStart/Stop")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--cpu-budget-ref", type=float, default=150.0)
     args = ap.parse_args()

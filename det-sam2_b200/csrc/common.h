@@ -37,6 +37,9 @@ inline int post_launch(const char* what) {
 // dims/strides innermost first; strides in BYTES for dims 1.. (dim 0 is contiguous).
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box);
+// General form: elt_bytes 2 (bf16) or 4 (f32); swizzle_bytes 64 or 128 (inner box bytes <= swizzle).
+int make_tmap(CUtensorMap* out, const void* base, int elt_bytes, int swizzle_bytes, int rank,
+              const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
 
 int sm_count();
 

@@ -2,15 +2,21 @@
 //
 //   out[M,N] = epilogue( A[M,K] · W[N,K]^T )         A, W bf16 K-major; f32 accumulate in TMEM
 //
-// CTA = 256 threads, one CTA per SM, static round-robin over 128 x BN output tiles.
-//   warp 0      : TMA producer   (cp.async.bulk.tensor 2-D, 128B swizzle, 4-stage ring)
-//   warp 1      : MMA issuer     (tcgen05.mma cta_group::1, M=128, N=BN, K=16 per instruction)
-//   warp 2      : TMEM allocator (512 columns = 2 accumulator stages of <=256 columns)
-//   warps 4..7  : epilogue       (tcgen05.ld 32x32b -> bias/act/gamma/rotary/residual -> global)
+// CTA = 384 threads, one CTA per SM, static round-robin over 128 x BN output tiles.
+//   warp 0       : TMA producer   (cp.async.bulk.tensor 2-D, 128B swizzle, 4-stage ring)
+//   warp 1       : MMA issuer     (tcgen05.mma cta_group::1, M=128, N=BN, K=16 per instruction)
+//   warp 2       : TMEM allocator (512 columns = 2 accumulator stages of <=256 columns)
+//   warps 4..11  : epilogue, two warps per TMEM lane quarter, alternating 32-column chunks:
+//                  tcgen05.ld 32x32b -> bias / act / gamma / rotary in registers (thread = row) ->
+//                  swizzled shared staging -> TMA store (cp.async.bulk.tensor, fully coalesced) or,
+//                  for the in-place residual add x += f(x), TMA reduce-add (cp.reduce.async.bulk .add
+//                  f32 executed at L2), so no SM ever reads the residual.  Row-per-thread global
+//                  stores are kept only as the fallback for odd cases (two outputs, row-periodic
+//                  residual tables, unaligned pitches).
 // The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of
-// tile i+1.  BN is a run-time multiple of 16 (<=256) chosen so that it divides N where possible
-// (Hiera widths 144/288/576/1152 are not powers of two).
+// tile i+1.  BN is chosen per problem to minimise waves x tile width.
 #include <math.h>
+#include <string.h>
 
 #include "common.h"
 #include "tc05.cuh"
@@ -23,12 +29,17 @@ constexpr int kStages = 4;
 constexpr int kABytes = kBM * kBK * 2;        // 16 KB
 constexpr int kBBytesMax = 256 * kBK * 2;     // 32 KB
 constexpr int kStageBytes = kABytes + kBBytesMax;
-constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int kGemmThreads = 256;
+constexpr int kEpiWarps = 8;
+constexpr int kStagingBytes = 4096;           // 32 rows x 128 B per epilogue warp
+constexpr int kGemmSmem = kStages * kStageBytes + kEpiWarps * kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kGemmThreads = 128 + 32 * kEpiWarps;
+
+enum StoreMode { kStoreDirect = 0, kStoreTmaF32 = 1, kStoreTmaAddF32 = 2, kStoreTmaBf16 = 3 };
 
 struct GemmParams {
   int M, N, K, BN;
   int tiles_m, tiles_n;
+  int store_mode;
   const float* bias;
   const float* gamma;
   const float* residual;
@@ -42,15 +53,27 @@ struct GemmParams {
   int rope_col0, rope_col1, rope_period, rope_rows_per_batch, rope_row_limit;
 };
 
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7) on the MUFU fast paths (rcp.approx, ex2.approx):
+// ~14 issue slots per element instead of ~50 for libdevice erff — the GELU epilogues of the Hiera MLPs
+// were epilogue-bound on it.  Total error ~1e-6 absolute, far below the bf16 store rounding.
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);
+  const float hx = 0.5f * x;
+  return fmaf(copysignf(erf_abs, x), hx, hx);
 }
 
-// Epilogue for NC (16 or 32) consecutive columns of one row held in registers.
+// bias / activation / gamma / rotary on NC consecutive columns of one row (registers).
 template <int NC>
-__device__ __forceinline__ void epilogue_cols(const GemmParams& p, const uint32_t* acc, int row,
-                                              int col0) {
-  float v[NC];
+__device__ __forceinline__ void epilogue_math(const GemmParams& p, const uint32_t* acc, int row, int col0,
+                                              float (&v)[NC]) {
 #pragma unroll
   for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(acc[i]);
   const bool full = (col0 + NC <= p.N);
@@ -86,6 +109,12 @@ __device__ __forceinline__ void epilogue_cols(const GemmParams& p, const uint32_
       }
     }
   }
+}
+
+// Fallback store: residual add + row-per-thread global stores.
+template <int NC>
+__device__ __forceinline__ void epilogue_store_direct(const GemmParams& p, float (&v)[NC], int row, int col0) {
+  const bool full = (col0 + NC <= p.N);
   if (p.residual) {
     const long long rr = p.res_row_mod > 0 ? (row % p.res_row_mod) : row;
     const float* r = p.residual + rr * p.ldr + col0;
@@ -136,12 +165,18 @@ __device__ __forceinline__ void epilogue_cols(const GemmParams& p, const uint32_
   }
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                         const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
+                         const __grid_constant__ CUtensorMap tmap_w,
+                         const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  const uint32_t staging_base = smem_base + kStages * kStageBytes;
+  const uint32_t bar_base = staging_base + kEpiWarps * kStagingBytes;
   // barrier layout: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -155,6 +190,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_a);
     tc::prefetch_tmap(&tmap_w);
+    if (p.store_mode != kStoreDirect) tc::prefetch_tmap(&tmap_c);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -163,7 +199,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(tfull_bar(s), 1);
-      tc::mbar_init(tempty_bar(s), 4);
+      tc::mbar_init(tempty_bar(s), kEpiWarps);
     }
     tc::fence_barrier_init();
   }
@@ -235,28 +271,80 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp >= 4) {
     // ---------------- epilogue ----------------
-    const int ew = warp - 4;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    const int ew = warp - 4;       // 0..7
+    const int lq = warp & 3;       // TMEM lane quarter this warp may touch: lanes [32*lq, 32*lq+32)
+    const int half = ew >> 2;      // which alternate 32-column chunks this warp takes
+    const uint32_t stg = staging_base + static_cast<uint32_t>(ew) * kStagingBytes;
+    const int mode = p.store_mode;
     int acc = 0;
     uint32_t acc_phase = 0;
+    bool pending = false;  // lane 0: a bulk store may still be reading the staging buffer
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = t / p.tiles_n, n_blk = t % p.tiles_n;
       tc::mbar_wait(tfull_bar(acc), acc_phase);
       tc::tc_fence_after();
-      const int row = m_blk * kBM + ew * 32 + lane;
+      const int row0 = m_blk * kBM + lq * 32;
+      const int row = row0 + lane;
       const uint32_t t_addr =
-          tmem_base + static_cast<uint32_t>(acc) * 256u + (static_cast<uint32_t>(ew * 32) << 16);
+          tmem_base + static_cast<uint32_t>(acc) * 256u + (static_cast<uint32_t>(lq * 32) << 16);
       const int n0 = n_blk * p.BN;
-      for (int c = 0; c < p.BN; c += 32) {
-        if (p.BN - c >= 32) {
-          uint32_t r[32];
+      for (int c = half * 32; c < p.BN; c += 64) {
+        const bool wide = (p.BN - c) >= 32;
+        uint32_t r[32];
+        if (wide) {
           tc::tmem_ld32(t_addr + c, r);
-          tc::tmem_ld_wait();
-          if (row < p.M && n0 + c < p.N) epilogue_cols<32>(p, r, row, n0 + c);
         } else {
-          uint32_t r[16];
-          tc::tmem_ld16(t_addr + c, r);
-          tc::tmem_ld_wait();
-          if (row < p.M && n0 + c < p.N) epilogue_cols<16>(p, r, row, n0 + c);
+          uint32_t r16[16];
+          tc::tmem_ld16(t_addr + c, r16);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            r[i] = r16[i];
+            r[16 + i] = 0u;
+          }
+        }
+        tc::tmem_ld_wait();
+        if (n0 + c >= p.N) continue;          // warp-uniform
+        if (mode == kStoreDirect) {
+          if (row < p.M) {
+            float v[32];
+            epilogue_math<32>(p, r, row, n0 + c, v);
+            epilogue_store_direct<32>(p, v, row, n0 + c);
+          }
+          continue;
+        }
+        float v[32];
+        epilogue_math<32>(p, r, row < p.M ? row : 0, n0 + c, v);
+        // the previous bulk store must have finished READING the staging buffer
+        if (pending) {
+          tc::bulk_wait_read0();
+          pending = false;
+        }
+        __syncwarp();
+        if (mode == kStoreTmaBf16) {
+          // 32 rows x 64 B, SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
+          const uint32_t rowaddr = stg + static_cast<uint32_t>(lane) * 64u;
+          const uint32_t sw = (static_cast<uint32_t>(lane) >> 1) & 3u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            st_shared_v4(rowaddr + ((static_cast<uint32_t>(j) ^ sw) << 4), tc::pack_bf16(v[8 * j], v[8 * j + 1]),
+                         tc::pack_bf16(v[8 * j + 2], v[8 * j + 3]), tc::pack_bf16(v[8 * j + 4], v[8 * j + 5]),
+                         tc::pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+        } else {
+          // 32 rows x 128 B, SWIZZLE_128B: chunk j of row r lives at chunk j ^ (r & 7)
+          const uint32_t rowaddr = stg + static_cast<uint32_t>(lane) * 128u;
+          const uint32_t sw = static_cast<uint32_t>(lane) & 7u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(rowaddr + ((static_cast<uint32_t>(j) ^ sw) << 4), __float_as_uint(v[4 * j]),
+                         __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+        }
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (mode == kStoreTmaAddF32) tc::tma_reduce_add_2d(&tmap_c, stg, n0 + c, row0);
+          else tc::tma_store_2d(&tmap_c, stg, n0 + c, row0);
+          tc::bulk_commit();
+          pending = true;
         }
       }
       tc::tc_fence_before();
@@ -267,6 +355,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         acc_phase ^= 1;
       }
     }
+    if (pending) tc::bulk_wait0();  // global writes complete before the CTA retires
   }
 
   tc::tc_fence_before();
@@ -336,16 +425,23 @@ __global__ void gemm_bf16_simt_kernel(const __nv_bfloat16* __restrict__ A, long 
   }
 }
 
-static int choose_bn(int N) {
-  if (N % 16 == 0) {
-    for (int bn = 256; bn >= 96; bn -= 16)
-      if (N % bn == 0) return bn;
-    if (N <= 256) return N;
+// Tile width: one n-tile when N <= 256 (any multiple of 16); otherwise the multiple of 32 that
+// minimises (waves x tile width), i.e. the tensor-pipe time of the slowest SM.
+static int choose_bn(int M, int N, int sms) {
+  if (N <= 256) return ((N + 15) / 16) * 16;
+  const int tiles_m = (M + kBM - 1) / kBM;
+  int best = 256;
+  long long best_cost = -1;
+  for (int bn = 256; bn >= 64; bn -= 32) {
+    const long long tiles = static_cast<long long>(tiles_m) * ((N + bn - 1) / bn);
+    const long long waves = (tiles + sms - 1) / sms;
+    const long long cost = waves * (bn + 24);  // +24: per-tile fixed cost (barriers, accumulator hand-over)
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
   }
-  if (N <= 16) return 16;
-  if (N <= 32) return 32;
-  if (N <= 64) return 64;
-  return 128;
+  return best;
 }
 
 }  // namespace ds2
@@ -398,11 +494,39 @@ extern "C" int ds2_gemm(const ds2_gemm_args* a, void* stream) {
   DS2_REQUIRE((a->lda % 8) == 0 && (a->ldw % 8) == 0, DS2_E_ALIGN,
               "ds2_gemm: lda/ldw must be multiples of 8 elements (got %lld, %lld)",
               static_cast<long long>(a->lda), static_cast<long long>(a->ldw));
-  p.BN = choose_bn(a->N);
+  const int sms = sm_count();
+  DS2_REQUIRE(sms > 0, DS2_E_NODEVICE, "ds2_gemm: no CUDA device");
+  p.BN = choose_bn(a->M, a->N, sms);
   p.tiles_m = (a->M + kBM - 1) / kBM;
   p.tiles_n = (a->N + p.BN - 1) / p.BN;
+  // epilogue store path
+  p.store_mode = kStoreDirect;
+  const bool one_out = (a->out_f32 != nullptr) != (a->out_bf16 != nullptr);
+  if (one_out && a->impl != 2) {
+    if (a->out_bf16 && !a->residual && (a->ldc_bf16 % 8) == 0 &&
+        (reinterpret_cast<uintptr_t>(a->out_bf16) & 15) == 0) {
+      p.store_mode = kStoreTmaBf16;
+    } else if (a->out_f32 && (a->ldc % 4) == 0 && (reinterpret_cast<uintptr_t>(a->out_f32) & 15) == 0) {
+      if (!a->residual) p.store_mode = kStoreTmaF32;
+      else if (a->residual == a->out_f32 && a->ldr == a->ldc && a->res_row_mod == 0) p.store_mode = kStoreTmaAddF32;
+    }
+  }
 
-  CUtensorMap ta, tw;
+  CUtensorMap ta, tw, tcm;
+  memset(&tcm, 0, sizeof(tcm));
+  if (p.store_mode == kStoreTmaBf16) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->M)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(a->ldc_bf16) * 2};
+    const uint32_t box[2] = {32, 32};
+    int rc = make_tmap(&tcm, a->out_bf16, 2, 64, 2, dims, strides, box);
+    if (rc) return rc;
+  } else if (p.store_mode == kStoreTmaF32 || p.store_mode == kStoreTmaAddF32) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->M)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(a->ldc) * 4};
+    const uint32_t box[2] = {32, 32};
+    int rc = make_tmap(&tcm, a->out_f32, 4, 128, 2, dims, strides, box);
+    if (rc) return rc;
+  }
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->M)};
     const uint64_t strides[1] = {static_cast<uint64_t>(a->lda) * 2};
@@ -425,10 +549,8 @@ extern "C" int ds2_gemm(const ds2_gemm_args* a, void* stream) {
                 cudaGetErrorString(e));
     attr_set = true;
   }
-  const int sms = sm_count();
-  DS2_REQUIRE(sms > 0, DS2_E_NODEVICE, "ds2_gemm: no CUDA device");
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < sms ? tiles : sms;
-  gemm_bf16_tcgen05_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(ta, tw, p);
+  gemm_bf16_tcgen05_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(ta, tw, tcm, p);
   return post_launch("gemm_bf16_tcgen05_kernel");
 }

@@ -38,15 +38,33 @@ __device__ __forceinline__ bool is_fg(const uint8_t* m8, const float* sc, long l
   return m8 ? (m8[i] != 0) : (sc[i] <= 0.f);
 }
 
+// Initial parent = left end of the pixel's horizontal run *inside its warp's 32-pixel segment*
+// (ballot + clz), so the long horizontal chains of big components never go through union-find.
 __global__ void cc_init_kernel(const uint8_t* __restrict__ m8, const float* __restrict__ sc, int* __restrict__ parent,
-                               int* __restrict__ area, int* __restrict__ minblk, long long total, int HW) {
+                               int* __restrict__ area, int* __restrict__ minblk, long long total, int HW, int W) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  parent[i] = is_fg(m8, sc, i) ? static_cast<int>(i % HW) : -1;
+  const int lane = threadIdx.x & 31;
+  const bool valid = i < total;
+  const bool fg = valid && is_fg(m8, sc, i);
+  const int p = valid ? static_cast<int>(i % HW) : 0;
+  const int x = p % W;
+  const unsigned fgmask = __ballot_sync(0xffffffffu, fg);
+  // linked to the left neighbour: both foreground, same row, same warp segment
+  const bool link = fg && lane > 0 && x > 0 && ((fgmask >> (lane - 1)) & 1u);
+  const unsigned startmask = ~__ballot_sync(0xffffffffu, link);  // bit set = lane starts a run
+  if (!valid) return;
+  const unsigned below = startmask & (0xffffffffu >> (31 - lane));  // starts at lanes <= lane (lane 0 always set)
+  const int start_lane = 31 - __clz(below);
+  parent[i] = fg ? p - (lane - start_lane) : -1;
   area[i] = 0;
   if (minblk) minblk[i] = INT_MAX;
 }
 
+// Unions only where a link is not already implied by a neighbour's link (8-connectivity):
+//   * lane-0 pixels re-join runs split at warp-segment boundaries;
+//   * a pixel whose left neighbour is foreground inherits that neighbour's links to the row above,
+//     except the up-right one when the pixel directly above is background;
+//   * otherwise: up if foreground, else up-left and up-right individually.
 __global__ void cc_merge_kernel(int* __restrict__ parent, long long total, int H, int W) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -55,27 +73,42 @@ __global__ void cc_merge_kernel(int* __restrict__ parent, long long total, int H
   int* par = parent + (i - p);
   if (par[p] < 0) return;
   const int y = p / W, x = p % W;
-  if (x > 0 && par[p - 1] >= 0) uf_union(par, p, p - 1);
-  if (y > 0) {
-    if (par[p - W] >= 0) uf_union(par, p, p - W);
-    if (x > 0 && par[p - W - 1] >= 0) uf_union(par, p, p - W - 1);
-    if (x + 1 < W && par[p - W + 1] >= 0) uf_union(par, p, p - W + 1);
+  const bool left = x > 0 && par[p - 1] >= 0;
+  if (left && (threadIdx.x & 31) == 0) uf_union(par, p, p - 1);
+  if (y == 0) return;
+  const bool up = par[p - W] >= 0;
+  const bool upr = x + 1 < W && par[p - W + 1] >= 0;
+  if (left) {
+    if (upr && !up) uf_union(par, p, p - W + 1);
+    return;
   }
+  if (up) {
+    uf_union(par, p, p - W);
+    return;
+  }
+  if (x > 0 && par[p - W - 1] >= 0) uf_union(par, p, p - W - 1);
+  if (upr) uf_union(par, p, p - W + 1);
 }
 
 __global__ void cc_count_kernel(const int* __restrict__ parent, int* __restrict__ area, int* __restrict__ minblk,
                                 long long total, int H, int W) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
   const int HW = H * W;
-  const int p = static_cast<int>(i % HW);
+  const bool valid = i < total;
+  const int p = valid ? static_cast<int>(i % HW) : 0;
   const long long base = i - p;
-  if (parent[i] < 0) return;
+  const bool fg = valid && parent[i] >= 0;
+  const unsigned active = __ballot_sync(0xffffffffu, fg);
+  if (!fg) return;
   const int root = uf_find(parent + base, p);
-  atomicAdd(area + base + root, 1);
+  // warp-aggregated atomics: lanes sharing (image, root) elect one leader — a big component would
+  // otherwise serialise tens of thousands of atomics on a single address
+  const long long key = base + root;
+  const unsigned peers = __match_any_sync(active, key);
+  if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(area + key, __popc(peers));
   if (minblk) {
     const int y = p / W, x = p % W;
-    atomicMin(minblk + base + root, (y & ~1) * W + (x & ~1));
+    atomicMin(minblk + key, (y & ~1) * W + (x & ~1));
   }
 }
 
@@ -157,7 +190,7 @@ int ds2_connected_components(const uint8_t* mask, int32_t* labels, int32_t* coun
   int* parent = tmp;
   int* minblk = tmp + total;
   const int HW = H * W;
-  cc_init_kernel<<<nblocks(total, 256), 256, 0, st>>>(mask, nullptr, parent, counts, minblk, total, HW);
+  cc_init_kernel<<<nblocks(total, 256), 256, 0, st>>>(mask, nullptr, parent, counts, minblk, total, HW, W);
   int rc = post_launch("cc_init_kernel");
   if (!rc) {
     cc_merge_kernel<<<nblocks(total, 256), 256, 0, st>>>(parent, total, H, W);
@@ -183,7 +216,7 @@ int ds2_fill_holes(float* scores, int32_t* labels_ws, int32_t* counts_ws, int32_
   cudaStream_t st = as_stream(stream);
   const long long total = static_cast<long long>(N) * H * W;
   const int HW = H * W;
-  cc_init_kernel<<<nblocks(total, 256), 256, 0, st>>>(nullptr, scores, labels_ws, counts_ws, nullptr, total, HW);
+  cc_init_kernel<<<nblocks(total, 256), 256, 0, st>>>(nullptr, scores, labels_ws, counts_ws, nullptr, total, HW, W);
   int rc = post_launch("cc_init_kernel");
   if (rc) return rc;
   cc_merge_kernel<<<nblocks(total, 256), 256, 0, st>>>(labels_ws, total, H, W);

@@ -57,7 +57,15 @@ static std::mutex g_tmap_mu;
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tmap(out, base, 2, 128, rank, dims, strides_bytes, box);
+}
+
+int make_tmap(CUtensorMap* out, const void* base, int elt_bytes, int swizzle_bytes, int rank,
+              const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
   EncodeTiledFn enc = get_encode();
+  DS2_REQUIRE(elt_bytes == 2 || elt_bytes == 4, DS2_E_ARG, "tensor map element size %d unsupported", elt_bytes);
+  DS2_REQUIRE(swizzle_bytes == 64 || swizzle_bytes == 128, DS2_E_ARG, "tensor map swizzle %d unsupported",
+              swizzle_bytes);
   DS2_REQUIRE(enc != nullptr, DS2_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
   DS2_REQUIRE(rank >= 2 && rank <= 3, DS2_E_ARG, "tensor map rank %d unsupported", rank);
   DS2_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, DS2_E_ALIGN,
@@ -65,7 +73,8 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   TmapKey key;
   memset(&key, 0, sizeof(key));
   key.v[0] = reinterpret_cast<uint64_t>(base);
-  key.v[1] = static_cast<uint64_t>(rank);
+  key.v[1] = static_cast<uint64_t>(rank) | (static_cast<uint64_t>(elt_bytes) << 8) |
+             (static_cast<uint64_t>(swizzle_bytes) << 16);
   for (int i = 0; i < rank; ++i) {
     key.v[2 + i] = dims[i];
     key.v[5 + i] = box[i];
@@ -94,10 +103,11 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
   CUtensorMap m;
-  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
-                   const_cast<void*>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(&m, elt_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                   static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, bx, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DS2_REQUIRE(r == CUDA_SUCCESS, DS2_E_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d",
               static_cast<int>(r));
   {

@@ -40,6 +40,46 @@ def test_gemm_plain(ops, M, N, K):
     assert (ob.float() - ref).abs().max().item() < 4e-2
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 144, 160), (4096, 432, 144), (1000, 1152, 576),
+                                   (4096, 32, 256), (333, 64, 2048), (65536, 256, 64), (300, 16, 64)])
+@pytest.mark.parametrize("mode", ["f32", "bf16", "inplace", "direct"])
+def test_gemm_store_paths(ops, M, N, K, mode):
+    """TMA-store epilogues (f32, bf16, in-place reduce-add) against the row-per-thread fallback and torch."""
+    torch.manual_seed(11)
+    a = bf(torch.randn(M, K, device=DEV))
+    w = bf(torch.randn(N, K, device=DEV) / math.sqrt(K))
+    b = torch.randn(N, device=DEV)
+    ref = a.float() @ w.float().t() + b
+    if mode == "f32":
+        o = torch.full((M, N), float("nan"), device=DEV)
+        ops.gemm(a, w, bias=b, out_f32=o)
+        assert (o - ref).abs().max().item() < 1e-3
+    elif mode == "bf16":
+        o = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+        ops.gemm(a, w, bias=b, act=2, out_bf16=o)
+        assert (o.float() - F.gelu(ref)).abs().max().item() < 4e-2
+    elif mode == "inplace":
+        x = torch.randn(M, N, device=DEV)
+        x0 = x.clone()
+        ops.gemm(a, w, bias=b, residual=x, out_f32=x)
+        assert (x - (x0 + ref)).abs().max().item() < 1e-3
+    else:
+        o = torch.full((M, N), float("nan"), device=DEV)
+        ops.gemm(a, w, bias=b, out_f32=o, impl=2)
+        assert (o - ref).abs().max().item() < 1e-3
+
+
+def test_gemm_bf16_store_into_column_slice(ops):
+    torch.manual_seed(12)
+    a = bf(torch.randn(500, 256, device=DEV))
+    w = bf(torch.randn(512, 256, device=DEV) / 16)
+    buf = torch.zeros(500, 768, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, w, out_bf16=buf[:, :512])
+    ref = a.float() @ w.float().t()
+    assert (buf[:, :512].float() - ref).abs().max().item() < 4e-2
+    assert buf[:, 512:].abs().max().item() == 0
+
+
 def test_gemm_epilogue_all(ops):
     torch.manual_seed(2)
     M, N, K = 1024, 256, 256
