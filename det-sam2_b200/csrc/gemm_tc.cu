@@ -78,9 +78,20 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, const uint32_
   for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(acc[i]);
   const bool full = (col0 + NC <= p.N);
   if (p.bias) {
+    if (full && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
 #pragma unroll
-    for (int i = 0; i < NC; ++i)
-      if (full || col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
+      for (int i = 0; i < NC / 4; ++i) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);
+        v[4 * i] += t.x;
+        v[4 * i + 1] += t.y;
+        v[4 * i + 2] += t.z;
+        v[4 * i + 3] += t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+        if (col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
+    }
   }
   if (p.act == 1) {
 #pragma unroll
@@ -288,12 +299,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t t_addr =
           tmem_base + static_cast<uint32_t>(acc) * 256u + (static_cast<uint32_t>(lq * 32) << 16);
       const int n0 = n_blk * p.BN;
-      for (int c = half * 32; c < p.BN; c += 64) {
-        const bool wide = (p.BN - c) >= 32;
-        uint32_t r[32];
-        if (wide) {
+      // loads 32 (or a 16-wide tail, or no) accumulator columns starting at column c of the tile
+      auto load_cols = [&](int c, uint32_t(&r)[32]) {
+        const int left = p.BN - c;
+        if (left >= 32) {
           tc::tmem_ld32(t_addr + c, r);
-        } else {
+        } else if (left >= 16) {
           uint32_t r16[16];
           tc::tmem_ld16(t_addr + c, r16);
 #pragma unroll
@@ -301,43 +312,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             r[i] = r16[i];
             r[16 + i] = 0u;
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = 0u;
         }
-        tc::tmem_ld_wait();
-        if (n0 + c >= p.N) continue;          // warp-uniform
-        if (mode == kStoreDirect) {
-          if (row < p.M) {
-            float v[32];
-            epilogue_math<32>(p, r, row, n0 + c, v);
-            epilogue_store_direct<32>(p, v, row, n0 + c);
-          }
-          continue;
-        }
-        float v[32];
-        epilogue_math<32>(p, r, row < p.M ? row : 0, n0 + c, v);
+      };
+      auto wait_staging = [&]() {
         // the previous bulk store must have finished READING the staging buffer
         if (pending) {
           tc::bulk_wait_read0();
           pending = false;
         }
         __syncwarp();
-        if (mode == kStoreTmaBf16) {
-          // 32 rows x 64 B, SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
-          const uint32_t rowaddr = stg + static_cast<uint32_t>(lane) * 64u;
-          const uint32_t sw = (static_cast<uint32_t>(lane) >> 1) & 3u;
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            st_shared_v4(rowaddr + ((static_cast<uint32_t>(j) ^ sw) << 4), tc::pack_bf16(v[8 * j], v[8 * j + 1]),
-                         tc::pack_bf16(v[8 * j + 2], v[8 * j + 3]), tc::pack_bf16(v[8 * j + 4], v[8 * j + 5]),
-                         tc::pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-        } else {
-          // 32 rows x 128 B, SWIZZLE_128B: chunk j of row r lives at chunk j ^ (r & 7)
-          const uint32_t rowaddr = stg + static_cast<uint32_t>(lane) * 128u;
-          const uint32_t sw = static_cast<uint32_t>(lane) & 7u;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            st_shared_v4(rowaddr + ((static_cast<uint32_t>(j) ^ sw) << 4), __float_as_uint(v[4 * j]),
-                         __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
-        }
+      };
+      auto issue_store = [&](int c) {
         tc::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -345,6 +333,68 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           else tc::tma_store_2d(&tmap_c, stg, n0 + c, row0);
           tc::bulk_commit();
           pending = true;
+        }
+      };
+      const int mrow = row < p.M ? row : 0;
+      if (mode == kStoreTmaBf16) {
+        // 64-column chunks: 32 rows x 128 B staging, SWIZZLE_128B (16-byte chunk j of row r at j ^ (r & 7)),
+        // one TMA store of a full 128-byte line per row
+        for (int c = half * 64; c < p.BN; c += 128) {
+          uint32_t r0[32], r1[32];
+          load_cols(c, r0);
+          load_cols(c + 32, r1);
+          tc::tmem_ld_wait();
+          if (n0 + c >= p.N) continue;  // warp-uniform
+          uint32_t pk[32];
+          {
+            float v[32];
+            epilogue_math<32>(p, r0, mrow, n0 + c, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = tc::pack_bf16(v[2 * i], v[2 * i + 1]);
+          }
+          if (n0 + c + 32 < p.N && c + 32 < p.BN) {
+            float v[32];
+            epilogue_math<32>(p, r1, mrow, n0 + c + 32, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[16 + i] = tc::pack_bf16(v[2 * i], v[2 * i + 1]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[16 + i] = 0u;
+          }
+          wait_staging();
+          const uint32_t rowaddr = stg + static_cast<uint32_t>(lane) * 128u;
+          const uint32_t sw = static_cast<uint32_t>(lane) & 7u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(rowaddr + ((static_cast<uint32_t>(j) ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2],
+                         pk[4 * j + 3]);
+          issue_store(c);
+        }
+      } else {
+        for (int c = half * 32; c < p.BN; c += 64) {
+          uint32_t r[32];
+          load_cols(c, r);
+          tc::tmem_ld_wait();
+          if (n0 + c >= p.N) continue;  // warp-uniform
+          if (mode == kStoreDirect) {
+            if (row < p.M) {
+              float v[32];
+              epilogue_math<32>(p, r, row, n0 + c, v);
+              epilogue_store_direct<32>(p, v, row, n0 + c);
+            }
+            continue;
+          }
+          float v[32];
+          epilogue_math<32>(p, r, mrow, n0 + c, v);
+          wait_staging();
+          // 32 rows x 128 B, SWIZZLE_128B
+          const uint32_t rowaddr = stg + static_cast<uint32_t>(lane) * 128u;
+          const uint32_t sw = static_cast<uint32_t>(lane) & 7u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(rowaddr + ((static_cast<uint32_t>(j) ^ sw) << 4), __float_as_uint(v[4 * j]),
+                         __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+          issue_store(c);
         }
       }
       tc::tc_fence_before();
@@ -427,12 +477,12 @@ __global__ void gemm_bf16_simt_kernel(const __nv_bfloat16* __restrict__ A, long 
 
 // Tile width: one n-tile when N <= 256 (any multiple of 16); otherwise the multiple of 32 that
 // minimises (waves x tile width), i.e. the tensor-pipe time of the slowest SM.
-static int choose_bn(int M, int N, int sms) {
+static int choose_bn(int M, int N, int sms, int step) {
   if (N <= 256) return ((N + 15) / 16) * 16;
   const int tiles_m = (M + kBM - 1) / kBM;
   int best = 256;
   long long best_cost = -1;
-  for (int bn = 256; bn >= 64; bn -= 32) {
+  for (int bn = 256; bn >= 64; bn -= step) {
     const long long tiles = static_cast<long long>(tiles_m) * ((N + bn - 1) / bn);
     const long long waves = (tiles + sms - 1) / sms;
     const long long cost = waves * (bn + 24);  // +24: per-tile fixed cost (barriers, accumulator hand-over)
@@ -496,9 +546,6 @@ extern "C" int ds2_gemm(const ds2_gemm_args* a, void* stream) {
               static_cast<long long>(a->lda), static_cast<long long>(a->ldw));
   const int sms = sm_count();
   DS2_REQUIRE(sms > 0, DS2_E_NODEVICE, "ds2_gemm: no CUDA device");
-  p.BN = choose_bn(a->M, a->N, sms);
-  p.tiles_m = (a->M + kBM - 1) / kBM;
-  p.tiles_n = (a->N + p.BN - 1) / p.BN;
   // epilogue store path
   p.store_mode = kStoreDirect;
   const bool one_out = (a->out_f32 != nullptr) != (a->out_bf16 != nullptr);
@@ -512,13 +559,17 @@ extern "C" int ds2_gemm(const ds2_gemm_args* a, void* stream) {
     }
   }
 
+  // bf16 stores go out in 64-column boxes, so tiles must not end inside one
+  p.BN = choose_bn(a->M, a->N, sms, p.store_mode == kStoreTmaBf16 ? 64 : 32);
+  p.tiles_m = (a->M + kBM - 1) / kBM;
+  p.tiles_n = (a->N + p.BN - 1) / p.BN;
   CUtensorMap ta, tw, tcm;
   memset(&tcm, 0, sizeof(tcm));
   if (p.store_mode == kStoreTmaBf16) {
     const uint64_t dims[2] = {static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->M)};
     const uint64_t strides[1] = {static_cast<uint64_t>(a->ldc_bf16) * 2};
-    const uint32_t box[2] = {32, 32};
-    int rc = make_tmap(&tcm, a->out_bf16, 2, 64, 2, dims, strides, box);
+    const uint32_t box[2] = {64, 32};
+    int rc = make_tmap(&tcm, a->out_bf16, 2, 128, 2, dims, strides, box);
     if (rc) return rc;
   } else if (p.store_mode == kStoreTmaF32 || p.store_mode == kStoreTmaAddF32) {
     const uint64_t dims[2] = {static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->M)};

@@ -62,14 +62,29 @@ struct SeqGeom {
   int Lq, Lk;
 };
 
-template <int DP>
-__global__ void __launch_bounds__(128) mha_kernel(const MhaParams p) {
-  constexpr int QS = DP + 8;   // smem row stride (elements) for Q / K tiles
-  constexpr int VS = 64 + 8;   // smem row stride for V^T
+// 16-byte asynchronous global->shared copy; src_bytes == 0 zero-fills the destination.
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                   static_cast<uint32_t>(__cvta_generic_to_shared(dst))),
+               "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// NW warps = 16*NW query rows per CTA; K/V chunks of 64 keys are double-buffered with cp.async so the
+// loads of chunk j+1 overlap the MMAs of chunk j.
+template <int DP, int NW>
+__global__ void __launch_bounds__(32 * NW) mha_kernel(const MhaParams p) {
+  constexpr int QS = DP + 8;   // smem row stride (elements) for Q / K / V tiles (conflict-free for ldmatrix)
+  constexpr int QT = 16 * NW;  // query rows per CTA
+  constexpr int NT = 32 * NW;  // threads
   extern __shared__ __align__(16) uint8_t smem_mha[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_mha);
-  __nv_bfloat16* Ks = Qs + 64 * QS;
-  __nv_bfloat16* Vt = Ks + 64 * QS;
+  __nv_bfloat16* KV = Qs + QT * QS;   // [2 buffers][K 64 rows | V 64 rows][QS]; V row-major, read via ldmatrix.trans
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -90,7 +105,7 @@ __global__ void __launch_bounds__(128) mha_kernel(const MhaParams p) {
     Lq = p.Lq;
     Lk = p.Lk;
   }
-  const int q0 = blockIdx.z * 64;
+  const int q0 = blockIdx.z * QT;
   if (q0 >= Lq) return;
   const int Lk_valid = (p.Lk_valid > 0 && w == 0) ? p.Lk_valid : Lk;
   const int DV8 = p.D / 8;  // 16-byte vectors per head row
@@ -104,7 +119,7 @@ __global__ void __launch_bounds__(128) mha_kernel(const MhaParams p) {
   };
 
   // ---- stage Q tile (rows >= Lq and dims >= D are zero) ----
-  for (int i = tid; i < 64 * (DP / 8); i += 128) {
+  for (int i = tid; i < QT * (DP / 8); i += NT) {
     const int r = i / (DP / 8), c = i % (DP / 8);
     uint4 val = make_uint4(0, 0, 0, 0);
     const int qr = q0 + r;
@@ -151,27 +166,38 @@ __global__ void __launch_bounds__(128) mha_kernel(const MhaParams p) {
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   const bool warp_active = (q0 + warp * 16) < Lq;
 
-  for (int k0 = 0; k0 < Lk; k0 += 64) {
-    __syncthreads();
-    // ---- stage K chunk [64][DP] and V^T chunk [DP][64] ----
-    for (int i = tid; i < 64 * (DP / 8); i += 128) {
+  // ---- K/V chunk producer (cp.async, zero-fill for rows >= Lk, padded dims and pad-less tokens) ----
+  auto stage = [&](int k0, int buf) {
+    __nv_bfloat16* Kb = KV + buf * (128 * QS);
+    __nv_bfloat16* Vb = Kb + 64 * QS;
+    for (int i = tid; i < 64 * (DP / 8); i += NT) {
       const int r = i / (DP / 8), c = i % (DP / 8);
       const int kr = k0 + r;
-      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+      const __nv_bfloat16* ks = nullptr;
+      const __nv_bfloat16* vs = nullptr;
       if (kr < Lk && c < DV8) {
-        const __nv_bfloat16* ks = tok_ptr(p.k, p.k_bs, p.k_tok, p.pad_k, kr);
-        const __nv_bfloat16* vs = tok_ptr(p.v, p.v_bs, p.v_tok, p.pad_v, kr);
-        if (ks) kv = *reinterpret_cast<const uint4*>(ks + c * 8);
-        if (vs) vv = *reinterpret_cast<const uint4*>(vs + c * 8);
+        ks = tok_ptr(p.k, p.k_bs, p.k_tok, p.pad_k, kr);
+        vs = tok_ptr(p.v, p.v_bs, p.v_tok, p.pad_v, kr);
       }
-      *reinterpret_cast<uint4*>(Ks + r * QS + c * 8) = kv;
-      const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) Vt[(c * 8 + e) * VS + r] = ve[e];
+      cp_async16(Kb + r * QS + c * 8, ks ? static_cast<const void*>(ks + c * 8) : static_cast<const void*>(p.k), ks ? 16 : 0);
+      cp_async16(Vb + r * QS + c * 8, vs ? static_cast<const void*>(vs + c * 8) : static_cast<const void*>(p.v), vs ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+  const int n_chunks = (Lk + 63) / 64;
+  stage(0, 0);
+  for (int j = 0; j < n_chunks; ++j) {
+    const int k0 = j * 64;
+    if (j + 1 < n_chunks) {
+      stage(k0 + 64, (j + 1) & 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
-    if (!warp_active) continue;
-
+    const __nv_bfloat16* Ks = KV + (j & 1) * (128 * QS);
+    const __nv_bfloat16* Vs = Ks + 64 * QS;
+    if (warp_active) {
     // ---- S = Q K^T for this warp's 16 rows x 64 keys ----
     float s[8][4];
 #pragma unroll
@@ -231,17 +257,26 @@ __global__ void __launch_bounds__(128) mha_kernel(const MhaParams p) {
       o[i][2] *= a1;
       o[i][3] *= a1;
     }
-    // ---- O += P V ----
+    // ---- O += P V : one ldmatrix.x4.trans yields the B fragments of two 8-wide output tiles ----
+    {
+      // lanes 0-7 / 8-15: keys kk*16 + 0..7 / 8..15 of dims tile i; lanes 16-31: same keys, tile i+1
+      const uint32_t vbase = static_cast<uint32_t>(__cvta_generic_to_shared(
+          Vs + ((lane & 7) + ((lane >> 3) & 1) * 8) * QS + (lane >> 4) * 8));
 #pragma unroll
-    for (int i = 0; i < DP / 8; ++i) {
-      const __nv_bfloat16* vrow = Vt + (i * 8 + g) * VS;
+      for (int i = 0; i < DP / 8; i += 2) {
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vrow + kk * 16 + 2 * t);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vrow + kk * 16 + 8 + 2 * t);
-        mma_bf16_16816(o[i], pa[kk], b0, b1);
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t b0, b1, b2, b3;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                       : "r"(vbase + static_cast<uint32_t>((kk * 16 * QS + i * 8) * 2)));
+          mma_bf16_16816(o[i], pa[kk], b0, b1);
+          mma_bf16_16816(o[i + 1], pa[kk], b2, b3);
+        }
       }
     }
+    }  // warp_active
+    __syncthreads();  // every warp is done with buffer j&1 before chunk j+2 is staged into it
   }
   if (!warp_active) return;
   // ---- finalize: quad-reduce row sums, normalise, store ----
@@ -271,18 +306,26 @@ __global__ void __launch_bounds__(128) mha_kernel(const MhaParams p) {
   }
 }
 
-template <int DP>
-static int launch_mha(const MhaParams& p, dim3 grid, cudaStream_t st) {
-  const int smem = (2 * 64 * (DP + 8) + DP * 72) * 2;
+template <int DP, int NW>
+static int launch_mha_nw(const MhaParams& p, dim3 grid, cudaStream_t st) {
+  const int smem = (16 * NW + 2 * 128) * (DP + 8) * 2;
   if (smem > 48 * 1024) {
     static bool set = false;
     if (!set) {
-      cudaFuncSetAttribute(mha_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(mha_kernel<DP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       set = true;
     }
   }
-  mha_kernel<DP><<<grid, 128, smem, st>>>(p);
+  mha_kernel<DP, NW><<<grid, 32 * NW, smem, st>>>(p);
   return post_launch("mha_kernel");
+}
+
+// 128-row query tiles when a sequence has at least 128 queries (halves the K/V re-reads of the global
+// Hiera blocks and the image->token decoder attention), 64-row tiles otherwise.
+template <int DP>
+static int launch_mha(const MhaParams& p, int nseq, int H, int Lq, cudaStream_t st) {
+  if (Lq >= 128) return launch_mha_nw<DP, 8>(p, dim3(nseq, H, (Lq + 127) / 128), st);
+  return launch_mha_nw<DP, 4>(p, dim3(nseq, H, (Lq + 63) / 64), st);
 }
 
 }  // namespace ds2
@@ -342,13 +385,12 @@ extern "C" int ds2_mha(const ds2_mha_args* a, void* stream) {
     nseq = a->B;
   }
   DS2_REQUIRE((Lq + 63) / 64 <= 65535 && a->H <= 65535, DS2_E_ARG, "ds2_mha: grid too large");
-  dim3 grid(nseq, a->H, (Lq + 63) / 64);
   cudaStream_t st = as_stream(stream);
   const int D = a->D;
-  if (D <= 16) return launch_mha<16>(p, grid, st);
-  if (D <= 32) return launch_mha<32>(p, grid, st);
-  if (D <= 64) return launch_mha<64>(p, grid, st);
-  if (D <= 80) return launch_mha<80>(p, grid, st);
-  if (D <= 96) return launch_mha<96>(p, grid, st);
-  return launch_mha<128>(p, grid, st);
+  if (D <= 16) return launch_mha<16>(p, nseq, a->H, Lq, st);
+  if (D <= 32) return launch_mha<32>(p, nseq, a->H, Lq, st);
+  if (D <= 64) return launch_mha<64>(p, nseq, a->H, Lq, st);
+  if (D <= 80) return launch_mha<80>(p, nseq, a->H, Lq, st);
+  if (D <= 96) return launch_mha<96>(p, nseq, a->H, Lq, st);
+  return launch_mha<128>(p, nseq, a->H, Lq, st);
 }
