@@ -86,3 +86,25 @@ class BilliardVideo:
             out[i] = [float(max(0, cx - r)), float(max(0, cy - r)), float(min(self.W - 1, cx + r)),
                       float(min(self.H - 1, cy + r))]
         return out
+
+
+class GroundTruthDetector:
+    """Stand-in for the YOLOv8 box-prompt detector on synthetic video ("ground-truth boxes =
+    disc bbox +-2 px; detector time reported separately as n.a.").  Presents the injected-detector interface of
+    ``VideoProcessor``: called with the frames that fall on the ``detect_interval`` grid, in stream order, and
+    returns one detection list per frame (class = object id, as Det-SAM2 uses the class as obj_id)."""
+
+    def __init__(self, video, detect_interval, first_frame=0, appear_at=None):
+        self.video, self.interval, self.next_idx = video, detect_interval, first_frame
+        self.appear_at = appear_at or {}  # obj_id -> first frame at which the detector reports it
+
+    def __call__(self, frames_bgr):
+        out = []
+        for _ in frames_bgr:
+            t = self.next_idx
+            dets = [{"coordinates": np.asarray(b, np.float32), "class": np.asarray([float(oid)], np.float32),
+                     "confidence": np.asarray([0.99], np.float32)}
+                    for oid, b in self.video.boxes(t).items() if t >= self.appear_at.get(oid, 0)]
+            out.append(dets)
+            self.next_idx += self.interval
+        return out

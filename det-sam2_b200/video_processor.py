@@ -1,0 +1,253 @@
+"""Host-side mirror of Det-SAM2's stream driver ``VideoProcessor``
+(/root/reference/det_sam2_inference/det_sam2_RT.py:25-684): frames are accumulated into a buffer,
+every ``frame_buffer_size`` frames the detector produces box prompts for the frames that fall on the
+``detect_interval`` grid, the buffer is appended to the predictor state, prompts are added, the last
+``max_frame_num_to_track`` frames are re-tracked in REVERSE from the newest frame, and frames older
+than ``max_inference_state_frames`` are released (constant-memory window).  An optional pickled
+"preload memory bank" seeds the state.
+
+Same constructor keywords, methods (``process_frame``, ``Detect_and_SAM2_inference``,
+``detect_predict``, ``Detect_2_SAM2_Prompt``, ``run``, ``clear``, ``save/load_inference_state``) and
+result type (``video_segments: {frame_idx: {obj_id: bool ndarray [1,H,W]}}``) as the reference.
+
+Out of scope, as in SURVEY.md §8: the YOLOv8 detector itself ("left untouched, timed separately") is
+*injected* — ``detector(frames_bgr) -> [[{"coordinates", "class", "confidence"}, ...], ...]`` — and
+loaded from ultralytics only when ``detect_model_weights`` is given and no detector is passed;
+matplotlib rendering (``vis_frame_stride``, ``visualize_prompt``) is not provided.
+"""
+import os
+import pickle
+
+import numpy as np
+import torch
+
+
+def _yolo_detector(weights, conf):
+    """det_sam2_RT.py:96,230-245: the reference's own detector call, unchanged."""
+    try:
+        from ultralytics import YOLO
+    except ImportError as e:  # fail loudly: there is no stand-in detector in the product
+        raise ImportError("ultralytics is required for detect_model_weights; pass detector=... instead") from e
+    model = YOLO(weights)
+
+    def detect(frames_bgr):
+        out = []
+        for result in model(frames_bgr, stream=True, conf=conf, iou=0.1, verbose=False):
+            dets = []
+            if result.boxes is not None:
+                for box in result.boxes:
+                    dets.append({"coordinates": box.xyxy[0].cpu().numpy(), "class": box.cls.cpu().numpy(),
+                                 "confidence": box.conf.cpu().numpy()})
+            out.append(dets)
+        return out
+
+    return detect
+
+
+class VideoProcessor:
+    def __init__(self, output_dir=None, sam2_checkpoint=None, model_cfg="configs/sam2.1/sam2.1_hiera_l.yaml",
+                 detect_model_weights=None, detect_confidence=0.85, skip_classes=frozenset({11, 14, 15, 19}),
+                 vis_frame_stride=-1, visualize_prompt=False, frame_buffer_size=30, detect_interval=30,
+                 max_frame_num_to_track=60, max_inference_state_frames=60, load_inference_state_path=None,
+                 save_inference_state_path=None, *, predictor=None, detector=None, device="cuda"):
+        if vis_frame_stride != -1 or visualize_prompt:
+            raise NotImplementedError("matplotlib rendering is outside the hot path; use vis_frame_stride=-1")
+        if save_inference_state_path is not None:
+            # det_sam2_RT.py:67-68
+            assert max_inference_state_frames == -1, \
+                "saving a preload memory bank requires max_inference_state_frames == -1 (nothing may be released)"
+        self.output_dir = output_dir
+        self.sam2_checkpoint = sam2_checkpoint
+        self.model_cfg = model_cfg
+        self.detect_model_weights = detect_model_weights
+        self.detect_confidence = detect_confidence
+        self.skip_classes = set(skip_classes)
+        self.vis_frame_stride = vis_frame_stride
+        self.visualize_prompt = visualize_prompt
+        self.frame_buffer_size = frame_buffer_size
+        self.detect_interval = detect_interval
+        self.frame_buffer = []
+        self.max_frame_num_to_track = max_frame_num_to_track
+        self.max_inference_state_frames = max_inference_state_frames
+        self.load_inference_state_path = load_inference_state_path
+        self.save_inference_state_path = save_inference_state_path
+        self.pre_frames = 0
+        self.special_classes = 11  # det_sam2_RT.py:71 (pockets: many instances of one class)
+        self.special_classes_detection = []
+        self.special_classes_count = 0
+        if predictor is None:
+            from .build_sam import build_sam2_video_predictor
+            predictor = build_sam2_video_predictor(model_cfg, sam2_checkpoint, device=device)
+        self.predictor = predictor
+        if detector is None and detect_model_weights is not None:
+            detector = _yolo_detector(detect_model_weights, detect_confidence)
+        self.detect_model = detector
+        self.video_segments = {}
+        self.inference_state = None
+        if output_dir:
+            os.makedirs(output_dir, exist_ok=True)
+
+    # ---- detector seam (det_sam2_RT.py:201-269) ----------------------------------------------------
+    def detect_predict(self, images, past_num_frames):
+        detection_results = {}
+        if self.detect_interval == -1:
+            return detection_results
+        selected, absolute = [], []
+        for i, image in enumerate(images):
+            frame_idx = past_num_frames + i
+            if frame_idx % self.detect_interval == 0:
+                selected.append(np.ascontiguousarray(image[..., ::-1]))  # RGB -> BGR, what YOLO was trained on
+                absolute.append(frame_idx)
+        if not selected:
+            return detection_results
+        if self.detect_model is None:
+            raise RuntimeError("detect_interval != -1 but no detector was provided")
+        for i, dets in enumerate(self.detect_model(selected)):
+            dets = list(dets)
+            if not self.special_classes_detection:
+                self.special_classes_count = 0
+            n_special = sum(1 for d in dets if int(np.asarray(d["class"]).reshape(-1)[0]) == self.special_classes)
+            if n_special > self.special_classes_count:
+                self.special_classes_detection = [d["coordinates"] for d in dets
+                                                  if int(np.asarray(d["class"]).reshape(-1)[0]) == self.special_classes]
+                self.special_classes_count = n_special
+            detection_results[f"frame_{absolute[i]}"] = dets
+        return detection_results
+
+    # ---- prompts (det_sam2_RT.py:271-316) ----------------------------------------------------------
+    def Detect_2_SAM2_Prompt(self, detection_results_json):
+        if not detection_results_json:
+            return self.inference_state
+        for key, detections in detection_results_json.items():
+            ann_frame_idx = int(key.replace("frame_", ""))
+            for det in detections:
+                obj_class = int(np.asarray(det["class"]).reshape(-1)[0])
+                if obj_class in self.skip_classes:
+                    continue
+                self.predictor.add_new_points_or_box(
+                    inference_state=self.inference_state, frame_idx=ann_frame_idx, obj_id=obj_class,
+                    box=np.array(det["coordinates"], dtype=np.float32))
+        return self.inference_state
+
+    # ---- one chunk (det_sam2_RT.py:342-411) --------------------------------------------------------
+    def Detect_and_SAM2_inference(self, frame_idx):
+        past_num_frames = self.inference_state["num_frames"] if self.inference_state else 0
+        detection_results_json = self.detect_predict(self.frame_buffer, past_num_frames)
+        if self.inference_state is None:
+            self.inference_state = self.predictor.init_state(video_path=self.frame_buffer)
+        else:
+            self.inference_state = self.predictor.update_state(video_path=self.frame_buffer,
+                                                               inference_state=self.inference_state)
+        try:
+            self.inference_state = self.Detect_2_SAM2_Prompt(detection_results_json)
+        except RuntimeError as e:
+            if "reset_state" in str(e):
+                self.predictor.reset_state(self.inference_state)
+                self.inference_state = self.Detect_2_SAM2_Prompt(detection_results_json)
+            else:
+                raise
+        for out_frame_idx, out_obj_ids, out_mask_logits in self.predictor.propagate_in_video(
+                self.inference_state, start_frame_idx=frame_idx,
+                max_frame_num_to_track=self.max_frame_num_to_track, reverse=True):
+            if out_frame_idx >= self.pre_frames:
+                self.video_segments[out_frame_idx] = self._masks_to_host(out_obj_ids, out_mask_logits)
+        if self.max_inference_state_frames != -1:
+            self.predictor.release_old_frames(self.inference_state, frame_idx, self.max_inference_state_frames,
+                                              self.pre_frames, release_images=self.vis_frame_stride == -1)
+
+    @staticmethod
+    def _masks_to_host(obj_ids, mask_logits):
+        """det_sam2_RT.py:396-399 does B x ``(logits[i] > 0).cpu().numpy()``; here the threshold runs
+        once on the device and ONE copy brings all objects back."""
+        m = (mask_logits > 0.0).cpu().numpy()
+        return {oid: m[i] for i, oid in enumerate(obj_ids)}
+
+    def process_frame(self, frame_idx, frame):
+        """det_sam2_RT.py:421-435."""
+        self.frame_buffer.append(frame)
+        if len(self.frame_buffer) >= self.frame_buffer_size:
+            self.Detect_and_SAM2_inference(frame_idx)
+            self.frame_buffer.clear()
+        return self.inference_state
+
+    def clear(self):
+        """det_sam2_RT.py:189-199."""
+        self.frame_buffer = []
+        self.pre_frames = 0
+        self.special_classes_detection = []
+        self.video_segments = {}
+        self.inference_state = None
+
+    # ---- preload bank (det_sam2_RT.py:489-503) -----------------------------------------------------
+    def save_inference_state(self, save_path):
+        directory = os.path.dirname(save_path)
+        if directory and not os.path.exists(directory):
+            os.makedirs(directory)
+        with open(save_path, "wb") as f:
+            pickle.dump(self.inference_state, f)
+
+    def load_inference_state(self, load_path):
+        with open(load_path, "rb") as f:
+            return pickle.load(f)
+
+    def load_frames_from_folder(self, folder_path):
+        import cv2
+        frames = []
+        for name in sorted(f for f in os.listdir(folder_path) if f.endswith((".png", ".jpg", ".jpeg"))):
+            frame = cv2.imread(os.path.join(folder_path, name))
+            if frame is None:
+                continue
+            frames.append(cv2.cvtColor(frame, cv2.COLOR_BGR2RGB))
+        return frames
+
+    # ---- whole stream (det_sam2_RT.py:526-640) -----------------------------------------------------
+    def run(self, video_path=None, frame_dir=None, output_video_segments_pkl_path=None,
+            output_special_classes_detection_pkl_path=None, frames=None):
+        """``frames`` (an iterable of RGB uint8 ndarrays) is an addition for in-memory / synthetic
+        streams; ``video_path`` and ``frame_dir`` behave as in the reference."""
+        if self.load_inference_state_path is not None:
+            st = self.load_inference_state(self.load_inference_state_path)
+            st["preloading_memory_cond_frame_idx"] = list(st["output_dict"]["cond_frame_outputs"].keys())
+            st["preloading_memory_non_cond_frames_idx"] = list(st["output_dict"]["non_cond_frame_outputs"].keys())
+            self.pre_frames = st["num_frames"]
+            self.inference_state = st
+            self.predictor.init_preloading_state(st)
+
+        def stream():
+            if frames is not None:
+                yield from frames
+            elif video_path is not None:
+                import cv2
+                cap = cv2.VideoCapture(video_path)
+                if not cap.isOpened():
+                    raise IOError(f"cannot open video {video_path}")
+                while True:
+                    ret, frame = cap.read()
+                    if not ret:
+                        break
+                    yield cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
+                cap.release()
+            elif frame_dir is not None:
+                yield from self.load_frames_from_folder(frame_dir)
+            else:
+                raise ValueError("one of video_path, frame_dir or frames is required")
+
+        frame_idx = 0
+        for frame_rgb in stream():
+            self.inference_state = self.process_frame(self.pre_frames + frame_idx, frame_rgb)
+            frame_idx += 1
+        if self.frame_buffer:  # tail shorter than frame_buffer_size
+            self.Detect_and_SAM2_inference(frame_idx=self.pre_frames + frame_idx - 1)
+            self.frame_buffer.clear()
+        # results are re-based so that they do not count the preload frames (det_sam2_RT.py:612)
+        self.video_segments = {idx - self.pre_frames: seg for idx, seg in self.video_segments.items()
+                               if idx >= self.pre_frames}
+        if output_video_segments_pkl_path:
+            with open(output_video_segments_pkl_path, "wb") as f:
+                pickle.dump(self.video_segments, f)
+        if output_special_classes_detection_pkl_path:
+            with open(output_special_classes_detection_pkl_path, "wb") as f:
+                pickle.dump(self.special_classes_detection, f)
+        if self.save_inference_state_path is not None:
+            self.save_inference_state(self.save_inference_state_path)
+        return self.video_segments

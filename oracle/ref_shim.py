@@ -118,3 +118,70 @@ def build_reference_predictor(cfg, state_dict=None, device="cpu"):
     model = model.to(device)
     model.eval()
     return model
+
+
+def reference_video_processor_class(predictor, detector):
+    """Imports the UNMODIFIED det_sam2_inference/det_sam2_RT.py with its absent third-party imports
+    (ultralytics, IPython, matplotlib, pympler — SURVEY.md §0) replaced by inert stubs, and returns a
+    subclass factory whose ``predictor`` is `predictor` and whose YOLO model is `detector`
+    (``detector(frames_bgr) -> [[{"coordinates","class","confidence"}...]...]``), adapted to the
+    ultralytics result interface the reference reads (det_sam2_RT.py:230-245)."""
+    install()
+    import numpy as np
+    import torch
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    class _Val:
+        def __init__(self, a):
+            self._a = np.asarray(a)
+
+        def cpu(self):
+            return self
+
+        def numpy(self):
+            return self._a
+
+        def __getitem__(self, i):
+            return _Val(self._a[i])
+
+    class _Box:
+        def __init__(self, d):
+            self.xyxy = _Val(np.asarray(d["coordinates"], np.float32)[None])
+            self.cls = _Val(np.asarray(d["class"]).reshape(-1))
+            self.conf = _Val(np.asarray(d["confidence"]).reshape(-1))
+
+    class _Result:
+        def __init__(self, dets):
+            self.boxes = [_Box(d) for d in dets]
+
+    class YOLO:
+        def __init__(self, weights=None):
+            pass
+
+        def __call__(self, frames, **kw):
+            return (_Result(d) for d in detector(frames))
+
+    stub("pympler", asizeof=None)
+    disp = stub("IPython.display", display=lambda *a, **k: None, Image=None, clear_output=lambda *a, **k: None)
+    stub("IPython", display=disp)
+    stub("ultralytics", checks=lambda: None, YOLO=YOLO)
+    if "matplotlib" not in sys.modules:
+        try:
+            import matplotlib.pyplot  # noqa: F401
+        except ImportError:
+            plt = stub("matplotlib.pyplot")
+            stub("matplotlib", pyplot=plt)
+    stub("sam2.build_sam", build_sam2_video_predictor=lambda *a, **k: predictor)
+    inf = os.path.join(REF_ROOT, "det_sam2_inference")
+    if inf not in sys.path:
+        sys.path.insert(0, inf)
+    sys.modules.pop("det_sam2_RT", None)
+    import det_sam2_RT
+    # the constructor enters a CUDA autocast context when a GPU is present (det_sam2_RT.py:101-107);
+    # on this CPU-only container it is a no-op
+    return det_sam2_RT.VideoProcessor

@@ -1,0 +1,230 @@
+"""TEST INFRASTRUCTURE — API-level scenarios driven through *any* object that presents the reference's
+``SAM2VideoPredictor`` interface (/root/reference/sam2/sam2_video_predictor.py): the unmodified
+reference (through oracle/ref_shim.py, build container only), this repo's predictor over the CPU
+oracle engine, or this repo's predictor over the sm_100a CUDA engine.  Because the predictor API is
+the drop-in boundary, ONE driver serves all three; parity = the recorded arrays agree.
+
+Every scenario returns ``{name: np.ndarray}``.  Nothing in the product imports this module.
+
+Scenarios
+  offline   BASELINE.json configs[0]: sam2.1_hiera_tiny, 4 synthetic 512x512 frames, 1 box prompt on
+            frame 0 -> init_state -> add_new_points_or_box -> propagate_in_video.
+  stream    Det-SAM2 streaming semantics (det_sam2_RT.py:342-411) on a reduced-resolution tiny model:
+            init_state(chunk) / update_state(chunk), box prompts on the last frame of each chunk,
+            reverse propagate with max_frame_num_to_track, an online NEW object id while tracking
+            (svp:250-327), release_old_frames with release_images (svp:1215-1277).
+  preload   preload memory bank (det_sam2_RT.py:489-503, svp:123-156): every frame of a short clip is
+            a conditioning frame, state is pickled, re-loaded, init_preloading_state, new frames
+            appended with update_state and tracked against the bank.
+"""
+import io
+import pickle
+
+import numpy as np
+import torch
+
+from detsam2_b200.config import get_config
+from detsam2_b200.synthetic import BilliardVideo
+
+# reduced resolution for the plumbing-heavy scenarios (T = 32*32 tokens): same code paths, 4x cheaper
+SMALL = dict(image_size=512)
+
+
+def scenario_config(name):
+    if name == "offline":
+        return get_config("tiny")
+    return get_config("tiny", **SMALL)
+
+
+def _np(t):
+    return t.detach().to(torch.float32).cpu().numpy().copy()
+
+
+def _record_frame(rec, tag, st, frame_idx, masks):
+    """Per yielded frame: the video-res logits (as the caller sees them) and what the state keeps."""
+    rec[f"{tag}.f{frame_idx}.video_res_masks"] = _np(masks)
+    od = st["output_dict"]
+    out = od["cond_frame_outputs"].get(frame_idx) or od["non_cond_frame_outputs"].get(frame_idx)
+    if out is None:
+        return
+    rec[f"{tag}.f{frame_idx}.pred_masks"] = _np(out["pred_masks"])
+    rec[f"{tag}.f{frame_idx}.obj_ptr"] = _np(out["obj_ptr"])
+    rec[f"{tag}.f{frame_idx}.object_score_logits"] = _np(out["object_score_logits"])
+    if out.get("maskmem_features") is not None:
+        # every 4th channel: keeps the committed fixtures small, still covers all pixels / objects
+        rec[f"{tag}.f{frame_idx}.maskmem_features"] = _np(out["maskmem_features"][:, ::4])
+
+
+def run_offline(predictor, num_frames=4, size=512, num_objects=1, seed=3):
+    vid = BilliardVideo(num_objects=num_objects, height=size, width=size, num_frames=num_frames, seed=seed)
+    frames = list(vid.frames())
+    rec = {}
+    with torch.inference_mode():
+        st = predictor.init_state(frames)
+        for oid, box in vid.boxes(0).items():
+            f, ids, m = predictor.add_new_points_or_box(st, 0, oid, box=np.asarray(box, dtype=np.float32))
+            rec[f"prompt.obj{oid}.video_res_masks"] = _np(m)
+        for f, ids, m in predictor.propagate_in_video(st):
+            _record_frame(rec, "track", st, f, m)
+        rec["obj_ids"] = np.asarray(list(st["obj_ids"]), dtype=np.int64)
+    return rec
+
+
+def run_stream(predictor, chunk=3, chunks=3, height=192, width=256, seed=5, max_track=5, window=4):
+    """Chunked stream: chunk 0 -> objects {0,1}; chunk 1 -> re-prompt + NEW object 2; chunk 2 ->
+    re-prompt all; after every chunk reverse-propagate `max_track` frames and release old frames."""
+    nobj = 3
+    vid = BilliardVideo(num_objects=nobj, height=height, width=width, num_frames=chunk * chunks, seed=seed)
+    rec = {}
+    st = None
+    with torch.inference_mode():
+        for c in range(chunks):
+            buf = [vid.frame(t) for t in range(c * chunk, (c + 1) * chunk)]
+            st = predictor.init_state(buf) if st is None else predictor.update_state(buf, st)
+            last = (c + 1) * chunk - 1
+            ids = (0, 1) if c == 0 else (0, 1, 2)
+            boxes = vid.boxes(last)
+            for oid in ids:
+                predictor.add_new_points_or_box(st, last, oid, box=np.asarray(boxes[oid], dtype=np.float32))
+            for f, oids, m in predictor.propagate_in_video(st, start_frame_idx=last, max_frame_num_to_track=max_track,
+                                                           reverse=True):
+                _record_frame(rec, f"c{c}", st, f, m)
+                rec[f"c{c}.f{f}.obj_ids"] = np.asarray(list(oids), dtype=np.int64)
+            predictor.release_old_frames(st, last, window, 0, release_images=True)
+            rec[f"c{c}.images_idx"] = np.asarray(st["images_idx"], dtype=np.int64)
+            rec[f"c{c}.cond_keys"] = np.asarray(sorted(st["output_dict"]["cond_frame_outputs"]), dtype=np.int64)
+            rec[f"c{c}.non_cond_keys"] = np.asarray(sorted(st["output_dict"]["non_cond_frame_outputs"]), dtype=np.int64)
+            rec[f"c{c}.num_frames"] = np.asarray([st["num_frames"], len(st["images"])], dtype=np.int64)
+    return rec
+
+
+def run_preload(predictor, pre=3, extra=3, height=192, width=256, seed=7):
+    nobj = 2
+    vid = BilliardVideo(num_objects=nobj, height=height, width=width, num_frames=pre + extra, seed=seed)
+    rec = {}
+    with torch.inference_mode():
+        # ---- build the bank: every frame a conditioning frame (detect_interval = 1) ----
+        st = predictor.init_state([vid.frame(t) for t in range(pre)])
+        for t in range(pre):
+            for oid, box in vid.boxes(t).items():
+                predictor.add_new_points_or_box(st, t, oid, box=np.asarray(box, dtype=np.float32))
+        for f, oids, m in predictor.propagate_in_video(st, start_frame_idx=pre - 1, max_frame_num_to_track=pre,
+                                                       reverse=True):
+            _record_frame(rec, "bank", st, f, m)
+        # ---- pickle round trip (det_sam2_RT.py:489-503) ----
+        blob = io.BytesIO()
+        pickle.dump(st, blob)
+        rec["bank.cond_keys"] = np.asarray(sorted(st["output_dict"]["cond_frame_outputs"]), dtype=np.int64)
+        st = pickle.loads(blob.getvalue())
+        # det_sam2_RT.py:127-133: mark the preload frames
+        st["preloading_memory_cond_frame_idx"] = list(st["output_dict"]["cond_frame_outputs"].keys())
+        st["preloading_memory_non_cond_frames_idx"] = list(st["output_dict"]["non_cond_frame_outputs"].keys())
+        predictor.init_preloading_state(st, offload_video_to_cpu=True, offload_state_to_cpu=False)
+        # ---- stream new frames against the bank, no new prompts (detect_interval = -1) ----
+        st = predictor.update_state([vid.frame(t) for t in range(pre, pre + extra)], st)
+        last = pre + extra - 1
+        # forward pass over the appended frames starting from the last preload frame
+        for f, oids, m in predictor.propagate_in_video(st, start_frame_idx=pre - 1, max_frame_num_to_track=extra,
+                                                       reverse=False):
+            _record_frame(rec, "live", st, f, m)
+        predictor.release_old_frames(st, last, 2, pre, release_images=True)
+        rec["live.images_idx"] = np.asarray(st["images_idx"], dtype=np.int64)
+        rec["live.cond_keys"] = np.asarray(sorted(st["output_dict"]["cond_frame_outputs"]), dtype=np.int64)
+        rec["live.non_cond_keys"] = np.asarray(sorted(st["output_dict"]["non_cond_frame_outputs"]), dtype=np.int64)
+    return rec
+
+
+def run_video_processor(make_vp, num_frames=11, height=160, width=224, seed=11):
+    """Det-SAM2's own driver (det_sam2_RT.py VideoProcessor.run) over a frame folder: K = 4 frames per
+    chunk, detection every 4 frames, reverse window M = 6, state window S = 6 with image release, a
+    third object that the detector only reports from frame 4 on (online new id), and a 3-frame tail.
+    `make_vp(detector, **ctor_kwargs)` builds the reference's or this repo's VideoProcessor."""
+    import os
+    import tempfile
+
+    import cv2
+    from detsam2_b200.synthetic import GroundTruthDetector
+    vid = BilliardVideo(num_objects=3, height=height, width=width, num_frames=num_frames, seed=seed)
+    det = GroundTruthDetector(vid, detect_interval=4, appear_at={2: 4})
+    rec = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        fdir = os.path.join(tmp, "frames")
+        os.makedirs(fdir)
+        for t in range(num_frames):
+            cv2.imwrite(os.path.join(fdir, f"{t:05d}.png"), cv2.cvtColor(vid.frame(t), cv2.COLOR_RGB2BGR))
+        vp = make_vp(det, output_dir=os.path.join(tmp, "out"), frame_buffer_size=4, detect_interval=4,
+                     max_frame_num_to_track=6, max_inference_state_frames=6, skip_classes={11, 14, 15, 19})
+        with torch.inference_mode():
+            vp.run(frame_dir=fdir, output_video_segments_pkl_path=os.path.join(tmp, "seg.pkl"),
+                   output_special_classes_detection_pkl_path=os.path.join(tmp, "special.pkl"))
+        with open(os.path.join(tmp, "seg.pkl"), "rb") as f:
+            segs = pickle.load(f)
+    rec["frames"] = np.asarray(sorted(segs), dtype=np.int64)
+    for t in sorted(segs):
+        ids = sorted(segs[t])
+        rec[f"f{t}.obj_ids"] = np.asarray(ids, dtype=np.int64)
+        rec[f"f{t}.masks_packed"] = np.packbits(np.stack([segs[t][i] for i in ids]).astype(np.uint8))
+    st = vp.inference_state
+    rec["images_idx"] = np.asarray(st["images_idx"], dtype=np.int64)
+    rec["cond_keys"] = np.asarray(sorted(st["output_dict"]["cond_frame_outputs"]), dtype=np.int64)
+    rec["non_cond_keys"] = np.asarray(sorted(st["output_dict"]["non_cond_frame_outputs"]), dtype=np.int64)
+    return rec
+
+
+def packed_mask_iou(a, b):
+    """IoU of two np.packbits arrays."""
+    a, b = np.unpackbits(a), np.unpackbits(b)
+    u = np.logical_or(a, b).sum()
+    return 1.0 if u == 0 else float(np.logical_and(a, b).sum()) / float(u)
+
+
+def load_golden(name):
+    """tests/golden/<name>.npz -> (arrays, weights fingerprint)."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", f"{name}.npz")
+    assert os.path.exists(path), f"{path} missing: run `python -m oracle.gen_golden` in the build container"
+    z = np.load(path)
+    d = {k: z[k] for k in z.files}
+    d.pop("__torch_version", None)
+    return d, d.pop("__weights_fingerprint")
+
+
+SCENARIOS = {"offline": run_offline, "stream": run_stream, "preload": run_preload}
+
+
+def compare(got, ref, rtol_rms, iou_min=None, int_exact=True):
+    """Returns a list of human-readable mismatches (empty = parity).  Float arrays are compared by
+    relative RMS error; integer arrays must be identical; `*.video_res_masks` additionally by the
+    IoU of the thresholded masks when `iou_min` is given."""
+    bad = []
+    for k, r in ref.items():
+        if k not in got:
+            bad.append(f"{k}: missing")
+            continue
+        g = got[k]
+        if g.shape != r.shape:
+            bad.append(f"{k}: shape {g.shape} != {r.shape}")
+            continue
+        if k.endswith("masks_packed"):
+            iou = packed_mask_iou(g, r)
+            if iou < (iou_min if iou_min is not None else 1.0):
+                bad.append(f"{k}: packed-mask IoU {iou:.5f}")
+            continue
+        if np.issubdtype(r.dtype, np.integer):
+            if int_exact and not np.array_equal(g, r):
+                bad.append(f"{k}: integer mismatch {g.tolist()} != {r.tolist()}")
+            continue
+        g64, r64 = g.astype(np.float64), r.astype(np.float64)
+        den = max(np.sqrt(np.mean(r64 ** 2)), 1e-12)
+        err = np.sqrt(np.mean((g64 - r64) ** 2)) / den
+        # fixtures stored as fp16 carry their own quantisation (2^-11 relative, ~3e-4 rms)
+        tol = rtol_rms + (6e-4 if r.dtype == np.float16 else 0.0)
+        if not np.isfinite(err) or err > tol:
+            bad.append(f"{k}: rel-rms {err:.3e} > {tol:.1e}")
+        if iou_min is not None and k.endswith("video_res_masks"):
+            a, b = g > 0, r > 0
+            u = np.logical_or(a, b).sum()
+            iou = 1.0 if u == 0 else np.logical_and(a, b).sum() / u
+            if iou < iou_min:
+                bad.append(f"{k}: mask IoU {iou:.5f} < {iou_min}")
+    return bad

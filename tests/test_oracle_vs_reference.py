@@ -1,0 +1,49 @@
+"""Live pin of the oracle against the UNMODIFIED reference imported from /root/reference (build
+container only; skipped on the GPU box where the reference does not exist — the committed fixtures
+under tests/golden/ carry the same comparison there)."""
+import os
+
+import pytest
+import torch
+
+from detsam2_b200.predictor import SAM2VideoPredictor
+from detsam2_b200.weights import synthetic_state_dict
+from oracle import ref_shim, scenarios
+from oracle import sam2_oracle as O
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present")
+
+
+def test_preload_scenario_live():
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    cfg = scenarios.scenario_config("preload")
+    sd = synthetic_state_dict(cfg, 0)
+    ref = scenarios.run_preload(ref_shim.build_reference_predictor(cfg, sd, device="cpu"))
+    got = scenarios.run_preload(SAM2VideoPredictor(O.OracleEngine(cfg, sd, fill_holes=False), fill_hole_area=0))
+    assert set(got) == set(ref)
+    bad = scenarios.compare(got, ref, 1e-4, iou_min=0.999)
+    assert not bad, "\n".join(bad)
+
+
+def test_error_behaviour_matches_reference():
+    """ValueError / RuntimeError on the same bad calls (svp:363-366, 385-388, 943-944)."""
+    import numpy as np
+    from detsam2_b200.synthetic import BilliardVideo
+    cfg = scenarios.scenario_config("stream")
+    sd = synthetic_state_dict(cfg, 0)
+    vid = BilliardVideo(num_objects=1, height=128, width=128, num_frames=2, seed=0)
+    frames = list(vid.frames())
+    preds = [ref_shim.build_reference_predictor(cfg, sd, device="cpu"),
+             SAM2VideoPredictor(O.OracleEngine(cfg, sd, fill_holes=False))]
+    for p in preds:
+        st = p.init_state(frames)
+        with pytest.raises(ValueError):
+            p.add_new_points_or_box(st, 0, 0, points=np.zeros((1, 2), np.float32))          # labels missing
+        with pytest.raises(ValueError):
+            p.add_new_points_or_box(st, 0, 0)                                                # nothing given
+        with pytest.raises(ValueError):
+            p.add_new_points_or_box(st, 0, 0, box=np.array([1, 2, 30, 40], np.float32), clear_old_points=False)
+        with pytest.raises(RuntimeError):
+            next(iter(p.propagate_in_video(st)))                                             # no prompts yet
+        with pytest.raises(AssertionError):
+            p.update_state([np.zeros((64, 64, 3), np.uint8)], st)                            # size mismatch
