@@ -148,7 +148,9 @@ def run_ours(args):
     clocks = None
     launches = 0
     kern = {}
-    for mode in ("device", "e2e"):
+    # "kernel": a few extra steps of the same workload with the memory-attention seam launched eagerly, so
+    # that CUDA events can bracket the dominant kernel (events cannot bracket a node of a replayed graph)
+    for mode in ("device", "e2e", "kernel"):
         st, gen = session(offload_video=(mode == "e2e"))
         bits = torch.empty((B * S * S) // 8, dtype=torch.uint8, device=dev)
         host_bits = torch.empty((B * S * S) // 8, dtype=torch.uint8).pin_memory()
@@ -166,8 +168,9 @@ def run_ours(args):
         if mode == "device":
             sampler = ClockSampler(local_rank)
             sampler.start()
+        if mode == "kernel":
             eng.kernel_timers = []
-        l0 = ops.launch_count()
+        l0 = eng.launches_executed()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         prof = args.cuda_profiler and mode == "device"
@@ -183,7 +186,9 @@ def run_ours(args):
         ms = e0.elapsed_time(e1)
         if mode == "device":
             clocks = sampler.stop()
-            launches = ops.launch_count() - l0
+            launches = eng.launches_executed() - l0
+            graph_replays = eng.graphs.replays
+        if mode == "kernel":
             timers, eng.kernel_timers = eng.kernel_timers, None
             for tag, a, b, meta in timers:
                 kern.setdefault(tag, []).append((a.elapsed_time(b), meta))
@@ -215,7 +220,10 @@ def run_ours(args):
                 "avg_launch_ms": round(avg_ms, 4), "launches_timed": len(durs), "keys_N": N,
                 "flops_per_launch_executed": fm["cross_exec_per_launch"],
                 "achieved_reference_formulation": round(fm["cross_alg_per_launch"] / (avg_ms * 1e-3) / 1e12, 1),
-                "share_of_step": round(sum(durs) / results["device"], 4)}
+                "share_of_step": round(sum(durs) / results["kernel"], 4),
+                "timing": f"CUDA events around each of the {len(durs)} launches of {K} extra steps of the same workload with "
+                          f"the memory-attention seam launched eagerly ({round(results['kernel'] / K, 3)} ms/step); the "
+                          f"timed `value` steps replay CUDA graphs, whose nodes events cannot bracket"}
     line = {
         "metric": METRIC, "value": round(fps, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(results["device"] / K, 3), "higher_is_better": True, "scaling": "weak",
@@ -230,6 +238,8 @@ def run_ours(args):
                 "d2h_bytes_per_step": (B * S * S) // 8, "ms_per_step": round(results["e2e"] / K, 3),
                 "api": "SAM2VideoPredictor.propagate_in_video + bit-packed (mask > 0) D2H"},
         "gpu_launches": int(launches),
+        "launch_mode": f"{len(eng.graphs.graphs)} captured CUDA graphs (one per seam signature), {graph_replays} replays so far; "
+                       f"gpu_launches counts kernel nodes executed by replays + eager C-ABI launches in the timed region",
         "clocks": clocks,
         "roofline": roof,
     }

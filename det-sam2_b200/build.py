@@ -23,6 +23,7 @@ SOURCES = [
     "decoder.cu",
     "post.cu",
     "prompt.cu",
+    "bank.cu",
 ]
 
 NVCC_FLAGS = [

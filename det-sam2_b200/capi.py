@@ -111,6 +111,7 @@ SYMBOLS = {
     "ds2_bank_ptr": (C.c_int, [_P, _P, _P, _P, _I, _L, _I, _P]),
     "ds2_prompt_tokens": (C.c_int, [_P, _P, _I, _I, _P, _P, _P, _P, _I, _F, _P, _P]),
     "ds2_bank_ptr_pe": (C.c_int, [_P, _F, _P, _P, _P, _P, _I, _L, _I, _P]),
+    "ds2_bank_assemble": (C.c_int, [_P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "ds2_memenc_finish": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "ds2_connected_components": (C.c_int, [_P, _P, _P, _I, _I, _I, _P]),
     "ds2_fill_holes": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),

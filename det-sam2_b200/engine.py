@@ -20,7 +20,9 @@ Seams (one per reference function the predictor calls):
   fill_holes / resize_masks   misc.py:365-393 (+ csrc/connected_components.cu), svp:618-642
 """
 import math
+import os
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -67,6 +69,101 @@ def _dense_pe(gauss, side):
     return torch.cat([c.sin(), c.cos()], dim=-1).reshape(side * side, -1).contiguous()
 
 
+class _SeamGraphs:
+    """CUDA-graph cache for the engine seams.  A seam body is a fixed sequence of C-ABI kernel launches
+    whose arguments depend only on the seam's *signature* (shapes, flags) once its tensor inputs live in
+    stable buffers; after `min_hits` eager executions of a signature the body is captured once (inputs
+    copied into static buffers first) and from then on replayed — ~500 ctypes launches per frame become
+    four cudaGraphLaunch calls.  Per-step variation that is not a tensor input (which stored frames make
+    up the memory bank, pointer distances) lives in a device-resident table the kernels read
+    (ds2_bank_assemble), never in launch arguments."""
+
+    def __init__(self, device, enabled=True, min_hits=2, max_graphs=96):
+        self.device, self.enabled, self.min_hits, self.max_graphs = device, enabled, min_hits, max_graphs
+        self.hits = {}
+        self.graphs = {}   # key -> (CUDAGraph, static_inputs, outputs)
+        self.pool = None
+        self.replays = 0
+        self.captures = 0
+        self.captured_launches = 0   # C-ABI launches recorded into graphs (they did not execute then)
+        self.replayed_launches = 0   # kernel nodes executed by graph replays
+
+    def run(self, key, inputs, body, clone):
+        """inputs: {name: tensor}; body(inputs_dict) -> tuple of tensors; clone: tuple of bools (copy the
+        output out of the graph's static storage because the caller keeps it beyond the next replay)."""
+        if not self.enabled:
+            return body({k: v.to(self.device, non_blocking=True) for k, v in inputs.items()})
+        g = self.graphs.get(key)
+        if g is None:
+            n = self.hits.get(key, 0) + 1
+            self.hits[key] = n
+            if n <= self.min_hits or len(self.graphs) >= self.max_graphs:
+                if len(self.hits) > 4096:
+                    self.hits.clear()
+                return body({k: v.to(self.device, non_blocking=True) for k, v in inputs.items()})
+            static = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in inputs.items()}
+            for k, v in inputs.items():
+                static[k].copy_(v, non_blocking=True)
+            body(static)  # eager on the static buffers: workspaces, TMA descriptors, func attributes exist
+            torch.cuda.current_stream().synchronize()
+            graph = torch.cuda.CUDAGraph()
+            if self.pool is None:
+                self.pool = torch.cuda.graph_pool_handle()
+            l0 = ops.launch_count()
+            with torch.cuda.graph(graph, pool=self.pool):
+                outs = body(static)
+            nodes = ops.launch_count() - l0
+            self.captured_launches += nodes
+            g = (graph, static, outs, nodes)
+            self.graphs[key] = g
+            self.captures += 1
+        graph, static, outs, nodes = g
+        for k, v in inputs.items():
+            static[k].copy_(v, non_blocking=True)
+        graph.replay()
+        self.replays += 1
+        self.replayed_launches += nodes
+        return tuple(o.clone() if c else o for o, c in zip(outs, clone))
+
+
+class _TableRing:
+    """Per-step bank tables: a small ring of pinned host buffers (so the CPU can run ahead of the GPU
+    without overwriting a table whose H2D copy has not executed yet) and ONE device buffer with a fixed
+    address that the captured bank kernels read."""
+    MAXF, MAXP = 128, 64
+    OFF_FSRC, OFF_PSRC = 0, 8 * 128
+    OFF_TPOS = OFF_PSRC + 8 * 64
+    OFF_DIST = OFF_TPOS + 4 * 128
+    NBYTES = OFF_DIST + 4 * 64
+
+    def __init__(self, device, slots=16):
+        self.host = [torch.empty(self.NBYTES, dtype=torch.uint8).pin_memory() for _ in range(slots)]
+        self.events = [None] * slots
+        self.i = 0
+        self.dev = torch.zeros(self.NBYTES, dtype=torch.uint8, device=device)
+        base = self.dev.data_ptr()
+        self.fsrc, self.psrc = base + self.OFF_FSRC, base + self.OFF_PSRC
+        self.tpos, self.dist = base + self.OFF_TPOS, base + self.OFF_DIST
+
+    def upload(self, frame_ptrs, frame_tpos, ptr_ptrs, ptr_dist):
+        nf, npt = len(frame_ptrs), len(ptr_ptrs)
+        if nf > self.MAXF or npt > self.MAXP:
+            raise Ds2Error(f"memory bank of {nf} frames / {npt} pointers exceeds the table capacity")
+        i = self.i
+        self.i = (i + 1) % len(self.host)
+        if self.events[i] is not None:
+            self.events[i].synchronize()
+        h = self.host[i].numpy()
+        h[self.OFF_FSRC:self.OFF_FSRC + 8 * nf].view(np.int64)[:] = frame_ptrs
+        h[self.OFF_PSRC:self.OFF_PSRC + 8 * npt].view(np.int64)[:] = ptr_ptrs
+        h[self.OFF_TPOS:self.OFF_TPOS + 4 * nf].view(np.int32)[:] = frame_tpos
+        h[self.OFF_DIST:self.OFF_DIST + 4 * npt].view(np.float32)[:] = ptr_dist
+        self.dev.copy_(self.host[i], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[i] = ev
+
+
 class FrameFeats:
     """Backbone outputs of one frame (what the reference keeps in cached_features, svp:1190)."""
     __slots__ = ("vis_f32", "vis_bf16", "feat_s0", "feat_s1", "pix_proj")
@@ -79,7 +176,7 @@ class FrameFeats:
 class CudaEngine:
     name = "cuda-sm100a"
 
-    def __init__(self, cfg, state_dict, device="cuda"):
+    def __init__(self, cfg, state_dict, device="cuda", use_graphs=True):
         if not torch.cuda.is_available():
             raise Ds2Error("CudaEngine needs a CUDA device: the hot path has no CPU implementation")
         ops._lib()  # raises if libdetsam2.so cannot be loaded / built
@@ -89,8 +186,17 @@ class CudaEngine:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self._ws = {}
         # bench.py sets this to a list to collect (tag, start_event, end_event, meta) of the dominant kernel
+        # (CUDA events cannot bracket a node inside a replayed graph, so that seam then runs eagerly)
         self.kernel_timers = None
+        with torch.cuda.device(self.device):
+            self.graphs = _SeamGraphs(self.device, enabled=(use_graphs and os.environ.get("DS2_GRAPHS", "1") != "0"))
+            self._tables = _TableRing(self.device)
         self._pack(state_dict)
+
+    def launches_executed(self):
+        """Kernels of libdetsam2.so that have executed on the device so far: eager C-ABI launches plus
+        the kernel nodes of every graph replay (launches recorded during capture did not execute)."""
+        return ops.launch_count() - self.graphs.captured_launches + self.graphs.replayed_launches
 
     # ---------------------------------------------------------------------------------------------
     # weights
@@ -289,6 +395,22 @@ class CudaEngine:
             self._ws[key] = t
         return t
 
+    def _buf_rows(self, name, B, rows, cols, dtype, min_rows):
+        """[B, rows, cols] view of a capacity-allocated workspace whose base address does not depend on
+        `rows` (the number of memory tokens changes from step to step while the bank fills up; captured
+        graphs of every bank size then share one buffer).  Buffers only ever grow by adding a new one —
+        an address that a captured graph uses is never freed."""
+        key = ("rows", name, B, cols, dtype)
+        lst = self._ws.setdefault(key, [])
+        for cap, t in lst:
+            if cap >= rows:
+                return t[: B * rows * cols].view(B, rows, cols)
+        cap = max(rows, min_rows)
+        t = torch.empty(B * cap * cols, dtype=dtype, device=self.device)
+        lst.append((cap, t))
+        lst.sort(key=lambda e: e[0])
+        return t[: B * rows * cols].view(B, rows, cols)
+
     # ---------------------------------------------------------------------------------------------
     # seam 1: image encoder
     # ---------------------------------------------------------------------------------------------
@@ -297,7 +419,14 @@ class CudaEngine:
         S = cfg.image_size
         if image_f16.dtype != torch.float16 or tuple(image_f16.shape) != (3, S, S):
             raise Ds2Error(f"encode_image expects an fp16 [3,{S},{S}] frame, got {image_f16.dtype} {tuple(image_f16.shape)}")
-        img = image_f16.to(self.device, non_blocking=True).contiguous()
+        vis, vis16, feat_s0, feat_s1 = self.graphs.run(("enc",), {"img": image_f16.contiguous()},
+                                                       self._encode_image_body, (True, True, True, True))
+        return FrameFeats(vis, vis16, feat_s0, feat_s1)
+
+    def _encode_image_body(self, inp):
+        cfg, p = self.cfg, self.p
+        S = cfg.image_size
+        img = inp["img"]
         Hc = Wc = S // 4
         T = Hc * Wc
         E = cfg.embed_dim
@@ -366,7 +495,7 @@ class CudaEngine:
         ops.gemm(s2, p["s1.w"], bias=p["s1.b"], out_f32=feat_s1)
         feat_s0 = torch.empty((h1 * w1_, 32), dtype=F32, device=self.device)
         ops.gemm(s1, p["s0.w"], bias=p["s0.b"], out_f32=feat_s0)
-        return FrameFeats(vis, vis16, feat_s0, feat_s1)
+        return vis, vis16, feat_s0, feat_s1
 
     # ---------------------------------------------------------------------------------------------
     # seam 2: memory attention over the bank
@@ -386,17 +515,15 @@ class CudaEngine:
         T = cfg.feat_size * cfg.feat_size
         D, M = cfg.hidden_dim, cfg.mem_dim
         if is_init_cond_frame:
-            # directly_add_no_mem_embed (sam2_base.py:651-657)
-            out = torch.empty((1, T, D), dtype=F32, device=self.device)
+            # directly_add_no_mem_embed (sam2_base.py:651-657); a workspace (stable address) so that the
+            # decoder graph of the B sequential box prompts of a detection frame can be replayed
+            out = self._buf("init_pix", (1, T, D), F32)
             ops.axpby(feats.vis_f32, p["no_mem_embed"], 1.0, 1.0, b_row_mod=1, out_f32=out.view(T, D))
             return out if B == 1 else out.expand(B, T, D).contiguous()
         plan = plan_memory(frame_idx, output_dict, num_frames, reverse, preload_idx, cfg.num_maskmem,
                            cfg.max_cond_frames_in_attn, cfg.max_obj_ptrs_in_encoder)
-        n_ptr_tok = 4 * len(plan.ptrs)
-        N = len(plan.frames) * T + n_ptr_tok
-        kin = self._buf("bank_kin", (B, N, M), BF16)
-        val = self._buf("bank_val", (B, N, M), BF16)
-        row = 0
+        keep = []  # temporaries whose addresses are in the table
+        fptr, ftpos, pptr, pdist = [], [], [], []
         for tpos_idx, out in plan.frames:
             mf = out["maskmem_features"]
             if mf.shape[0] != B:
@@ -404,19 +531,39 @@ class CudaEngine:
             mem = self._token_major(mf.to(self.device, non_blocking=True), B, T, M)
             if mem.dtype != BF16:
                 mem = mem.to(BF16)
-            ops.bank_gather(mem, p["maskmem_pos"], p["maskmem_tpos"][tpos_idx], kin, val, B, T, M, N * M, row)
-            row += T
+            keep.append(mem)
+            fptr.append(mem.data_ptr())
+            ftpos.append(tpos_idx)
         for dist, out in plan.ptrs:
             ptr = out["obj_ptr"]
             if ptr.shape[0] != B:
                 raise RuntimeError(f"object pointer of a stored frame has batch {ptr.shape[0]}, expected {B}")
             ptr = ptr.to(self.device, dtype=F32).contiguous()
-            ops.bank_ptr_pe(ptr, dist / plan.t_diff_max, p["ptr_tpos.w"], p["ptr_tpos.b"], kin, val, B, N * M, row)
-            row += 4
-        assert row == N
+            keep.append(ptr)
+            pptr.append(ptr.data_ptr())
+            pdist.append(dist / plan.t_diff_max)
+        self._tables.upload(fptr, ftpos, pptr, pdist)
+        nf, npt = len(fptr), len(pptr)
+        body = lambda inp: self._memory_attention_body(inp, B, nf, npt)  # noqa: E731
+        if self.kernel_timers is not None:
+            return body({"vis": feats.vis_f32})[0]
+        return self.graphs.run(("ma", B, nf, npt), {"vis": feats.vis_f32}, body, (False,))[0]
+
+    def _memory_attention_body(self, inp, B, nf, npt):
+        cfg, p = self.cfg, self.p
+        T = cfg.feat_size * cfg.feat_size
+        D, M = cfg.hidden_dim, cfg.mem_dim
+        n_ptr_tok = 4 * npt
+        N = nf * T + n_ptr_tok
+        cap = (cfg.num_maskmem + 1) * T + 4 * cfg.max_obj_ptrs_in_encoder
+        kin = self._buf_rows("bank_kin", B, N, M, BF16, cap)
+        val = self._buf_rows("bank_val", B, N, M, BF16, cap)
+        tb = self._tables
+        ops.bank_assemble(tb.fsrc, tb.tpos, nf, tb.psrc, tb.dist, npt, p["maskmem_pos"], p["maskmem_tpos"],
+                          p["ptr_tpos.w"], p["ptr_tpos.b"], kin, val, B, T, M)
         # x = curr + 0.1 * curr_pos, identical for every object at the input (memory_attention.py:139-141)
         x1 = self._buf("ma_x1", (T, D), F32)
-        ops.axpby(feats.vis_f32, p["vision_pos"], 1.0, 0.1, out_f32=x1)
+        ops.axpby(inp["vis"], p["vision_pos"], 1.0, 0.1, out_f32=x1)
         x = self._buf("ma_x", (B, T, D), F32)
         x.copy_(x1.unsqueeze(0).expand(B, T, D))
         x2 = x.view(B * T, D)
@@ -424,7 +571,7 @@ class CudaEngine:
         qkv = self._buf("ma_qkv", (B * T, 3 * D), BF16)
         att = self._buf("ma_att", (B, T, D), BF16)
         q16 = self._buf("ma_q", (B, T, D), BF16)
-        k16 = self._buf("ma_k", (B, N, D), BF16)
+        k16 = self._buf_rows("ma_k", B, N, D, BF16, cap)
         o64 = self._buf("ma_o64", (B, T, M), BF16)
         hff = self._buf("ma_ff", (B * T, cfg.memattn_ffn), BF16)
         rope = p["rope"]
@@ -454,7 +601,7 @@ class CudaEngine:
             ops.gemm(hff, p[w + "ff2.w"], bias=p[w + "ff2.b"], residual=x2, out_f32=x2)
         out = torch.empty((B, T, D), dtype=F32, device=self.device)
         ops.layernorm(x2, p["ma.norm.w"], p["ma.norm.b"], 1e-5, out_f32=out.view(B * T, D))
-        return out
+        return (out,)
 
     # ---------------------------------------------------------------------------------------------
     # seam 3: prompt encoder + mask decoder + selection epilogue
@@ -477,26 +624,49 @@ class CudaEngine:
                 "on the Det-SAM2 streaming path and are not implemented by the CUDA engine yet")
         T = cfg.feat_size * cfg.feat_size
         D = cfg.hidden_dim
-        Dh = D // 2
-        H = cfg.decoder_heads
         pix = pix_feat.reshape(B * T, D)
         if not pix.is_contiguous():
             pix = pix.contiguous()
-        P = 0
-        coords = labels = None
         if point_coords is not None:
             P = point_coords.shape[1]
-            coords = point_coords.to(self.device, dtype=F32).contiguous()
-            labels = point_labels.to(self.device, dtype=torch.int32).contiguous()
+            coords = point_coords.to(dtype=F32)
+            labels = point_labels.to(dtype=torch.int32)
             if coords.shape[0] != B:
                 raise Ds2Error("point prompts must have one row per object")
         else:
             # no prompt: one padding point with label -1 (sam2_base.py:302-304) + the pad point
             P = 1
-            coords = self._buf("nopt_c", (B, 1, 2), F32)
-            labels = self._buf("nopt_l", (B, 1), torch.int32)
-            coords.zero_()
-            labels.fill_(-1)
+            coords, labels = self._noprompt(B)
+        mm = bool(multimask_output)
+        body = lambda inp: self._sam_heads_body(inp, pix, B, P, mm)  # noqa: E731
+        low, iou_out, obj_ptr, score = self.graphs.run(
+            ("sam", B, P, mm, pix.data_ptr()),
+            {"coords": coords, "labels": labels, "s0": feats.feat_s0, "s1": feats.feat_s1}, body,
+            (True, True, True, True))
+        nt = 6 + P + 1
+        S4 = 4 * cfg.feat_size
+        # "_"-prefixed entries are workspace views for tests / diagnostics (valid until the next call)
+        return {"pred_masks": low, "ious": iou_out, "obj_ptr": obj_ptr, "object_score_logits": score,
+                "_all_masks": self._buf("dec_masks", (B, 4, S4, S4), F32), "_all_ious": self._buf("dec_ious", (B, 4), F32),
+                "_best_idx": self._buf("dec_best", (B,), torch.int32)}
+
+    def _noprompt(self, B):
+        key = ("noprompt", B)
+        v = self._ws.get(key)
+        if v is None:
+            v = (torch.zeros((B, 1, 2), dtype=F32, device=self.device),
+                 torch.full((B, 1), -1, dtype=torch.int32, device=self.device))
+            self._ws[key] = v
+        return v
+
+    def _sam_heads_body(self, inp, pix, B, P, multimask_output):
+        cfg, p = self.cfg, self.p
+        T = cfg.feat_size * cfg.feat_size
+        D = cfg.hidden_dim
+        Dh = D // 2
+        H = cfg.decoder_heads
+        coords, labels = inp["coords"].contiguous(), inp["labels"].contiguous()
+        feat_s0, feat_s1 = inp["s0"], inp["s1"]
         nt = 6 + P + 1
         R = B * nt
         qpe = self._buf("dec_qpe", (R, D), F32)
@@ -580,12 +750,12 @@ class CudaEngine:
         g1 = self._buf("dec_g1", (B * T, 4 * 64), F32)
         ops.gemm(keys16, p["up0.w"], out_f32=g1)
         y1 = self._buf("dec_y1", (B * 4 * T, 64), BF16)
-        ops.upscale1(g1, p["up0.b"], feats.feat_s1, p["up0.ln.w"], p["up0.ln.b"], y1, B, fs, fs, 64)
+        ops.upscale1(g1, p["up0.b"], feat_s1, p["up0.ln.w"], p["up0.ln.b"], y1, B, fs, fs, 64)
         g2 = self._buf("dec_g2", (B * 4 * T, 4 * 32), F32)
         ops.gemm(y1, p["up1.w"], out_f32=g2)
         S4 = 4 * fs
         masks = self._buf("dec_masks", (B, 4, S4, S4), F32)
-        ops.upscale2_masks(g2, p["up1.b"], feats.feat_s0, hyper, masks, B, 2 * fs, 2 * fs, 32, 4)
+        ops.upscale2_masks(g2, p["up1.b"], feat_s0, hyper, masks, B, 2 * fs, 2 * fs, 32, 4)
         mtok = hs.view(B, nt, D)[:, 2:6].contiguous()
         low = torch.empty((B, 1, S4, S4), dtype=F32, device=self.device)
         iou_out = torch.empty((B, 1), dtype=F32, device=self.device)
@@ -597,9 +767,7 @@ class CudaEngine:
         ops.mlp3(tok, p["objptr.w1"], p["objptr.b1"], p["objptr.w2"], p["objptr.b2"], p["objptr.w3"], p["objptr.b3"],
                  obj_ptr, rows=B, nmlp=1)
         ops.objptr_mix(obj_ptr, score, p["no_obj_ptr"], B, D)
-        # "_"-prefixed entries are workspace views for tests / diagnostics (valid until the next call)
-        return {"pred_masks": low, "ious": iou_out, "obj_ptr": obj_ptr, "object_score_logits": score,
-                "_all_masks": masks, "_all_ious": ious, "_best_idx": best}
+        return low, iou_out, obj_ptr, score
 
     def mask_as_output(self, feats, mask_inputs):
         """sam2_base.py:399-448.  Only the all-zero mask is needed on the Det-SAM2 path
@@ -625,13 +793,25 @@ class CudaEngine:
         T = fs * fs
         D, M = cfg.hidden_dim, cfg.mem_dim
         Sl = 4 * fs
-        low = pred_masks_low_res.to(self.device, dtype=F32).reshape(B, Sl, Sl).contiguous()
-        score = object_score_logits.to(self.device, dtype=F32).reshape(B).contiguous()
+        low = pred_masks_low_res.to(dtype=F32).reshape(B, Sl, Sl)
+        score = object_score_logits.to(dtype=F32).reshape(B)
         binarize = bool(cfg.binarize_mask_from_pts_for_mem_enc and is_mask_from_pts)
-        if feats.pix_proj is None:
-            pp = torch.empty((T, D), dtype=F32, device=self.device)
-            ops.gemm(feats.vis_bf16, p["pixproj.w"], bias=p["pixproj.b"], out_f32=pp)
-            feats.pix_proj = pp
+        body = lambda inp: self._encode_memory_body(inp, B, binarize)  # noqa: E731
+        (mem,) = self.graphs.run(("me", B, binarize), {"vis16": feats.vis_bf16, "low": low, "score": score}, body,
+                                 (True,))
+        maskmem = mem.view(B, fs, fs, M).permute(0, 3, 1, 2)  # [B,64,h,w] view, channels-last storage
+        pos = p["maskmem_pos"].view(1, fs, fs, M).permute(0, 3, 1, 2).expand(B, -1, -1, -1)
+        return maskmem, [pos]
+
+    def _encode_memory_body(self, inp, B, binarize):
+        cfg, p = self.cfg, self.p
+        fs = cfg.feat_size
+        T = fs * fs
+        D, M = cfg.hidden_dim, cfg.mem_dim
+        Sl = 4 * fs
+        low, score = inp["low"].contiguous(), inp["score"].contiguous()
+        pix_proj = self._buf("me_pixproj", (T, D), F32)
+        ops.gemm(inp["vis16"], p["pixproj.w"], bias=p["pixproj.b"], out_f32=pix_proj)
         m1 = self._buf("me_m1", (B, 2 * Sl, 2 * Sl, 4), BF16)
         ops.maskds_stage1(low, B, Sl, binarize, cfg.sigmoid_scale_for_mem_enc, cfg.sigmoid_bias_for_mem_enc,
                           p["md0.w"], p["md0.b"], p["md0.ln.w"], p["md0.ln.b"], m1)
@@ -650,7 +830,7 @@ class CudaEngine:
         m4 = self._buf("me_m4", (B * T, D), BF16)
         ops.layernorm(g4, p["md3.ln.w"], p["md3.ln.b"], 1e-6, act=2, out_bf16=m4)
         x = self._buf("me_x", (B * T, D), F32)
-        ops.gemm(m4, p["md4.w"], bias=p["md4.b"], residual=feats.pix_proj, res_row_mod=T, out_f32=x)
+        ops.gemm(m4, p["md4.w"], bias=p["md4.b"], residual=pix_proj, res_row_mod=T, out_f32=x)
         dw = self._buf("me_dw", (B * T, D), F32)
         t16 = self._buf("me_t16", (B * T, D), BF16)
         h = self._buf("me_h", (B * T, 4 * D), BF16)
@@ -665,9 +845,7 @@ class CudaEngine:
         ops.gemm(t16, p["memout.w"], bias=p["memout.b"], out_f32=o)
         mem = torch.empty((B, T, M), dtype=BF16, device=self.device)
         ops.memenc_finish(o, score, p["no_obj_embed_spatial"], mem, B, T, M)
-        maskmem = mem.view(B, fs, fs, M).permute(0, 3, 1, 2)  # [B,64,h,w] view, channels-last storage
-        pos = p["maskmem_pos"].view(1, fs, fs, M).permute(0, 3, 1, 2).expand(B, -1, -1, -1)
-        return maskmem, [pos]
+        return (mem,)
 
     # ---------------------------------------------------------------------------------------------
     # seam 5: post-processing

@@ -222,6 +222,14 @@ def bank_ptr_pe(ptr, dist_norm, w, bias, kin, val, B, dst_bs, row0):
                                 _stream()), "ds2_bank_ptr_pe")
 
 
+def bank_assemble(frame_src, frame_tpos, nf, ptr_src, ptr_dist, np_, pos, tpos_table, ptr_w, ptr_bias, kin, val, B, T,
+                  Cc):
+    """frame_src / frame_tpos / ptr_src / ptr_dist are DEVICE addresses (ints) of the per-step tables."""
+    _chk(_lib().ds2_bank_assemble(C.c_void_p(frame_src), C.c_void_p(frame_tpos), nf, C.c_void_p(ptr_src),
+                                  C.c_void_p(ptr_dist), np_, _p(pos), _p(tpos_table), _p(ptr_w), _p(ptr_bias),
+                                  _p(kin), _p(val), B, T, Cc, _stream()), "ds2_bank_assemble")
+
+
 def memenc_finish(x, score, no_obj_embed, out, B, T, Cc):
     _chk(_lib().ds2_memenc_finish(_p(x), _p(score), _p(no_obj_embed), _p(out), B, T, Cc, _stream()),
          "ds2_memenc_finish")

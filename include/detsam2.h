@@ -213,6 +213,16 @@ int ds2_prompt_tokens(const float* coords, const int32_t* labels, int32_t B, int
  * sam2_utils.py:69-79): tpos = W[64,256] . sine1d(dist_norm, 256) + bias                        */
 int ds2_bank_ptr_pe(const float* ptr, float dist_norm, const float* w, const float* bias, void* kin_bf16,
                     void* val_bf16, int32_t B, int64_t dst_bs, int32_t row0, void* stream);
+/* whole-bank assembly from DEVICE-resident tables (graph-replay friendly: every launch argument is
+ * static, the per-step variation lives in the tables).  frame_src[f] -> bf16 [B,T,C] memory of stored
+ * frame f, frame_tpos[f] = row of tpos_table ([num_maskmem, C]); ptr_src[j] -> f32 [B,256] pointer,
+ * ptr_dist[j] = signed temporal distance / (max_obj_ptrs - 1).  Output rows: nf*T memory tokens
+ * then 4*np pointer tokens; kin/val bf16 [B, nf*T + 4*np, C].  Replaces the torch.cat / flatten /
+ * permute / get_1d_sine_pe / obj_ptr_tpos_proj chain of sam2_base.py:564-650.                    */
+int ds2_bank_assemble(const void* const* frame_src, const int32_t* frame_tpos, int32_t nf,
+                      const float* const* ptr_src, const float* ptr_dist, int32_t np, const float* pos,
+                      const float* tpos_table, const float* ptr_w, const float* ptr_bias, void* kin_bf16,
+                      void* val_bf16, int32_t B, int32_t T, int32_t C, void* stream);
 /* memory-encoder tail (sam2_base.py:733-741, sam2_video_predictor.py:1337):
  * out bf16 [B,T,C] = x + (1 - [score_b > 0]) * no_obj_embed                                      */
 int ds2_memenc_finish(const float* x, const float* score, const float* no_obj_embed, void* out_bf16,

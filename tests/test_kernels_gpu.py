@@ -518,3 +518,37 @@ def test_connected_components_and_fill_holes(ops):
     assert (scores.cpu().numpy() == exp).all()
     with pytest.raises(Exception):
         ops.connected_components(torch.zeros(1, 1, 5, 4, dtype=torch.uint8, device=DEV))
+
+
+def test_bank_assemble_matches_per_frame_gather(ops):
+    """Table-driven whole-bank assembly == the per-frame gather + per-pointer kernels it replaces."""
+    import numpy as np
+    torch.manual_seed(5)
+    B, T, C, nf, npt = 3, 256, 64, 4, 5
+    mems = [torch.randn(B, T, C, device=DEV).bfloat16() for _ in range(nf)]
+    ptrs = [torch.randn(B, 256, device=DEV) for _ in range(npt)]
+    tidx = [6, 0, 3, 5]
+    dist = [0.0, 1 / 15, -3 / 15, 7 / 15, 1.0]
+    pos = torch.randn(T, C, device=DEV)
+    tpos = torch.randn(7, C, device=DEV)
+    w = torch.randn(64, 256, device=DEV) / 16
+    bias = torch.randn(64, device=DEV) * 0.1
+    N = nf * T + 4 * npt
+    kin_ref = torch.zeros(B, N, C, device=DEV, dtype=torch.bfloat16)
+    val_ref = torch.zeros_like(kin_ref)
+    for f in range(nf):
+        ops.bank_gather(mems[f], pos, tpos[tidx[f]], kin_ref, val_ref, B, T, C, N * C, f * T)
+    for j in range(npt):
+        ops.bank_ptr_pe(ptrs[j], dist[j], w, bias, kin_ref, val_ref, B, N * C, nf * T + 4 * j)
+    tab_f = torch.tensor([m.data_ptr() for m in mems], dtype=torch.int64, device=DEV)
+    tab_t = torch.tensor(tidx, dtype=torch.int32, device=DEV)
+    tab_p = torch.tensor([p.data_ptr() for p in ptrs], dtype=torch.int64, device=DEV)
+    tab_d = torch.tensor(dist, dtype=torch.float32, device=DEV)
+    kin = torch.zeros_like(kin_ref)
+    val = torch.zeros_like(kin_ref)
+    ops.bank_assemble(tab_f.data_ptr(), tab_t.data_ptr(), nf, tab_p.data_ptr(), tab_d.data_ptr(), npt, pos, tpos, w, bias,
+                      kin, val, B, T, C)
+    assert torch.equal(kin, kin_ref) and torch.equal(val, val_ref)
+    # reference semantics (sam2_base.py:564-650) in fp32
+    exp = mems[1].float() + pos[None] + tpos[0][None, None]
+    assert (kin[:, T:2 * T].float() - exp).abs().max().item() < 0.04
