@@ -108,12 +108,14 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, const uint32_
   if (p.rope_cs && col0 >= p.rope_col0 && col0 < p.rope_col1) {
     const int rb = row % p.rope_rows_per_batch;
     if (rb < p.rope_row_limit) {
+      // table is pair-major [128][period]: the 32 lanes of a warp (= 32 consecutive rows = consecutive
+      // positions) read 256 contiguous bytes per pair instead of 32 different table rows
       const int pos = rb % p.rope_period;
-      const float2* cs = reinterpret_cast<const float2*>(p.rope_cs) + static_cast<size_t>(pos) * 128 +
-                         (((col0 - p.rope_col0) & 255) >> 1);
+      const float2* cs = reinterpret_cast<const float2*>(p.rope_cs) +
+                         static_cast<size_t>(((col0 - p.rope_col0) & 255) >> 1) * p.rope_period + pos;
 #pragma unroll
       for (int i = 0; i < NC / 2; ++i) {
-        const float2 c = __ldg(cs + i);
+        const float2 c = __ldg(cs + static_cast<size_t>(i) * p.rope_period);
         const float a = v[2 * i], b = v[2 * i + 1];
         v[2 * i] = a * c.x - b * c.y;
         v[2 * i + 1] = a * c.y + b * c.x;
@@ -455,8 +457,8 @@ __global__ void gemm_bf16_simt_kernel(const __nv_bfloat16* __restrict__ A, long 
       const int rb = row % p.rope_rows_per_batch;
       if (rb < p.rope_row_limit) {
         const int pos = rb % p.rope_period;
-        const float2 c = reinterpret_cast<const float2*>(p.rope_cs)[static_cast<size_t>(pos) * 128 +
-                                                                   (((col - p.rope_col0) & 255) >> 1)];
+        const float2 c = reinterpret_cast<const float2*>(p.rope_cs)[static_cast<size_t>(((col - p.rope_col0) & 255) >> 1) *
+                                                                       p.rope_period + pos];
         const float a = v[0], b = v[1];
         v[0] = a * c.x - b * c.y;
         v[1] = a * c.y + b * c.x;

@@ -78,7 +78,7 @@ __device__ __forceinline__ void cp_async_wait() {
 // NW warps = 16*NW query rows per CTA; K/V chunks of 64 keys are double-buffered with cp.async so the
 // loads of chunk j+1 overlap the MMAs of chunk j.
 template <int DP, int NW>
-__global__ void __launch_bounds__(32 * NW) mha_kernel(const MhaParams p) {
+__global__ void __launch_bounds__(32 * NW, (DP <= 96 ? (NW == 8 ? 2 : 4) : 1)) mha_kernel(const MhaParams p) {
   constexpr int QS = DP + 8;   // smem row stride (elements) for Q / K / V tiles (conflict-free for ldmatrix)
   constexpr int QT = 16 * NW;  // query rows per CTA
   constexpr int NT = 32 * NW;  // threads

@@ -51,12 +51,13 @@ def _sine_pe_2d(num_pos_feats_total, h, w, temperature=10000.0):
 
 
 def _rope_table(dim, side, theta):
-    """position_encoding.py:173-182 as interleaved (cos, sin) [side*side, dim/2, 2]."""
+    """position_encoding.py:173-182 as interleaved (cos, sin), pair-major [dim/2, side*side, 2] (the GEMM
+    epilogue's lanes walk consecutive positions, so position is the fast axis)."""
     fr = 1.0 / (theta ** (torch.arange(0, dim, 4)[: dim // 4].float() / dim))
     t = torch.arange(side * side, dtype=F32)
     tx, ty = (t % side).float(), torch.div(t, side, rounding_mode="floor").float()
     ang = torch.cat([torch.outer(tx, fr), torch.outer(ty, fr)], dim=-1)
-    return torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()
+    return torch.stack([ang.cos(), ang.sin()], dim=-1).permute(1, 0, 2).contiguous()
 
 
 def _dense_pe(gauss, side):
@@ -561,11 +562,13 @@ class CudaEngine:
         tb = self._tables
         ops.bank_assemble(tb.fsrc, tb.tpos, nf, tb.psrc, tb.dist, npt, p["maskmem_pos"], p["maskmem_tpos"],
                           p["ptr_tpos.w"], p["ptr_tpos.b"], kin, val, B, T, M)
-        # x = curr + 0.1 * curr_pos, identical for every object at the input (memory_attention.py:139-141)
+        # x = curr + 0.1 * curr_pos is identical for every object at the input (memory_attention.py:139-141),
+        # so everything of layer 0 that precedes the first look at the per-object bank — LN1, self-attention,
+        # its residual, LN2 and the cross-attention query projection — is computed ONCE and broadcast to the
+        # B objects (same arithmetic per row, 1/B of the work)
         x1 = self._buf("ma_x1", (T, D), F32)
         ops.axpby(inp["vis"], p["vision_pos"], 1.0, 0.1, out_f32=x1)
         x = self._buf("ma_x", (B, T, D), F32)
-        x.copy_(x1.unsqueeze(0).expand(B, T, D))
         x2 = x.view(B * T, D)
         t16 = self._buf("ma_t", (B * T, D), BF16)
         qkv = self._buf("ma_qkv", (B * T, 3 * D), BF16)
@@ -576,15 +579,23 @@ class CudaEngine:
         hff = self._buf("ma_ff", (B * T, cfg.memattn_ffn), BF16)
         rope = p["rope"]
         scale = 1.0 / math.sqrt(D)
-        qkv3 = qkv.view(B, T, 3 * D)
         for l in range(cfg.memattn_layers):
             w = f"ma{l}."
-            ops.layernorm(x2, p[w + "n1.w"], p[w + "n1.b"], 1e-5, out_bf16=t16)
-            ops.gemm(t16, p[w + "sa_qkv.w"], bias=p[w + "sa_qkv.b"], out_bf16=qkv, rope=(rope, 0, 2 * D, T, T))
-            ops.flash_attn(qkv3[:, :, :D], qkv3[:, :, D:2 * D], qkv3[:, :, 2 * D:], att, scale)
-            ops.gemm(att.view(B * T, D), p[w + "sa_out.w"], bias=p[w + "sa_out.b"], residual=x2, out_f32=x2)
-            ops.layernorm(x2, p[w + "n2.w"], p[w + "n2.b"], 1e-5, out_bf16=t16)
-            ops.gemm(t16, p[w + "ca_q.w"], bias=p[w + "ca_q.b"], out_bf16=q16.view(B * T, D), rope=(rope, 0, D, T, T))
+            # rows of the shared prefix: one object's worth in layer 0, all objects afterwards
+            Bs = 1 if l == 0 else B
+            xs = x1 if l == 0 else x2
+            R = Bs * T
+            qkv3 = qkv[:R].view(Bs, T, 3 * D)
+            ops.layernorm(xs, p[w + "n1.w"], p[w + "n1.b"], 1e-5, out_bf16=t16[:R])
+            ops.gemm(t16[:R], p[w + "sa_qkv.w"], bias=p[w + "sa_qkv.b"], out_bf16=qkv[:R], rope=(rope, 0, 2 * D, T, T))
+            ops.flash_attn(qkv3[:, :, :D], qkv3[:, :, D:2 * D], qkv3[:, :, 2 * D:], att[:Bs], scale)
+            ops.gemm(att[:Bs].view(R, D), p[w + "sa_out.w"], bias=p[w + "sa_out.b"], residual=xs, out_f32=xs)
+            ops.layernorm(xs, p[w + "n2.w"], p[w + "n2.b"], 1e-5, out_bf16=t16[:R])
+            ops.gemm(t16[:R], p[w + "ca_q.w"], bias=p[w + "ca_q.b"], out_bf16=q16[:Bs].view(R, D), rope=(rope, 0, D, T, T))
+            if l == 0:
+                x.copy_(x1.unsqueeze(0).expand(B, T, D))
+                if B > 1:
+                    q16[1:].copy_(q16[:1].expand(B - 1, T, D))
             ops.gemm(kin.view(B * N, M), p[w + "ca_k.w"], bias=p[w + "ca_k.b"], out_bf16=k16.view(B * N, D),
                      rope=(rope, 0, D, N, N - n_ptr_tok))
             if self.kernel_timers is not None:

@@ -41,7 +41,7 @@ def _req(t, dtype, name):
 def gemm(a, w, *, bias=None, act=0, gamma=None, residual=None, res_row_mod=0, out_f32=None, out_bf16=None,
          rope=None, impl=0):
     """out = epilogue(a @ w.T).  a [M,K] bf16 (row-strided ok), w [N,K] bf16.
-    rope = (cs [P,128,2] f32, col0, col1, rows_per_batch, row_limit)."""
+    rope = (cs [128,P,2] f32 (pair-major), col0, col1, rows_per_batch, row_limit)."""
     _req(a, BF16, "gemm.a"); _req(w, BF16, "gemm.w"); _req(bias, F32, "gemm.bias")
     _req(gamma, F32, "gemm.gamma"); _req(residual, F32, "gemm.residual")
     _req(out_f32, F32, "gemm.out_f32"); _req(out_bf16, BF16, "gemm.out_bf16")
@@ -65,7 +65,8 @@ def gemm(a, w, *, bias=None, act=0, gamma=None, residual=None, res_row_mod=0, ou
         cs, c0, c1, rpb, lim = rope
         _req(cs, F32, "gemm.rope_cs")
         g.rope_cs, g.rope_col0, g.rope_col1 = cs.data_ptr(), c0, c1
-        g.rope_period, g.rope_rows_per_batch, g.rope_row_limit = cs.shape[0], rpb, lim
+        assert cs.shape[0] == 128 and cs.is_contiguous()
+        g.rope_period, g.rope_rows_per_batch, g.rope_row_limit = cs.shape[1], rpb, lim
     g.impl = impl
     _chk(_lib().ds2_gemm(C.byref(g), _stream()), "ds2_gemm")
 

@@ -59,7 +59,7 @@ typedef struct ds2_gemm_args {
   void* out_bf16;        /* row pitch ldc_bf16, or NULL */
   int64_t ldc, ldc_bf16;
   /* rotary epilogue (RoPEAttention, sam/transformer.py:311-363; position_encoding.py:193-220) */
-  const float* rope_cs;  /* [rope_period][128][2] (cos, sin) or NULL */
+  const float* rope_cs;  /* [128][rope_period][2] (cos, sin), pair-major (position fastest), or NULL */
   int32_t rope_col0, rope_col1;   /* rotate columns c in [col0, col1); pair = ((c-col0) % 256)/2 */
   int32_t rope_period;            /* table rows; position = (row % rope_rows_per_batch) % period */
   int32_t rope_rows_per_batch;    /* rows per batch item */

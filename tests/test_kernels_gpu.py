@@ -102,7 +102,7 @@ def test_gemm_rope(ops):
     ang = torch.rand(64, 128, device=DEV) * 6.28
     cs = torch.stack([ang.cos(), ang.sin()], -1).contiguous()
     of = torch.empty(B * T, 768, device=DEV)
-    ops.gemm(a, w, out_f32=of, rope=(cs, 0, 512, T, T - 4))
+    ops.gemm(a, w, out_f32=of, rope=(cs.permute(1, 0, 2).contiguous(), 0, 512, T, T - 4))
     ref = a.float() @ w.float().t()
     rows = torch.arange(B * T, device=DEV) % T
     pos = rows % 64

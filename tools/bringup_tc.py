@@ -63,7 +63,8 @@ def gemm_case(M, N, K, impl=0, bias=True, act=0, gamma=False, residual=False, re
     a.ldc = N
     a.ldc_bf16 = N
     if rope:
-        a.rope_cs = cs.data_ptr()
+        cs_t = cs.permute(1, 0, 2).contiguous()  # pair-major table
+        a.rope_cs = cs_t.data_ptr()
         a.rope_col0, a.rope_col1 = 0, 256
         a.rope_period, a.rope_rows_per_batch = period, rows_per_batch
         a.rope_row_limit = rows_per_batch - 3
