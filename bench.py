@@ -177,8 +177,10 @@ def run_ours(args):
         if prof:
             torch.cuda.profiler.start()  # ncu --profile-from-start off: only the timed device steps
         e0.record()
+        h0 = time.perf_counter()
         for _ in range(K):
             step()
+        host_ms = (time.perf_counter() - h0) * 1e3   # CPU time to ENQUEUE the K steps (no sync inside)
         e1.record()
         barrier()
         if prof:
@@ -197,6 +199,7 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = t.item()
         results[mode] = ms
+        results[mode + "_host"] = host_ms
         del st, gen
     if rank != 0:
         if world > 1:
@@ -237,6 +240,7 @@ def run_ours(args):
         "e2e": {"value": round(fps_e2e, 3), "unit": UNIT, "h2d_bytes_per_step": 3 * S * S * 2,
                 "d2h_bytes_per_step": (B * S * S) // 8, "ms_per_step": round(results["e2e"] / K, 3),
                 "api": "SAM2VideoPredictor.propagate_in_video + bit-packed (mask > 0) D2H"},
+        "host_enqueue_ms_per_step": round(results["device_host"] / K, 3),
         "gpu_launches": int(launches),
         "launch_mode": f"{len(eng.graphs.graphs)} captured CUDA graphs (one per seam signature), {graph_replays} replays so far; "
                        f"gpu_launches counts kernel nodes executed by replays + eager C-ABI launches in the timed region",

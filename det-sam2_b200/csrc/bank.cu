@@ -16,6 +16,7 @@ bank_frames_kernel(const __nv_bfloat16* const* __restrict__ src, const int* __re
                    const float* __restrict__ pos, const float* __restrict__ tpos_table,
                    __nv_bfloat16* __restrict__ kin, __nv_bfloat16* __restrict__ val, int B, int T, int C,
                    long long dst_bs) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const int f = blockIdx.y;
   const __nv_bfloat16* __restrict__ mem = src[f];
   const float* __restrict__ tp_row = tpos_table + static_cast<long long>(tpos_idx[f]) * C;
@@ -50,6 +51,7 @@ bank_ptrs_kernel(const float* const* __restrict__ src, const float* __restrict__
                  const float* __restrict__ w /*[64,256]*/, const float* __restrict__ bias /*[64]*/,
                  __nv_bfloat16* __restrict__ kin, __nv_bfloat16* __restrict__ val, long long dst_bs,
                  long long row0) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   __shared__ float pe[256];
   __shared__ float tp[64];
   const int j = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
@@ -95,7 +97,7 @@ extern "C" int ds2_bank_assemble(const void* const* frame_src, const int32_t* fr
     long long blocks = (n + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;  // grid-stride: 8 resident CTAs per SM
     dim3 grid(static_cast<unsigned>(blocks), static_cast<unsigned>(nf));
-    bank_frames_kernel<<<grid, 256, 0, as_stream(stream)>>>(
+    DS2_LAUNCH((bank_frames_kernel), grid, 256, 0, as_stream(stream), 
         reinterpret_cast<const __nv_bfloat16* const*>(frame_src), frame_tpos, pos, tpos_table,
         reinterpret_cast<__nv_bfloat16*>(kin_bf16), reinterpret_cast<__nv_bfloat16*>(val_bf16), B, T, C, dst_bs);
     rc = post_launch("bank_frames_kernel");
@@ -104,7 +106,7 @@ extern "C" int ds2_bank_assemble(const void* const* frame_src, const int32_t* fr
   if (np > 0) {
     DS2_REQUIRE(ptr_src && ptr_dist && ptr_w && ptr_bias, DS2_E_ARG, "ds2_bank_assemble: null pointer table");
     dim3 grid(static_cast<unsigned>(np), static_cast<unsigned>(B));
-    bank_ptrs_kernel<<<grid, 256, 0, as_stream(stream)>>>(ptr_src, ptr_dist, ptr_w, ptr_bias,
+    DS2_LAUNCH((bank_ptrs_kernel), grid, 256, 0, as_stream(stream), ptr_src, ptr_dist, ptr_w, ptr_bias,
                                                          reinterpret_cast<__nv_bfloat16*>(kin_bf16),
                                                          reinterpret_cast<__nv_bfloat16*>(val_bf16), dst_bs,
                                                          static_cast<long long>(nf) * T);

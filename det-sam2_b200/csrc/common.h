@@ -45,4 +45,42 @@ int sm_count();
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// Every kernel of the library is launched with the programmatic-stream-serialization attribute and
+// executes pdl_sync() before it touches global memory: griddepcontrol.wait blocks until the preceding
+// grid has completed and flushed, griddepcontrol.launch_dependents lets the NEXT grid's CTAs be
+// scheduled (they run their prologue and then block in their own wait).  The launch latency and the
+// prologue (barrier init, TMEM allocation, tensor-map prefetch) of kernel i+1 thereby overlap the tail
+// of kernel i — the per-frame path is ~520 short dependent kernels, so the serialised launch gaps were
+// a measurable part of the frame.  Inside a stream capture the attribute becomes a programmatic graph
+// edge.  DS2_PDL=0 in the environment turns the attribute off (the device-side calls are no-ops then).
+bool pdl_enabled();
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+  pdl_wait();
+  pdl_launch();
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define DS2_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  ::ds2::launch_kernel(kernel, dim3(grid), dim3(block), static_cast<size_t>(smem), stream, __VA_ARGS__)
+#endif
+
 }  // namespace ds2

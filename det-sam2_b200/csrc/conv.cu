@@ -15,6 +15,7 @@ __device__ __forceinline__ float gelu_erf_c(float x) {
 // ---- patch embedding im2col: fp16 [3,S,S] -> bf16 [(S/4)^2, Kpad], k = c*49 + ky*7 + kx ----------
 __global__ void im2col_patch_kernel(const __half* __restrict__ img, __nv_bfloat16* __restrict__ out, int S,
                                     int Kpad) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const int So = S / 4;
   const int K8 = Kpad / 8;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -41,6 +42,7 @@ __global__ void im2col_patch_kernel(const __half* __restrict__ img, __nv_bfloat1
 // ---- im2col k3 s2 p1, channels-last bf16: [B,Hi,Wi,C] -> [B*Ho*Wo, 9*C], k = (ky*3+kx)*C + c ----
 __global__ void im2col_k3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int B,
                                    int Hi, int Wi, int C) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const int Ho = Hi / 2, Wo = Wi / 2, C8 = C / 8;
   const long long n = static_cast<long long>(B) * Ho * Wo * 9 * C8;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -69,6 +71,7 @@ template <int DWX>
 __global__ void __launch_bounds__(256) dwconv7_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, float* __restrict__ y, int B,
                                                       int Hm, int Wm, int C) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const int c = blockIdx.y * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const int tiles_x = (Wm + DWX - 1) / DWX;
@@ -123,6 +126,7 @@ __global__ void maskds_stage1_kernel(const float* __restrict__ lowres, int B, in
                                      float bias, const float* __restrict__ w, const float* __restrict__ cb,
                                      const float* __restrict__ lnw, const float* __restrict__ lnb,
                                      __nv_bfloat16* __restrict__ out) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const int So = Sl * 2, Sh = Sl * 4;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(B) * So * So) return;
@@ -163,6 +167,7 @@ __global__ void maskds_conv_kernel(const __nv_bfloat16* __restrict__ x, int B, i
                                    const float* __restrict__ w, const float* __restrict__ cb,
                                    const float* __restrict__ lnw, const float* __restrict__ lnb,
                                    __nv_bfloat16* __restrict__ out) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   __shared__ float sw[COUT * CIN * 9];
   for (int i = threadIdx.x; i < COUT * CIN * 9; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -215,7 +220,7 @@ int ds2_im2col_patch(const void* frame_f16, void* out_bf16, int32_t S, int32_t K
   DS2_REQUIRE(frame_f16 && out_bf16 && S > 0 && (S % 4) == 0 && Kpad >= 147 && (Kpad % 8) == 0, DS2_E_ARG,
               "ds2_im2col_patch: bad args");
   const long long n = static_cast<long long>(S / 4) * (S / 4) * (Kpad / 8);
-  im2col_patch_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+  DS2_LAUNCH((im2col_patch_kernel), static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream), 
       reinterpret_cast<const __half*>(frame_f16), reinterpret_cast<__nv_bfloat16*>(out_bf16), S, Kpad);
   return post_launch("im2col_patch_kernel");
 }
@@ -225,7 +230,7 @@ int ds2_im2col_k3s2(const void* x_bf16, void* out_bf16, int32_t B, int32_t Hi, i
   DS2_REQUIRE(x_bf16 && out_bf16 && B > 0 && (Hi % 2) == 0 && (Wi % 2) == 0 && (C % 8) == 0, DS2_E_ARG,
               "ds2_im2col_k3s2: bad args");
   const long long n = static_cast<long long>(B) * (Hi / 2) * (Wi / 2) * 9 * (C / 8);
-  im2col_k3s2_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+  DS2_LAUNCH((im2col_k3s2_kernel), static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream), 
       reinterpret_cast<const __nv_bfloat16*>(x_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16), B, Hi, Wi, C);
   return post_launch("im2col_k3s2_kernel");
 }
@@ -237,7 +242,7 @@ int ds2_dwconv7(const float* x, const float* w, const float* bias, float* y, int
   constexpr int kDwx = 16;
   const int threads = C >= 256 ? 256 : ((C + 31) / 32) * 32;
   dim3 grid(static_cast<unsigned>(B) * Hm * ((Wm + kDwx - 1) / kDwx), (C + threads - 1) / threads);
-  dwconv7_kernel<kDwx><<<grid, threads, 0, as_stream(stream)>>>(x, w, bias, y, B, Hm, Wm, C);
+  DS2_LAUNCH((dwconv7_kernel<kDwx>), grid, threads, 0, as_stream(stream), x, w, bias, y, B, Hm, Wm, C);
   return post_launch("dwconv7_kernel");
 }
 
@@ -248,7 +253,7 @@ int ds2_maskds_stage1(const float* lowres, int32_t B, int32_t Sl, int32_t binari
   DS2_REQUIRE(lowres && w && b && ln_w && ln_b && out_bf16 && B > 0 && Sl > 0, DS2_E_ARG,
               "ds2_maskds_stage1: bad args");
   const long long n = static_cast<long long>(B) * Sl * 2 * Sl * 2;
-  maskds_stage1_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+  DS2_LAUNCH((maskds_stage1_kernel), static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream), 
       lowres, B, Sl, binarize, scale, bias, w, b, ln_w, ln_b, reinterpret_cast<__nv_bfloat16*>(out_bf16));
   return post_launch("maskds_stage1_kernel");
 }
@@ -261,7 +266,7 @@ int ds2_maskds_conv(const void* x_bf16, int32_t B, int32_t Hi, int32_t Wi, int32
   DS2_REQUIRE(Cin == 4 && Cout == 16, DS2_E_ARG, "ds2_maskds_conv: only 4->16 is instantiated (got %d->%d)", Cin,
               Cout);
   const long long n = static_cast<long long>(B) * (Hi / 2) * (Wi / 2);
-  maskds_conv_kernel<4, 16><<<static_cast<unsigned>((n + 127) / 128), 128, 0, as_stream(stream)>>>(
+  DS2_LAUNCH((maskds_conv_kernel<4, 16>), static_cast<unsigned>((n + 127) / 128), 128, 0, as_stream(stream), 
       reinterpret_cast<const __nv_bfloat16*>(x_bf16), B, Hi, Wi, w, b, ln_w, ln_b,
       reinterpret_cast<__nv_bfloat16*>(out_bf16));
   return post_launch("maskds_conv_kernel");

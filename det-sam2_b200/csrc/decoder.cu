@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(256) upscale1_kernel(const float* __restrict__
                                                        const float* __restrict__ lnw,
                                                        const float* __restrict__ lnb,
                                                        __nv_bfloat16* __restrict__ y, int B, int Hm, int Wm, int C) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int Ho = Hm * 2, Wo = Wm * 2;
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(256) upscale2_masks_kernel(const float* __rest
                                                              const float* __restrict__ hyper,
                                                              float* __restrict__ masks, int B, int Hm, int Wm,
                                                              int M) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   constexpr int C = 32;
   __shared__ float sh[4 * C + C];
   const int Ho = Hm * 2, Wo = Wm * 2;
@@ -105,6 +107,7 @@ struct Mlp3Params {
   long long ldy;
 };
 __global__ void __launch_bounds__(256) mlp3_kernel(const Mlp3Params p) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   extern __shared__ float sm[];
   float* xin = sm;             // din
   float* h1 = xin + p.din;     // dh
@@ -152,6 +155,7 @@ __global__ void __launch_bounds__(256) sam_select_kernel(const float* __restrict
                                                          int multimask, float delta, float thresh,
                                                          float* __restrict__ low_res, float* __restrict__ iou_out,
                                                          int* __restrict__ best_idx, float* __restrict__ token_out) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   __shared__ int s_i, s_u, s_idx;
   const int b = blockIdx.x;
   const long long n = static_cast<long long>(S) * S;
@@ -211,6 +215,7 @@ __global__ void __launch_bounds__(256) sam_select_kernel(const float* __restrict
 
 __global__ void objptr_mix_kernel(float* __restrict__ ptr, const float* __restrict__ obj_score,
                                   const float* __restrict__ no_obj_ptr, int B, int C) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const float lam = obj_score[i / C] > 0.f ? 1.f : 0.f;
@@ -227,7 +232,7 @@ int ds2_upscale1(const float* g, const float* bias, const float* skip, const flo
   DS2_REQUIRE(g && bias && skip && ln_w && ln_b && y_bf16 && B > 0, DS2_E_ARG, "ds2_upscale1: bad args");
   DS2_REQUIRE(C == 64, DS2_E_ARG, "ds2_upscale1: C must be 64 (got %d)", C);
   const long long warps = static_cast<long long>(B) * Hm * 2 * Wm * 2;
-  upscale1_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(
+  DS2_LAUNCH((upscale1_kernel), static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, as_stream(stream), 
       g, bias, skip, ln_w, ln_b, reinterpret_cast<__nv_bfloat16*>(y_bf16), B, Hm, Wm, C);
   return post_launch("upscale1_kernel");
 }
@@ -239,7 +244,7 @@ int ds2_upscale2_masks(const float* g, const float* bias, const float* skip, con
   DS2_REQUIRE(C == 32 && M >= 1 && M <= 4, DS2_E_ARG, "ds2_upscale2_masks: C must be 32 and M <= 4");
   const long long per_obj = static_cast<long long>(Hm) * 2 * Wm * 2;
   dim3 grid(static_cast<unsigned>((per_obj + 255) / 256), B);
-  upscale2_masks_kernel<<<grid, 256, 0, as_stream(stream)>>>(g, bias, skip, hyper, masks, B, Hm, Wm, M);
+  DS2_LAUNCH((upscale2_masks_kernel), grid, 256, 0, as_stream(stream), g, bias, skip, hyper, masks, B, Hm, Wm, M);
   return post_launch("upscale2_masks_kernel");
 }
 
@@ -267,7 +272,7 @@ int ds2_mlp3(const ds2_mlp3_args* a, void* stream) {
   p.y = a->y;
   p.ldy = a->ldy;
   const int smem = (a->din + 2 * a->dh) * 4;
-  mlp3_kernel<<<a->rows, 256, smem, as_stream(stream)>>>(p);
+  DS2_LAUNCH((mlp3_kernel), a->rows, 256, smem, as_stream(stream), p);
   return post_launch("mlp3_kernel");
 }
 
@@ -277,7 +282,7 @@ int ds2_sam_select(const float* all_masks, const float* ious, const float* obj_s
   using namespace ds2;
   DS2_REQUIRE(all_masks && ious && obj_score && mask_tokens && low_res && iou_out && best_idx && token_out && B > 0,
               DS2_E_ARG, "ds2_sam_select: bad args");
-  sam_select_kernel<<<B, 256, 0, as_stream(stream)>>>(all_masks, ious, obj_score, mask_tokens, B, S, C, multimask,
+  DS2_LAUNCH((sam_select_kernel), B, 256, 0, as_stream(stream), all_masks, ious, obj_score, mask_tokens, B, S, C, multimask,
                                                      stab_delta, stab_thresh, low_res, iou_out, best_idx, token_out);
   return post_launch("sam_select_kernel");
 }
@@ -285,7 +290,7 @@ int ds2_sam_select(const float* all_masks, const float* ious, const float* obj_s
 int ds2_objptr_mix(float* ptr, const float* obj_score, const float* no_obj_ptr, int32_t B, int32_t C, void* stream) {
   using namespace ds2;
   DS2_REQUIRE(ptr && obj_score && no_obj_ptr && B > 0 && C > 0, DS2_E_ARG, "ds2_objptr_mix: bad args");
-  objptr_mix_kernel<<<(B * C + 255) / 256, 256, 0, as_stream(stream)>>>(ptr, obj_score, no_obj_ptr, B, C);
+  DS2_LAUNCH((objptr_mix_kernel), (B * C + 255) / 256, 256, 0, as_stream(stream), ptr, obj_score, no_obj_ptr, B, C);
   return post_launch("objptr_mix_kernel");
 }
 

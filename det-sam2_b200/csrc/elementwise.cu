@@ -37,6 +37,7 @@ struct LnParams {
 
 template <int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.rows) return;
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
 // lane + 32*i of the row, so every load / store instruction of a warp covers 512 contiguous bytes.
 template <int MAXV4>
 __global__ void __launch_bounds__(256) layernorm_vec_kernel(const LnParams p) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.rows) return;
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const LnParams p) {
 __global__ void axpby_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n4,
                              int C4, int b_row_mod, float alpha, float beta, float* __restrict__ of,
                              __nv_bfloat16* __restrict__ ob) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const long long row = i / C4;
@@ -169,6 +172,7 @@ __global__ void axpby_kernel(const float* __restrict__ a, const float* __restric
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                      long long n) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(x + i);
@@ -183,12 +187,14 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
 }
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y,
                                      long long n) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) y[i] = __bfloat162float(x[i]);
 }
 
 __global__ void maxpool2x2_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int Hm,
                                   int Wm, int C4) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int Ho = Hm / 2, Wo = Wm / 2;
   const long long n = static_cast<long long>(B) * Ho * Wo * C4;
@@ -213,6 +219,7 @@ __global__ void maxpool2x2_kernel(const float* __restrict__ x, float* __restrict
 
 __global__ void upsample2x_add_kernel(const float* __restrict__ top, const float* __restrict__ lat,
                                       float* __restrict__ y, int B, int Hm, int Wm, int C4) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int Ho = Hm * 2, Wo = Wm * 2;
   const long long n = static_cast<long long>(B) * Ho * Wo * C4;
@@ -233,6 +240,7 @@ __global__ void bank_gather_kernel(const __nv_bfloat16* __restrict__ mem, const 
                                    const float* __restrict__ tpos, __nv_bfloat16* __restrict__ kin,
                                    __nv_bfloat16* __restrict__ val, int B, int T, int C, long long dst_bs,
                                    int row0) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int C8 = C / 8;
   const long long n = static_cast<long long>(B) * T * C8;
@@ -257,6 +265,7 @@ __global__ void bank_gather_kernel(const __nv_bfloat16* __restrict__ mem, const 
 __global__ void bank_ptr_kernel(const float* __restrict__ ptr, const float* __restrict__ tpos,
                                 __nv_bfloat16* __restrict__ kin, __nv_bfloat16* __restrict__ val, int B,
                                 long long dst_bs, int row0) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over B*256
   if (i >= B * 256) return;
   const int b = i / 256, c = i % 256;
@@ -297,16 +306,16 @@ int ds2_layernorm(const ds2_ln_args* a, void* stream) {
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (a->x && (a->C % 4) == 0 && (a->ldx % 4) == 0 && (a->ldo % 4) == 0 && al16(a->x) && al16(a->w) && al16(a->b) &&
       al16(a->out_f32) && al16(a->out_bf16) && al16(a->out2_bf16) && al16(a->pos) && (!a->out2_bf16 || (a->C % 4) == 0)) {
-    if (a->C <= 128) layernorm_vec_kernel<1><<<grid, 256, 0, st>>>(p);
-    else if (a->C <= 256) layernorm_vec_kernel<2><<<grid, 256, 0, st>>>(p);
-    else if (a->C <= 640) layernorm_vec_kernel<5><<<grid, 256, 0, st>>>(p);
-    else layernorm_vec_kernel<10><<<grid, 256, 0, st>>>(p);
+    if (a->C <= 128) DS2_LAUNCH((layernorm_vec_kernel<1>), grid, 256, 0, st, p);
+    else if (a->C <= 256) DS2_LAUNCH((layernorm_vec_kernel<2>), grid, 256, 0, st, p);
+    else if (a->C <= 640) DS2_LAUNCH((layernorm_vec_kernel<5>), grid, 256, 0, st, p);
+    else DS2_LAUNCH((layernorm_vec_kernel<10>), grid, 256, 0, st, p);
     return post_launch("layernorm_vec_kernel");
   }
-  if (a->C <= 64) layernorm_kernel<2><<<grid, 256, 0, st>>>(p);
-  else if (a->C <= 256) layernorm_kernel<8><<<grid, 256, 0, st>>>(p);
-  else if (a->C <= 576) layernorm_kernel<18><<<grid, 256, 0, st>>>(p);
-  else layernorm_kernel<40><<<grid, 256, 0, st>>>(p);
+  if (a->C <= 64) DS2_LAUNCH((layernorm_kernel<2>), grid, 256, 0, st, p);
+  else if (a->C <= 256) DS2_LAUNCH((layernorm_kernel<8>), grid, 256, 0, st, p);
+  else if (a->C <= 576) DS2_LAUNCH((layernorm_kernel<18>), grid, 256, 0, st, p);
+  else DS2_LAUNCH((layernorm_kernel<40>), grid, 256, 0, st, p);
   return post_launch("layernorm_kernel");
 }
 
@@ -316,7 +325,7 @@ int ds2_axpby(const float* a, const float* b, int64_t rows, int32_t C, int32_t b
   DS2_REQUIRE(a && rows > 0 && C > 0 && (C % 4) == 0, DS2_E_ARG, "ds2_axpby: bad args (C %% 4 != 0?)");
   DS2_REQUIRE(out_f32 || out_bf16, DS2_E_ARG, "ds2_axpby: no output");
   const long long n4 = rows * (C / 4);
-  axpby_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, as_stream(stream)>>>(
+  DS2_LAUNCH((axpby_kernel), static_cast<unsigned>((n4 + 255) / 256), 256, 0, as_stream(stream), 
       a, b, n4, C / 4, b_row_mod, alpha, beta, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16));
   return post_launch("axpby_kernel");
 }
@@ -325,7 +334,7 @@ int ds2_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream) {
   using namespace ds2;
   DS2_REQUIRE(x && y && n > 0, DS2_E_ARG, "ds2_cast_f32_bf16: bad args");
   const long long t = (n + 3) / 4;
-  cast_f32_bf16_kernel<<<static_cast<unsigned>((t + 255) / 256), 256, 0, as_stream(stream)>>>(
+  DS2_LAUNCH((cast_f32_bf16_kernel), static_cast<unsigned>((t + 255) / 256), 256, 0, as_stream(stream), 
       x, reinterpret_cast<__nv_bfloat16*>(y), n);
   return post_launch("cast_f32_bf16_kernel");
 }
@@ -333,7 +342,7 @@ int ds2_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream) {
 int ds2_cast_bf16_f32(const void* x, float* y, int64_t n, void* stream) {
   using namespace ds2;
   DS2_REQUIRE(x && y && n > 0, DS2_E_ARG, "ds2_cast_bf16_f32: bad args");
-  cast_bf16_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+  DS2_LAUNCH((cast_bf16_f32_kernel), static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream), 
       reinterpret_cast<const __nv_bfloat16*>(x), y, n);
   return post_launch("cast_bf16_f32_kernel");
 }
@@ -343,7 +352,7 @@ int ds2_maxpool2x2(const float* x, float* y, int32_t B, int32_t Hm, int32_t Wm, 
   DS2_REQUIRE(x && y && B > 0 && (Hm % 2) == 0 && (Wm % 2) == 0 && (C % 4) == 0, DS2_E_ARG,
               "ds2_maxpool2x2: bad args");
   const long long n = static_cast<long long>(B) * (Hm / 2) * (Wm / 2) * (C / 4);
-  maxpool2x2_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(x, y, B, Hm, Wm, C / 4);
+  DS2_LAUNCH((maxpool2x2_kernel), static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream), x, y, B, Hm, Wm, C / 4);
   return post_launch("maxpool2x2_kernel");
 }
 
@@ -352,7 +361,7 @@ int ds2_upsample2x_add(const float* top, const float* lat, float* y, int32_t B, 
   using namespace ds2;
   DS2_REQUIRE(top && lat && y && B > 0 && (C % 4) == 0, DS2_E_ARG, "ds2_upsample2x_add: bad args");
   const long long n = static_cast<long long>(B) * Hm * 2 * Wm * 2 * (C / 4);
-  upsample2x_add_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(top, lat, y, B, Hm,
+  DS2_LAUNCH((upsample2x_add_kernel), static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream), top, lat, y, B, Hm,
                                                                                             Wm, C / 4);
   return post_launch("upsample2x_add_kernel");
 }
@@ -363,7 +372,7 @@ int ds2_bank_gather(const void* mem_bf16, const float* pos, const float* tpos, v
   DS2_REQUIRE(mem_bf16 && pos && tpos && kin_bf16 && val_bf16 && B > 0 && T > 0 && (C % 8) == 0, DS2_E_ARG,
               "ds2_bank_gather: bad args");
   const long long n = static_cast<long long>(B) * T * (C / 8);
-  bank_gather_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+  DS2_LAUNCH((bank_gather_kernel), static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream), 
       reinterpret_cast<const __nv_bfloat16*>(mem_bf16), pos, tpos, reinterpret_cast<__nv_bfloat16*>(kin_bf16),
       reinterpret_cast<__nv_bfloat16*>(val_bf16), B, T, C, dst_bs, row0);
   return post_launch("bank_gather_kernel");
@@ -373,7 +382,7 @@ int ds2_bank_ptr(const float* ptr, const float* tpos, void* kin_bf16, void* val_
                  int32_t row0, void* stream) {
   using namespace ds2;
   DS2_REQUIRE(ptr && tpos && kin_bf16 && val_bf16 && B > 0, DS2_E_ARG, "ds2_bank_ptr: bad args");
-  bank_ptr_kernel<<<(B * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
+  DS2_LAUNCH((bank_ptr_kernel), (B * 256 + 255) / 256, 256, 0, as_stream(stream), 
       ptr, tpos, reinterpret_cast<__nv_bfloat16*>(kin_bf16), reinterpret_cast<__nv_bfloat16*>(val_bf16), B,
       dst_bs, row0);
   return post_launch("bank_ptr_kernel");

@@ -10,10 +10,17 @@
 //                        S_h,j = Q_h K_j^T     tcgen05.mma SS, M=128 N=BN, 16 K-steps -> S[h][j&1]
 //                        O_h  += P_h,j V_j     tcgen05.mma TS (A = P in TMEM),  M=128 N=DV
 //                      S is double-buffered per query tile so Q·K^T of tile j+1 overlaps softmax j.
-//   warps 2..2+4*NQ  : softmax, one warpgroup per query tile, one thread per query row (TMEM lane):
-//                      tcgen05.ld S row, running max with lazy rescaling (threshold 2^8), ex2, row
-//                      sum, bf16 P written over S with tcgen05.st; conditional O rescale; final
-//                      O / l epilogue and global store.
+//   warps 2..        : softmax, SP warpgroups per query tile.  A row (TMEM lane) of a key tile is split
+//                      column-wise over SP threads (one per warpgroup, both on the SMSP that owns the
+//                      lane quarter): tcgen05.ld of BN/SP columns, local max, the SP partial maxima of
+//                      a row are exchanged through shared memory (bf16, one named barrier per lane
+//                      quarter) so all parts use the SAME reference, lazy rescaling (threshold 2^8),
+//                      ex2, partial row sum, bf16 P written over S with tcgen05.st; conditional O
+//                      rescale and the final O / l epilogue are split over the DV columns.
+//                      With one warpgroup the softmax of a 128x128 tile (~2400 clk: 128 dependent
+//                      MUFU.EX2 per thread at 4 lanes/clk/SMSP plus load/convert) was twice the MMA time
+//                      (1280 clk); two warps per SMSP overlap each other's TMEM loads, barrier waits
+//                      and stores with the other's MUFU work.
 // TMEM columns: S[h][i] at (2h+i)*BN, O[h] at 2*NQ*BN + h*DV  (<= 512).
 // DV = 64 is the cross-attention case: the 64->256 value projection is applied AFTER P·V by the
 // caller (softmax rows sum to one), which cuts P·V work and V traffic 4x; NQ = 2 halves the K
@@ -31,22 +38,43 @@ constexpr int kQM = 128;
 struct FlashParams {
   int B, Lq, Lk;
   float scale_log2;
+  int dbg;                 // timing experiments only (impl 5/6): 1 = load half of each K tile, 2 = skip the exps
+  const __nv_bfloat16* q;  // QT kernels read the query rows straight from global memory
+  long long ldq, bsq;
   __nv_bfloat16* out;
   long long ldo, bso;
 };
 
-template <int DV, int BN, int NQ, int KS, int VS>
+template <int DV, int BN, int NQ, int KS, int VS, int SP, int QT>
 struct FlashCfg {
-  static constexpr int kThreads = 64 + 128 * NQ;
-  static constexpr int kQBytes = kQM * kHD * 2;  // 64 KB per query tile
+  static constexpr int kThreads = 64 + 128 * NQ * SP;
+  static constexpr int kXchBytes = 2 * SP * NQ * kQM * 2;  // [parity][part][row] bf16 partial maxima
+  static constexpr int kQBytes = QT ? 0 : kQM * kHD * 2;  // 64 KB per query tile when Q is a shared-memory operand
   static constexpr int kKBytes = BN * kHD * 2;
   static constexpr int kVBytes = BN * DV * 2;
   static constexpr int kSmemData = NQ * kQBytes + KS * kKBytes + VS * kVBytes;
-  static constexpr int kSmem = kSmemData + 1024 + 512;
-  static constexpr int kTmemCols = 2 * NQ * BN + NQ * DV;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmem = kSmemData + 1024 + kBarBytes + (kXchBytes < 1024 ? 1024 : kXchBytes);
+  static_assert(BN % (32 * SP) == 0 && DV % (32 * SP) == 0, "column split");
+  static constexpr int kTmemCols = 2 * NQ * BN + NQ * DV + (QT ? NQ * (kHD / 2) : 0);
   static_assert(kTmemCols <= 512, "TMEM budget");
   static_assert(kSmem <= 232448, "shared memory budget");
 };
+
+// Stall accounting for tuning (impl == 8 only): cycles the MMA issuer spent blocked on each barrier class
+// and the softmax warps on theirs, summed over CTAs.  [0] kfull [1] vfull [2] pfull [3] total MMA-warp
+// cycles, [4] sfull (softmax warp 2) [5] odone [6] total softmax-warp cycles [7] CTAs.
+__device__ unsigned long long g_flash_stall[8];
+
+__device__ __forceinline__ void timed_wait(uint32_t bar, uint32_t parity, bool on, long long& acc) {
+  if (!on) {
+    tc::mbar_wait(bar, parity);
+    return;
+  }
+  const long long t = clock64();
+  tc::mbar_wait(bar, parity);
+  acc += clock64() - t;
+}
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -54,12 +82,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int DV, int BN, int NQ, int KS, int VS>
-__global__ void __launch_bounds__(64 + 128 * NQ, 1)
+template <int DV, int BN, int NQ, int KS, int VS, int SP, int QT>
+__global__ void __launch_bounds__(64 + 128 * NQ * SP, 1)
 flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
                           const __grid_constant__ CUtensorMap tmap_k,
                           const __grid_constant__ CUtensorMap tmap_v, const FlashParams p) {
-  using Cfg = FlashCfg<DV, BN, NQ, KS, VS>;
+  using Cfg = FlashCfg<DV, BN, NQ, KS, VS, SP, QT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sq = smem_base;
@@ -77,6 +105,7 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int o_odone = nb;    nb += NQ;
   auto bar = [&](int off, int i) { return bar_base + 8u * static_cast<uint32_t>(off + i); };
   const uint32_t tmem_slot = bar_base + 8u * static_cast<uint32_t>(nb);
+  const uint32_t xch_base = bar_base + Cfg::kBarBytes;  // partial row maxima / row sums of the split softmax
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -85,10 +114,10 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int n_tiles = (p.Lk + BN - 1) / BN;
 
   if (warp == 0 && lane == 0) {
-    tc::prefetch_tmap(&tmap_q);
+    if (!QT) tc::prefetch_tmap(&tmap_q);
     tc::prefetch_tmap(&tmap_k);
     tc::prefetch_tmap(&tmap_v);
-    for (int i = 0; i < NQ; ++i) tc::mbar_init(bar(o_q, i), 1);
+    for (int i = 0; i < NQ; ++i) tc::mbar_init(bar(o_q, i), QT ? 4 * SP : 1);
     for (int i = 0; i < KS; ++i) {
       tc::mbar_init(bar(o_kfull, i), 1);
       tc::mbar_init(bar(o_kempty, i), 1);
@@ -99,7 +128,7 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
     for (int i = 0; i < 2 * NQ; ++i) {
       tc::mbar_init(bar(o_sfull, i), 1);
-      tc::mbar_init(bar(o_pfull, i), 4);
+      tc::mbar_init(bar(o_pfull, i), 4 * SP);
     }
     for (int i = 0; i < NQ; ++i) tc::mbar_init(bar(o_odone, i), 1);
     tc::fence_barrier_init();
@@ -113,24 +142,39 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   tc::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // prologue done (barriers, TMEM, descriptor prefetch: nothing that depends on the previous grid);
+  // only now wait for the producer of our operands, and let the next grid start its own prologue
+  pdl_sync();
   auto tmem_s = [&](int h, int i) { return tmem_base + static_cast<uint32_t>((2 * h + i) * BN); };
   auto tmem_o = [&](int h) { return tmem_base + static_cast<uint32_t>(2 * NQ * BN + h * DV); };
+  // QT: the query tile lives in TMEM (128 lanes x 128 columns of bf16 pairs) and Q·K^T is a TS MMA, so
+  // the tensor core reads only the K tile from shared memory.  With both operands in shared memory a
+  // 128x128x16 MMA reads 8 KB per 64 clk = the whole 128 B/clk of the SM's shared memory, on top of the
+  // TMA writes of the K/V rings — the kernel was shared-memory-bandwidth bound at ~52 % of the MMA rate.
+  auto tmem_q = [&](int h) { return tmem_base + static_cast<uint32_t>(2 * NQ * BN + NQ * DV + h * (kHD / 2)); };
 
-  if (warp == 0 && lane == 0) {
+  // Role gates use elect.sync, not `lane == 0`: tcgen05.mma / TMA take their operands from the uniform
+  // datapath, and under a lane-id predicate the compiler wraps EVERY such instruction in an
+  // ELECT / BRA.U.ANY serialisation loop (~97 clk per MMA issued, measured with tools/mma_rate.cu, against
+  // 42-74 clk for the instruction itself) — the single issuing thread, not the tensor pipe, set the pace.
+  if (warp == 0 && tc::elect_one()) {
     // ------------------------------ TMA producer ------------------------------
-    for (int h = 0; h < NQ; ++h) {
-      tc::mbar_expect_tx(bar(o_q, h), Cfg::kQBytes);
-      for (int kk = 0; kk < kHD / 64; ++kk)
-        tc::tma_load_3d(sq + h * Cfg::kQBytes + kk * (kQM * 128), &tmap_q, bar(o_q, h), kk * 64,
-                        q0 + h * kQM, b);
+    if (!QT) {
+      for (int h = 0; h < NQ; ++h) {
+        tc::mbar_expect_tx(bar(o_q, h), Cfg::kQBytes);
+        for (int kk = 0; kk < kHD / 64; ++kk)
+          tc::tma_load_3d(sq + h * Cfg::kQBytes + kk * (kQM * 128), &tmap_q, bar(o_q, h), kk * 64,
+                          q0 + h * kQM, b);
+      }
     }
     for (int j = 0; j < n_tiles; ++j) {
       {
         const int s = j % KS;
         tc::mbar_wait(bar(o_kempty, s), ((j / KS) & 1) ^ 1);
-        tc::mbar_expect_tx(bar(o_kfull, s), Cfg::kKBytes);
+        const int nkk = (p.dbg == 1) ? kHD / 128 : kHD / 64;
+        tc::mbar_expect_tx(bar(o_kfull, s), nkk * (BN * 128));
         const uint32_t sk = sk0 + s * Cfg::kKBytes;
-        for (int kk = 0; kk < kHD / 64; ++kk)
+        for (int kk = 0; kk < nkk; ++kk)
           tc::tma_load_3d(sk + kk * (BN * 128), &tmap_k, bar(o_kfull, s), kk * 64, j * BN, b);
       }
       {
@@ -142,13 +186,16 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
           tc::tma_load_3d(sv + nn * (BN * 128), &tmap_v, bar(o_vfull, s), nn * 64, j * BN, b);
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && tc::elect_one()) {
     // ------------------------------ MMA issuer ------------------------------
     const uint32_t idesc_qk = tc::make_idesc_bf16(kQM, BN, 0, 0);
     const uint32_t idesc_pv = tc::make_idesc_bf16(kQM, DV, 0, 1);
+    const bool prof = p.dbg == 3;
+    long long w_k = 0, w_v = 0, w_p = 0;
+    const long long t_begin = clock64();
     auto issue_qk = [&](int j) {
       const int s = j % KS;
-      tc::mbar_wait(bar(o_kfull, s), (j / KS) & 1);
+      timed_wait(bar(o_kfull, s), (j / KS) & 1, prof, w_k);
       tc::tc_fence_after();
       const uint32_t sk = sk0 + s * Cfg::kKBytes;
 #pragma unroll
@@ -157,24 +204,29 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const uint32_t sqh = sq + h * Cfg::kQBytes;
 #pragma unroll
         for (int k = 0; k < kHD / 16; ++k) {
-          const uint64_t da = tc::make_desc_sw128(sqh + (k >> 2) * (kQM * 128) + (k & 3) * 32, 16, 1024);
           const uint64_t db = tc::make_desc_sw128(sk + (k >> 2) * (BN * 128) + (k & 3) * 32, 16, 1024);
-          tc::umma_ss(d, da, db, idesc_qk, k != 0 ? 1u : 0u);
+          if (QT) {
+            tc::umma_ts(d, tmem_q(h) + k * 8, db, idesc_qk, k != 0 ? 1u : 0u);
+          } else {
+            const uint64_t da = tc::make_desc_sw128(sqh + (k >> 2) * (kQM * 128) + (k & 3) * 32, 16, 1024);
+            tc::umma_ss(d, da, db, idesc_qk, k != 0 ? 1u : 0u);
+          }
         }
         tc::umma_commit(bar(o_sfull, 2 * h + (j & 1)));
       }
       tc::umma_commit(bar(o_kempty, s));
     };
     for (int h = 0; h < NQ; ++h) tc::mbar_wait(bar(o_q, h), 0);
+    tc::tc_fence_after();
     issue_qk(0);
     for (int j = 0; j < n_tiles; ++j) {
       if (j + 1 < n_tiles) issue_qk(j + 1);
       const int s = j % VS;
-      tc::mbar_wait(bar(o_vfull, s), (j / VS) & 1);
+      timed_wait(bar(o_vfull, s), (j / VS) & 1, prof, w_v);
       const uint32_t sv = sv0 + s * Cfg::kVBytes;
 #pragma unroll
       for (int h = 0; h < NQ; ++h) {
-        tc::mbar_wait(bar(o_pfull, 2 * h + (j & 1)), (j >> 1) & 1);
+        timed_wait(bar(o_pfull, 2 * h + (j & 1)), (j >> 1) & 1, prof, w_p);
         tc::tc_fence_after();
         const uint32_t pa = tmem_s(h, j & 1);
 #pragma unroll
@@ -187,36 +239,95 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
       tc::umma_commit(bar(o_vempty, s));
     }
+    if (prof) {
+      atomicAdd(&g_flash_stall[0], static_cast<unsigned long long>(w_k));
+      atomicAdd(&g_flash_stall[1], static_cast<unsigned long long>(w_v));
+      atomicAdd(&g_flash_stall[2], static_cast<unsigned long long>(w_p));
+      atomicAdd(&g_flash_stall[3], static_cast<unsigned long long>(clock64() - t_begin));
+      atomicAdd(&g_flash_stall[7], 1ull);
+    }
   } else if (warp >= 2) {
     // ------------------------------ softmax / epilogue ------------------------------
-    const int h = (warp - 2) >> 2;  // query tile of this warpgroup
-    const int lq = warp & 3;        // TMEM lane quarter this warp may access
+    constexpr int CW = BN / SP;       // S columns of a row handled by this thread
+    constexpr int OW = DV / SP;       // O columns of a row handled by this thread (rescale, epilogue)
+    const int sw = warp - 2;
+    const int h = sw / (4 * SP);      // query tile
+    const int part = (sw >> 2) % SP;  // which column part of the row
+    const int lq = warp & 3;          // TMEM lane quarter this warp may access
     const uint32_t lane_off = static_cast<uint32_t>(lq * 32) << 16;
-    const int row = q0 + h * kQM + lq * 32 + lane;
-    const uint32_t to = tmem_o(h) + lane_off;
+    const int rloc = h * kQM + lq * 32 + lane;  // row inside the CTA
+    const int row = q0 + rloc;
+    const uint32_t to = tmem_o(h) + lane_off + part * OW;
+    const int bar_id = 1 + h * 4 + lq;  // named barrier of the SP warps that share these 32 rows
+    auto xch_max = [&](int par, int pt) {
+      return xch_base + 2u * static_cast<uint32_t>((par * SP + pt) * (NQ * kQM) + rloc);
+    };
+    if (QT) {
+      // this thread's part of its query row: global -> registers -> TMEM (bf16 pairs, K-major A operand)
+      constexpr int QW = (kHD / 2) / SP;  // 32-bit columns per thread
+      const uint4* src = reinterpret_cast<const uint4*>(p.q + static_cast<long long>(b) * p.bsq +
+                                                        static_cast<long long>(row) * p.ldq + part * (kHD / SP));
+      const uint32_t tq = tmem_q(h) + lane_off + part * QW;
+#pragma unroll
+      for (int c = 0; c < QW / 32; ++c) {
+        uint32_t w[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint4 t = make_uint4(0u, 0u, 0u, 0u);
+          if (row < p.Lq) t = __ldg(src + c * 8 + i);
+          w[4 * i] = t.x;
+          w[4 * i + 1] = t.y;
+          w[4 * i + 2] = t.z;
+          w[4 * i + 3] = t.w;
+        }
+        tc::tmem_st32(tq + c * 32, w);
+      }
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(bar(o_q, h));
+    }
     float m_ref = -INFINITY;
     float l = 0.f;
+    const bool prof = p.dbg == 3 && warp == 2;
+    long long w_s = 0, w_o = 0;
+    const long long t_begin = clock64();
     for (int j = 0; j < n_tiles; ++j) {
-      tc::mbar_wait(bar(o_sfull, 2 * h + (j & 1)), (j >> 1) & 1);
+      timed_wait(bar(o_sfull, 2 * h + (j & 1)), (j >> 1) & 1, prof, w_s);
       tc::tc_fence_after();
       const uint32_t ts = tmem_s(h, j & 1) + lane_off;
-      uint32_t sraw[BN];
+      uint32_t sraw[CW];
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < CW / 32; ++c) {
         uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sraw[c * 32]);
-        tc::tmem_ld32(ts + c * 32, chunk);
+        tc::tmem_ld32(ts + part * CW + c * 32, chunk);
       }
       tc::tmem_ld_wait();
-      const int valid = p.Lk - j * BN;  // keys >= valid are TMA zero fill -> mask
-      float mt = -INFINITY;
-      if (valid >= BN) {
+      const int valid = p.Lk - j * BN - part * CW;  // columns >= valid are TMA zero fill -> mask
+      if (valid < CW) {
 #pragma unroll
-        for (int i = 0; i < BN; ++i) mt = fmaxf(mt, __uint_as_float(sraw[i]));
-      } else {
-#pragma unroll
-        for (int i = 0; i < BN; ++i) {
+        for (int i = 0; i < CW; ++i)
           if (i >= valid) sraw[i] = 0xff800000u;  // -inf
-          mt = fmaxf(mt, __uint_as_float(sraw[i]));
+      }
+      // four independent chains: the running max is not one CW-long dependency chain
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < CW; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(sraw[i]));
+      float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      if (SP > 1) {
+        // every part of a row must scale by the same reference: exchange the (bf16-rounded) partial
+        // maxima; the barrier also orders "all parts have loaded their S columns" before any part
+        // overwrites S with P below
+        const __nv_bfloat16 mine = __float2bfloat16_rn(mt);
+        asm volatile("st.shared.b16 [%0], %1;" ::"r"(xch_max(j & 1, part)), "h"(__bfloat16_as_ushort(mine)) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * SP) : "memory");
+        mt = __bfloat162float(mine);
+#pragma unroll
+        for (int o = 0; o < SP; ++o) {
+          if (o == part) continue;
+          unsigned short u;
+          asm volatile("ld.shared.b16 %0, [%1];" : "=h"(u) : "r"(xch_max(j & 1, o)) : "memory");
+          mt = fmaxf(mt, __bfloat162float(__ushort_as_bfloat16(u)));
         }
       }
       float alpha = 1.f;
@@ -229,29 +340,40 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         resc = true;
       }
       const float moff = m_ref * p.scale_log2;
-      float sum = 0.f;
-      uint32_t pk[BN / 2];
+      float sum0 = 0.f, sum1 = 0.f;
+      uint32_t pk[CW / 2];
 #pragma unroll
-      for (int i = 0; i < BN / 2; ++i) {
-        const float e0 = ex2_approx(fmaf(__uint_as_float(sraw[2 * i]), p.scale_log2, -moff));
-        const float e1 = ex2_approx(fmaf(__uint_as_float(sraw[2 * i + 1]), p.scale_log2, -moff));
-        sum += e0 + e1;
+      for (int i = 0; i < CW / 2; ++i) {
+        float e0 = fmaf(__uint_as_float(sraw[2 * i]), p.scale_log2, -moff);
+        float e1 = fmaf(__uint_as_float(sraw[2 * i + 1]), p.scale_log2, -moff);
+        if (p.dbg != 2) {
+          e0 = ex2_approx(e0);
+          e1 = ex2_approx(e1);
+        }
+        sum0 += e0;
+        sum1 += e1;
         pk[i] = tc::pack_bf16(e0, e1);
       }
-      l = l * alpha + sum;
+      l = l * alpha + (sum0 + sum1);
+      // P (bf16 pairs) overwrites the first BN/2 columns of S: this thread's part at [part*CW/2, +CW/2)
+      if (CW / 2 >= 32) {
 #pragma unroll
-      for (int c = 0; c < BN / 64; ++c) {
-        const uint32_t(&chunk)[32] = *reinterpret_cast<const uint32_t(*)[32]>(&pk[c * 32]);
-        tc::tmem_st32(ts + c * 32, chunk);
+        for (int c = 0; c < CW / 64; ++c) {
+          const uint32_t(&chunk)[32] = *reinterpret_cast<const uint32_t(*)[32]>(&pk[c * 32]);
+          tc::tmem_st32(ts + part * (CW / 2) + c * 32, chunk);
+        }
+      } else {
+        const uint32_t(&chunk)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&pk[0]);
+        tc::tmem_st16(ts + part * (CW / 2), chunk);
       }
       // Consume every phase of `odone` (P·V of tile j-1 complete) so this waiter is never more than
       // one phase behind the barrier — parity waits alias otherwise.  By now that MMA has long retired.
-      if (j > 0) tc::mbar_wait(bar(o_odone, h), (j - 1) & 1);
+      if (j > 0) timed_wait(bar(o_odone, h), (j - 1) & 1, prof, w_o);
       if (__any_sync(0xffffffffu, resc)) {
         // O is stable here: P·V of tile j-1 is complete and P·V of tile j is not yet issued
         tc::tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < DV / 32; ++c) {
+        for (int c = 0; c < OW / 32; ++c) {
           uint32_t o[32];
           tc::tmem_ld32(to + c * 32, o);
           tc::tmem_ld_wait();
@@ -265,13 +387,33 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(bar(o_pfull, 2 * h + (j & 1)));
     }
+    if (prof && lane == 0) {
+      atomicAdd(&g_flash_stall[4], static_cast<unsigned long long>(w_s));
+      atomicAdd(&g_flash_stall[5], static_cast<unsigned long long>(w_o));
+      atomicAdd(&g_flash_stall[6], static_cast<unsigned long long>(clock64() - t_begin));
+    }
+    if (SP > 1) {
+      // total row sum = sum of the parts (same reference in all of them); reuse the exchange buffer as f32
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * SP) : "memory");
+      const uint32_t xl = xch_base + 4u * static_cast<uint32_t>(part * (NQ * kQM) + rloc);
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(xl), "f"(l) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * SP) : "memory");
+      float lt = 0.f;
+#pragma unroll
+      for (int o = 0; o < SP; ++o) {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(xch_base + 4u * static_cast<uint32_t>(o * (NQ * kQM) + rloc)) : "memory");
+        lt += v;
+      }
+      l = lt;
+    }
     // epilogue: O / l -> bf16 -> global
     tc::mbar_wait(bar(o_odone, h), (n_tiles - 1) & 1);
     tc::tc_fence_after();
     const float inv = 1.0f / l;
-    __nv_bfloat16* orow = p.out + static_cast<long long>(b) * p.bso + static_cast<long long>(row) * p.ldo;
+    __nv_bfloat16* orow = p.out + static_cast<long long>(b) * p.bso + static_cast<long long>(row) * p.ldo + part * OW;
 #pragma unroll
-    for (int c = 0; c < DV / 32; ++c) {
+    for (int c = 0; c < OW / 32; ++c) {
       uint32_t o[32];
       tc::tmem_ld32(to + c * 32, o);
       tc::tmem_ld_wait();
@@ -305,6 +447,7 @@ __global__ void flash_simt_kernel(const __nv_bfloat16* __restrict__ q, const __n
                                   long long ldq, long long ldk, long long ldv, long long ldo,
                                   long long bsq, long long bsk, long long bsv, long long bso, int Lq,
                                   int Lk, int DV, float scale) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.y;
@@ -332,9 +475,9 @@ __global__ void flash_simt_kernel(const __nv_bfloat16* __restrict__ q, const __n
   for (int i = 0; i < per; ++i) orow[lane * per + i] = __float2bfloat16(acc[i] / l);
 }
 
-template <int DV, int BN, int NQ, int KS, int VS>
+template <int DV, int BN, int NQ, int KS, int VS, int SP, int QT>
 static int launch_flash(const ds2_flash_args* a, cudaStream_t st) {
-  using Cfg = FlashCfg<DV, BN, NQ, KS, VS>;
+  using Cfg = FlashCfg<DV, BN, NQ, KS, VS, SP, QT>;
   CUtensorMap tq, tk, tv;
   {
     const uint64_t dims[3] = {256, static_cast<uint64_t>(a->Lq), static_cast<uint64_t>(a->B)};
@@ -360,7 +503,7 @@ static int launch_flash(const ds2_flash_args* a, cudaStream_t st) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(flash_d256_tcgen05_kernel<DV, BN, NQ, KS, VS>,
+    cudaError_t e = cudaFuncSetAttribute(flash_d256_tcgen05_kernel<DV, BN, NQ, KS, VS, SP, QT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
     DS2_REQUIRE(e == cudaSuccess, static_cast<int>(e), "ds2_flash_attn: cudaFuncSetAttribute: %s",
                 cudaGetErrorString(e));
@@ -371,15 +514,28 @@ static int launch_flash(const ds2_flash_args* a, cudaStream_t st) {
   p.Lq = a->Lq;
   p.Lk = a->Lk;
   p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.dbg = a->impl == 5 ? 1 : (a->impl == 6 ? 2 : (a->impl == 8 ? 3 : 0));
+  p.q = reinterpret_cast<const __nv_bfloat16*>(a->q);
+  p.ldq = a->ldq;
+  p.bsq = a->bsq;
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   p.ldo = a->ldo;
   p.bso = a->bso;
   dim3 grid((a->Lq + kQM * NQ - 1) / (kQM * NQ), a->B);
-  flash_d256_tcgen05_kernel<DV, BN, NQ, KS, VS><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(tq, tk, tv, p);
+  DS2_LAUNCH((flash_d256_tcgen05_kernel<DV, BN, NQ, KS, VS, SP, QT>), grid, Cfg::kThreads, Cfg::kSmem, st, tq, tk, tv, p);
   return post_launch("flash_d256_tcgen05_kernel");
 }
 
 }  // namespace ds2
+
+extern "C" int ds2_debug_flash_stalls(unsigned long long* out8, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out8, ds2::g_flash_stall, 8 * sizeof(unsigned long long));
+  if (e == cudaSuccess && reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    e = cudaMemcpyToSymbol(ds2::g_flash_stall, z, sizeof(z));
+  }
+  return e == cudaSuccess ? DS2_OK : static_cast<int>(e);
+}
 
 extern "C" int ds2_flash_attn(const ds2_flash_args* a, void* stream) {
   using namespace ds2;
@@ -391,7 +547,7 @@ extern "C" int ds2_flash_attn(const ds2_flash_args* a, void* stream) {
   cudaStream_t st = as_stream(stream);
   if (a->impl == 1) {
     dim3 grid((a->Lq * 32 + 255) / 256, a->B);
-    flash_simt_kernel<<<grid, 256, 0, st>>>(
+    DS2_LAUNCH((flash_simt_kernel), grid, 256, 0, st, 
         reinterpret_cast<const __nv_bfloat16*>(a->q), reinterpret_cast<const __nv_bfloat16*>(a->k),
         reinterpret_cast<const __nv_bfloat16*>(a->v), reinterpret_cast<__nv_bfloat16*>(a->out), a->ldq,
         a->ldk, a->ldv, a->ldo, a->bsq, a->bsk, a->bsv, a->bso, a->Lq, a->Lk, a->DV, a->scale);
@@ -400,10 +556,18 @@ extern "C" int ds2_flash_attn(const ds2_flash_args* a, void* stream) {
   DS2_REQUIRE((a->ldq % 8) == 0 && (a->ldk % 8) == 0 && (a->ldv % 8) == 0 && (a->ldo % 8) == 0 &&
                   (a->bsq % 8) == 0 && (a->bsk % 8) == 0 && (a->bsv % 8) == 0 && (a->bso % 8) == 0,
               DS2_E_ALIGN, "ds2_flash_attn: pitches must be multiples of 8 elements");
-  // impl: 0 = default (one query tile, 128-key tiles), 3 = two query tiles per CTA / 64-key tiles
+  // impl: 0 = default: one query tile per CTA, Q resident in TMEM (TS MMA), one softmax warpgroup
+  //       9 = same with every softmax row split over two warpgroups (same speed once the kernel became
+  //           tensor-bound; its bf16-rounded running max changes P by rounding noise, so not the default)
+  //       2 = Q as a shared-memory operand (SS MMA), 3 = two query tiles per CTA / 64-key tiles (SS)
+  //       5, 6, 8 = timing experiments (half K loads, no exps, barrier-stall accounting)
   if (a->DV == 64) {
-    if (a->impl == 3) return launch_flash<64, 64, 2, 2, 3>(a, st);
-    return launch_flash<64, 128, 1, 2, 2>(a, st);
+    if (a->impl == 3) return launch_flash<64, 64, 2, 2, 3, 1, 0>(a, st);
+    if (a->impl == 2) return launch_flash<64, 128, 1, 2, 2, 1, 0>(a, st);
+    if (a->impl == 9) return launch_flash<64, 128, 1, 3, 2, 2, 1>(a, st);
+    return launch_flash<64, 128, 1, 3, 2, 1, 1>(a, st);
   }
-  return launch_flash<256, 64, 1, 2, 2>(a, st);
+  if (a->impl == 2) return launch_flash<256, 64, 1, 2, 2, 1, 0>(a, st);
+  if (a->impl == 9) return launch_flash<256, 64, 1, 3, 3, 2, 1>(a, st);
+  return launch_flash<256, 64, 1, 3, 3, 1, 1>(a, st);
 }

@@ -225,12 +225,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   tc::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // prologue done (barriers, TMEM, descriptor prefetch: nothing that depends on the previous grid);
+  // only now wait for the producer of our operands, and let the next grid start its own prologue
+  pdl_sync();
 
   const int num_tiles = p.tiles_m * p.tiles_n;
   const int k_blocks = (p.K + kBK - 1) / kBK;
   const uint32_t stage_tx = kABytes + static_cast<uint32_t>(p.BN) * kBK * 2;
 
-  if (warp == 0 && lane == 0) {
+  // Role gates use elect.sync, not `lane == 0`: tcgen05.mma / TMA take their operands from the uniform
+  // datapath, and under a lane-id predicate the compiler wraps EVERY such instruction in an
+  // ELECT / BRA.U.ANY serialisation loop (~97 clk per MMA issued, measured with tools/mma_rate.cu, against
+  // 42-74 clk for the instruction itself) — the single issuing thread, not the tensor pipe, set the pace.
+  if (warp == 0 && tc::elect_one()) {
     // ---------------- TMA producer ----------------
     int stage = 0;
     uint32_t phase = 0;
@@ -248,7 +255,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && tc::elect_one()) {
     // ---------------- MMA issuer ----------------
     const uint32_t idesc = tc::make_idesc_bf16(kBM, p.BN, 0, 0);
     int stage = 0;
@@ -424,6 +431,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 __global__ void gemm_bf16_simt_kernel(const __nv_bfloat16* __restrict__ A, long long lda,
                                       const __nv_bfloat16* __restrict__ W, long long ldw,
                                       const GemmParams p) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   __shared__ float sa[16][17];
   __shared__ float sb[16][17];
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -537,7 +545,7 @@ extern "C" int ds2_gemm(const ds2_gemm_args* a, void* stream) {
     p.BN = 16;
     p.tiles_m = p.tiles_n = 0;
     dim3 grid((a->N + 15) / 16, (a->M + 15) / 16), block(16, 16);
-    gemm_bf16_simt_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a->A), a->lda,
+    DS2_LAUNCH((gemm_bf16_simt_kernel), grid, block, 0, st, reinterpret_cast<const __nv_bfloat16*>(a->A), a->lda,
                                                   reinterpret_cast<const __nv_bfloat16*>(a->W), a->ldw,
                                                   p);
     return post_launch("gemm_bf16_simt_kernel");
@@ -604,6 +612,6 @@ extern "C" int ds2_gemm(const ds2_gemm_args* a, void* stream) {
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < sms ? tiles : sms;
-  gemm_bf16_tcgen05_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(ta, tw, tcm, p);
+  DS2_LAUNCH((gemm_bf16_tcgen05_kernel), grid, kGemmThreads, kGemmSmem, st, ta, tw, tcm, p);
   return post_launch("gemm_bf16_tcgen05_kernel");
 }

@@ -79,6 +79,7 @@ __device__ __forceinline__ void cp_async_wait() {
 // loads of chunk j+1 overlap the MMAs of chunk j.
 template <int DP, int NW>
 __global__ void __launch_bounds__(32 * NW, (DP <= 96 ? (NW == 8 ? 2 : 4) : 1)) mha_kernel(const MhaParams p) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   constexpr int QS = DP + 8;   // smem row stride (elements) for Q / K / V tiles (conflict-free for ldmatrix)
   constexpr int QT = 16 * NW;  // query rows per CTA
   constexpr int NT = 32 * NW;  // threads
@@ -316,7 +317,7 @@ static int launch_mha_nw(const MhaParams& p, dim3 grid, cudaStream_t st) {
       set = true;
     }
   }
-  mha_kernel<DP, NW><<<grid, 32 * NW, smem, st>>>(p);
+  DS2_LAUNCH((mha_kernel<DP, NW>), grid, 32 * NW, smem, st, p);
   return post_launch("mha_kernel");
 }
 

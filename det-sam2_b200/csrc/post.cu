@@ -42,6 +42,7 @@ __device__ __forceinline__ bool is_fg(const uint8_t* m8, const float* sc, long l
 // (ballot + clz), so the long horizontal chains of big components never go through union-find.
 __global__ void cc_init_kernel(const uint8_t* __restrict__ m8, const float* __restrict__ sc, int* __restrict__ parent,
                                int* __restrict__ area, int* __restrict__ minblk, long long total, int HW, int W) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const bool valid = i < total;
@@ -66,6 +67,7 @@ __global__ void cc_init_kernel(const uint8_t* __restrict__ m8, const float* __re
 //     except the up-right one when the pixel directly above is background;
 //   * otherwise: up if foreground, else up-left and up-right individually.
 __global__ void cc_merge_kernel(int* __restrict__ parent, long long total, int H, int W) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int HW = H * W;
@@ -92,6 +94,7 @@ __global__ void cc_merge_kernel(int* __restrict__ parent, long long total, int H
 
 __global__ void cc_count_kernel(const int* __restrict__ parent, int* __restrict__ area, int* __restrict__ minblk,
                                 long long total, int H, int W) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int HW = H * W;
   const bool valid = i < total;
@@ -114,6 +117,7 @@ __global__ void cc_count_kernel(const int* __restrict__ parent, int* __restrict_
 
 __global__ void cc_emit_kernel(const int* __restrict__ parent, const int* __restrict__ minblk,
                                int* __restrict__ labels, int* __restrict__ counts, long long total, int HW) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int p = static_cast<int>(i % HW);
@@ -130,6 +134,7 @@ __global__ void cc_emit_kernel(const int* __restrict__ parent, const int* __rest
 
 __global__ void fill_holes_kernel(float* __restrict__ scores, const int* __restrict__ parent,
                                   const int* __restrict__ area, long long total, int HW, int max_area) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   if (parent[i] < 0) return;
@@ -142,6 +147,7 @@ __global__ void fill_holes_kernel(float* __restrict__ scores, const int* __restr
 // PyTorch upsample_bilinear2d, align_corners=False, antialias=False
 __global__ void resize_bilinear_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int Hi, int Wi,
                                        int Ho, int Wo, float sh, float sw) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(N) * Ho * Wo;
   if (i >= total) return;
@@ -159,6 +165,7 @@ __global__ void resize_bilinear_kernel(const float* __restrict__ x, float* __res
 }
 
 __global__ void threshold_pack_kernel(const float* __restrict__ x, uint8_t* __restrict__ bits, long long n) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const long long byte = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long i0 = byte * 8;
   if (i0 >= n) return;
@@ -190,18 +197,18 @@ int ds2_connected_components(const uint8_t* mask, int32_t* labels, int32_t* coun
   int* parent = tmp;
   int* minblk = tmp + total;
   const int HW = H * W;
-  cc_init_kernel<<<nblocks(total, 256), 256, 0, st>>>(mask, nullptr, parent, counts, minblk, total, HW, W);
+  DS2_LAUNCH((cc_init_kernel), nblocks(total, 256), 256, 0, st, mask, nullptr, parent, counts, minblk, total, HW, W);
   int rc = post_launch("cc_init_kernel");
   if (!rc) {
-    cc_merge_kernel<<<nblocks(total, 256), 256, 0, st>>>(parent, total, H, W);
+    DS2_LAUNCH((cc_merge_kernel), nblocks(total, 256), 256, 0, st, parent, total, H, W);
     rc = post_launch("cc_merge_kernel");
   }
   if (!rc) {
-    cc_count_kernel<<<nblocks(total, 256), 256, 0, st>>>(parent, counts, minblk, total, H, W);
+    DS2_LAUNCH((cc_count_kernel), nblocks(total, 256), 256, 0, st, parent, counts, minblk, total, H, W);
     rc = post_launch("cc_count_kernel");
   }
   if (!rc) {
-    cc_emit_kernel<<<nblocks(total, 256), 256, 0, st>>>(parent, minblk, labels, counts, total, HW);
+    DS2_LAUNCH((cc_emit_kernel), nblocks(total, 256), 256, 0, st, parent, minblk, labels, counts, total, HW);
     rc = post_launch("cc_emit_kernel");
   }
   cudaFreeAsync(tmp, st);
@@ -216,16 +223,16 @@ int ds2_fill_holes(float* scores, int32_t* labels_ws, int32_t* counts_ws, int32_
   cudaStream_t st = as_stream(stream);
   const long long total = static_cast<long long>(N) * H * W;
   const int HW = H * W;
-  cc_init_kernel<<<nblocks(total, 256), 256, 0, st>>>(nullptr, scores, labels_ws, counts_ws, nullptr, total, HW, W);
+  DS2_LAUNCH((cc_init_kernel), nblocks(total, 256), 256, 0, st, nullptr, scores, labels_ws, counts_ws, nullptr, total, HW, W);
   int rc = post_launch("cc_init_kernel");
   if (rc) return rc;
-  cc_merge_kernel<<<nblocks(total, 256), 256, 0, st>>>(labels_ws, total, H, W);
+  DS2_LAUNCH((cc_merge_kernel), nblocks(total, 256), 256, 0, st, labels_ws, total, H, W);
   rc = post_launch("cc_merge_kernel");
   if (rc) return rc;
-  cc_count_kernel<<<nblocks(total, 256), 256, 0, st>>>(labels_ws, counts_ws, nullptr, total, H, W);
+  DS2_LAUNCH((cc_count_kernel), nblocks(total, 256), 256, 0, st, labels_ws, counts_ws, nullptr, total, H, W);
   rc = post_launch("cc_count_kernel");
   if (rc) return rc;
-  fill_holes_kernel<<<nblocks(total, 256), 256, 0, st>>>(scores, labels_ws, counts_ws, total, HW, max_area);
+  DS2_LAUNCH((fill_holes_kernel), nblocks(total, 256), 256, 0, st, scores, labels_ws, counts_ws, total, HW, max_area);
   return post_launch("fill_holes_kernel");
 }
 
@@ -234,7 +241,7 @@ int ds2_resize_bilinear(const float* x, float* y, int32_t N, int32_t Hi, int32_t
   using namespace ds2;
   DS2_REQUIRE(x && y && N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, DS2_E_ARG, "ds2_resize_bilinear: bad args");
   const long long total = static_cast<long long>(N) * Ho * Wo;
-  resize_bilinear_kernel<<<nblocks(total, 256), 256, 0, as_stream(stream)>>>(
+  DS2_LAUNCH((resize_bilinear_kernel), nblocks(total, 256), 256, 0, as_stream(stream), 
       x, y, N, Hi, Wi, Ho, Wo, static_cast<float>(Hi) / Ho, static_cast<float>(Wi) / Wo);
   return post_launch("resize_bilinear_kernel");
 }
@@ -242,7 +249,7 @@ int ds2_resize_bilinear(const float* x, float* y, int32_t N, int32_t Hi, int32_t
 int ds2_threshold_pack(const float* x, uint8_t* bits, int64_t n, void* stream) {
   using namespace ds2;
   DS2_REQUIRE(x && bits && n > 0, DS2_E_ARG, "ds2_threshold_pack: bad args");
-  threshold_pack_kernel<<<nblocks((n + 7) / 8, 256), 256, 0, as_stream(stream)>>>(x, bits, n);
+  DS2_LAUNCH((threshold_pack_kernel), nblocks((n + 7) / 8, 256), 256, 0, as_stream(stream), x, bits, n);
   return post_launch("threshold_pack_kernel");
 }
 

@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(128) prompt_tokens_kernel(const float* __restr
                                                             const float* __restrict__ out_tokens,   // [n_out,256]
                                                             int n_out, float image_size,
                                                             float* __restrict__ tokens) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const int nt = n_out + P + 1;
   const int b = blockIdx.x / nt, t = blockIdx.x % nt;
   const int j = threadIdx.x;  // frequency index 0..127
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(256) bank_ptr_pe_kernel(const float* __restric
                                                           __nv_bfloat16* __restrict__ kin,
                                                           __nv_bfloat16* __restrict__ val, long long dst_bs,
                                                           int row0) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   __shared__ float pe[256];
   __shared__ float tp[64];
   const int t = threadIdx.x;
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(256) bank_ptr_pe_kernel(const float* __restric
 __global__ void memenc_finish_kernel(const float* __restrict__ x, const float* __restrict__ score,
                                      const float* __restrict__ no_obj, __nv_bfloat16* __restrict__ out, int B,
                                      int T, int C) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long n = static_cast<long long>(B) * T * C;
   if (i >= n) return;
@@ -119,7 +122,7 @@ int ds2_prompt_tokens(const float* coords, const int32_t* labels, int32_t B, int
               "ds2_prompt_tokens: bad args");
   DS2_REQUIRE(P == 0 || (coords && labels), DS2_E_ARG, "ds2_prompt_tokens: P > 0 needs coords and labels");
   const int nt = n_out + P + 1;
-  prompt_tokens_kernel<<<B * nt, 128, 0, as_stream(stream)>>>(coords, labels, B, P, gauss, point_emb, not_a_point,
+  DS2_LAUNCH((prompt_tokens_kernel), B * nt, 128, 0, as_stream(stream), coords, labels, B, P, gauss, point_emb, not_a_point,
                                                            out_tokens, n_out, image_size, tokens);
   return post_launch("prompt_tokens_kernel");
 }
@@ -128,7 +131,7 @@ int ds2_bank_ptr_pe(const float* ptr, float dist_norm, const float* w, const flo
                     void* val_bf16, int32_t B, int64_t dst_bs, int32_t row0, void* stream) {
   using namespace ds2;
   DS2_REQUIRE(ptr && w && bias && kin_bf16 && val_bf16 && B > 0, DS2_E_ARG, "ds2_bank_ptr_pe: bad args");
-  bank_ptr_pe_kernel<<<B, 256, 0, as_stream(stream)>>>(ptr, dist_norm, w, bias,
+  DS2_LAUNCH((bank_ptr_pe_kernel), B, 256, 0, as_stream(stream), ptr, dist_norm, w, bias,
                                                      reinterpret_cast<__nv_bfloat16*>(kin_bf16),
                                                      reinterpret_cast<__nv_bfloat16*>(val_bf16), dst_bs, row0);
   return post_launch("bank_ptr_pe_kernel");
@@ -140,7 +143,7 @@ int ds2_memenc_finish(const float* x, const float* score, const float* no_obj_em
   DS2_REQUIRE(x && score && no_obj_embed && out_bf16 && B > 0 && T > 0 && C > 0, DS2_E_ARG,
               "ds2_memenc_finish: bad args");
   const long long n = static_cast<long long>(B) * T * C;
-  memenc_finish_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+  DS2_LAUNCH((memenc_finish_kernel), static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream), 
       x, score, no_obj_embed, reinterpret_cast<__nv_bfloat16*>(out_bf16), B, T, C);
   return post_launch("memenc_finish_kernel");
 }

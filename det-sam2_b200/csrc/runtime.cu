@@ -6,6 +6,8 @@
 #include <unordered_map>
 #include <string>
 
+#include <stdlib.h>
+
 #include "common.h"
 
 namespace ds2 {
@@ -117,6 +119,14 @@ int make_tmap(CUtensorMap* out, const void* base, int elt_bytes, int swizzle_byt
   }
   *out = m;
   return DS2_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DS2_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 int sm_count() {

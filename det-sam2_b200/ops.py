@@ -71,8 +71,13 @@ def gemm(a, w, *, bias=None, act=0, gamma=None, residual=None, res_row_mod=0, ou
     _chk(_lib().ds2_gemm(C.byref(g), _stream()), "ds2_gemm")
 
 
-def flash_attn(q, k, v, out, scale, impl=0):
+_FLASH_IMPL = int(__import__("os").environ.get("DS2_FLASH_IMPL", "0"))  # kernel-variant A/B switch (tuning only)
+
+
+def flash_attn(q, k, v, out, scale, impl=None):
     """q [B,Lq,256] k [B,Lk,256] v [B,Lk,DV] out [B,Lq,DV], bf16; last dim contiguous."""
+    if impl is None:
+        impl = _FLASH_IMPL
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
         _req(t, BF16, "flash." + n)
         assert t.stride(2) == 1

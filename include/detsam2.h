@@ -84,6 +84,11 @@ typedef struct ds2_flash_args {
 } ds2_flash_args;
 int ds2_flash_attn(const ds2_flash_args* args, void* stream);
 
+/* Tuning aid: barrier-stall cycle counters of flash launches made with impl == 8 (summed over CTAs):
+ * [0] K-tile wait [1] V-tile wait [2] P wait [3] MMA-warp cycles [4] S wait [5] O wait [6] softmax-warp
+ * cycles [7] CTAs.  Synchronises the device.  No reference counterpart. */
+int ds2_debug_flash_stalls(unsigned long long* out8, int reset);
+
 /* ---- generic multi-head attention with optional window addressing (Hiera, mask decoder) ------
  * replaces F.scaled_dot_product_attention in MultiScaleAttention.forward
  * (backbones/hieradet.py:57-82, window_partition/unpartition backbones/utils.py:16-63) and in

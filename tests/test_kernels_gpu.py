@@ -139,7 +139,13 @@ def test_gemm_rejects_cpu_and_misaligned(ops):
 @pytest.mark.parametrize("B,Lq,Lk,DV,impl,qmul", [
     (1, 128, 128, 64, 0, 1.0), (2, 300, 517, 64, 0, 1.0), (2, 256, 3000, 64, 0, 6.0),
     (2, 512, 1000, 256, 0, 1.0), (1, 256, 3000, 256, 0, 6.0),
-    (2, 512, 1000, 64, 3, 1.0), (2, 256, 3000, 64, 3, 6.0), (3, 4096, 4 + 2 * 4096, 64, 0, 1.0)])
+    (2, 512, 1000, 64, 3, 1.0), (2, 256, 3000, 64, 3, 6.0), (3, 4096, 4 + 2 * 4096, 64, 0, 1.0),
+    # impl 2 = Q as a shared-memory operand (impl 0 keeps Q in TMEM); odd key counts so the masked tail
+    # falls into either column half of the split-row softmax (impl 9)
+    (2, 300, 517, 64, 2, 1.0), (2, 512, 1000, 256, 2, 1.0), (2, 256, 3000, 64, 2, 6.0),
+    (1, 200, 128 + 3, 64, 9, 1.0), (1, 200, 128 + 67, 64, 9, 3.0), (1, 130, 64 + 5, 256, 9, 1.0),
+    (1, 130, 64 + 37, 256, 9, 3.0), (2, 300, 517, 64, 9, 1.0), (2, 512, 1000, 256, 9, 1.0),
+    (2, 256, 3000, 64, 9, 6.0), (1, 200, 128 + 67, 64, 0, 3.0), (1, 130, 64 + 37, 256, 0, 3.0)])
 def test_flash(ops, B, Lq, Lk, DV, impl, qmul):
     torch.manual_seed(5)
     q = bf(qmul * torch.randn(B, Lq, 256, device=DEV))
