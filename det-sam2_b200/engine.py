@@ -83,6 +83,7 @@ class _SeamGraphs:
         self.device, self.enabled, self.min_hits, self.max_graphs = device, enabled, min_hits, max_graphs
         self.hits = {}
         self.graphs = {}   # key -> (CUDAGraph, static_inputs, outputs)
+        self.static_cache = {}
         self.pool = None
         self.replays = 0
         self.captures = 0
@@ -102,7 +103,15 @@ class _SeamGraphs:
                 if len(self.hits) > 4096:
                     self.hits.clear()
                 return body({k: v.to(self.device, non_blocking=True) for k, v in inputs.items()})
-            static = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in inputs.items()}
+            # static inputs are shared by all graphs of one seam (same name/shape/dtype): graphs of a seam
+            # never run concurrently, and the ~20 bank-size signatures of the memory-attention seam would
+            # otherwise each pin their own copy (device memory must stay flat over an endless stream)
+            static = {}
+            for k, v in inputs.items():
+                ck = (key[0], k, tuple(v.shape), v.dtype)
+                if ck not in self.static_cache:
+                    self.static_cache[ck] = torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                static[k] = self.static_cache[ck]
             for k, v in inputs.items():
                 static[k].copy_(v, non_blocking=True)
             body(static)  # eager on the static buffers: workspaces, TMA descriptors, func attributes exist
@@ -610,7 +619,10 @@ class CudaEngine:
             ops.layernorm(x2, p[w + "n3.w"], p[w + "n3.b"], 1e-5, out_bf16=t16)
             ops.gemm(t16, p[w + "ff1.w"], bias=p[w + "ff1.b"], act=1, out_bf16=hff)
             ops.gemm(hff, p[w + "ff2.w"], bias=p[w + "ff2.b"], residual=x2, out_f32=x2)
-        out = torch.empty((B, T, D), dtype=F32, device=self.device)
+        # a workspace, not a fresh tensor: the conditioned features are consumed by the mask decoder of the
+        # same step, and a per-graph output buffer (B*T*D f32 = 268 MB at 16 objects) for each of the ~20
+        # bank-size signatures would grow device memory while the window fills
+        out = self._buf("ma_out", (B, T, D), F32)
         ops.layernorm(x2, p["ma.norm.w"], p["ma.norm.b"], 1e-5, out_f32=out.view(B * T, D))
         return (out,)
 

@@ -425,6 +425,12 @@ def two_way_transformer(sd, cfg, src, pos_src, tokens):
     return queries, keys
 
 
+# Tests set this to a list to record the two data-dependent DISCRETE choices of the prompted decode
+# (stability fallback, mask_decoder.py:261-296, and the argmax-IoU pick): with seeded random weights
+# they can be near ties, and a bf16 implementation may then legitimately choose the other mask.
+DECISION_LOG = None
+
+
 def mask_decoder(sd, cfg, image_embeddings, image_pe, sparse, dense, multimask_output, high_res_features):
     """MaskDecoder.forward / predict_masks (mask_decoder.py:105-247) + stability fallback (:249-296)."""
     d = "sam_mask_decoder."
@@ -463,6 +469,10 @@ def mask_decoder(sd, cfg, image_embeddings, image_pe, sparse, dense, multimask_o
             au = (sm > -dl).sum(-1).float()
             stab = torch.where(au > 0, ai / au, torch.ones_like(au))
             stable = stab >= cfg.dynamic_multimask_stability_thresh
+            if DECISION_LOG is not None:
+                top2 = torch.topk(mi, 2, dim=-1).values
+                DECISION_LOG.append({"stability": stab.reshape(-1).tolist(), "stable": stable.reshape(-1).tolist(),
+                                     "iou_top2_margin": (top2[:, 0] - top2[:, 1]).tolist()})
             masks = torch.where(stable[..., None, None], masks[:, 0:1], mm[bi, best].unsqueeze(1))
             iou_pred = torch.where(stable, iou_pred[:, 0:1], mi[bi, best].unsqueeze(1))
         else:

@@ -1,0 +1,167 @@
+"""BASELINE.json configs beyond the headline one, on the CUDA engine through the drop-in API:
+
+  * the other model sizes of the family (small, base_plus: window 14/7 with zero-padded windows, other
+    stage depths / global-attention blocks) against the fp32 CPU oracle on the same seeded inputs;
+  * configs[2]: base_plus, 1280x720 frames, preload memory bank (pickled, det_sam2_RT.py:489-503) + the
+    constant-memory window (max_inference_state_frames + release_old_frames), driven by VideoProcessor —
+    device memory must stay flat over the stream and every frame must come back segmented;
+  * configs[4]: 64 tracked objects on the large model (memory-attention stress, N = 7*4096 + 64 keys once
+    the bank is full): object-batch independence and finiteness at B = 64.
+
+The oracle finishes these sizes in seconds; full-size stress uses size-independent properties.
+"""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt().clamp_min(1e-12)).item()
+
+
+def _engine(name):
+    from detsam2_b200.config import get_config
+    from detsam2_b200.engine import CudaEngine
+    from detsam2_b200.weights import synthetic_state_dict
+    cfg = get_config(name)
+    sd = synthetic_state_dict(cfg, 0)
+    return cfg, sd, CudaEngine(cfg, sd, device="cuda:0")
+
+
+@pytest.mark.parametrize("name,hw,seed", [("small", (512, 640), 3), ("base_plus", (720, 1280), 2)])
+def test_model_family_tracked_frames_match_oracle(name, hw, seed):
+    """2 objects, boxes on frame 0, two tracked frames; every stored output vs the fp32 oracle.  Tolerances
+    are those of the large-model test (bf16 operands / fp32 accumulation against an fp32 reference).
+
+    The prompted decode makes two DISCRETE data-dependent choices per object (stability fallback at 0.98,
+    mask_decoder.py:261-296, then argmax over the predicted IoUs).  With seeded random weights these can be
+    near ties (base_plus, seed 3: top-2 IoU margin 0.008) and a bf16 implementation then legitimately picks
+    the other mask, after which nothing is comparable.  The seeds are chosen so that the fp32 oracle's own
+    margins are wide, and the test asserts that they are."""
+    from detsam2_b200.predictor import SAM2VideoPredictor
+    from detsam2_b200.synthetic import BilliardVideo
+    from oracle import sam2_oracle as O
+    cfg, sd, eng = _engine(name)
+    torch.set_num_threads(os.cpu_count() or 1)
+    vid = BilliardVideo(num_objects=2, height=hw[0], width=hw[1], num_frames=3, seed=seed)
+    frames = list(vid.frames())
+    outs = {}
+    O.DECISION_LOG = []
+    with torch.inference_mode():
+        for tag, e in (("cuda", eng), ("oracle", O.OracleEngine(cfg, sd, fill_holes=True))):
+            pred = SAM2VideoPredictor(e, fill_hole_area=8)
+            st = pred.init_state(frames)
+            for oid, box in vid.boxes(0).items():
+                pred.add_new_points_or_box(st, 0, oid, box=box)
+            masks = {f: m.float().cpu() for f, _, m in pred.propagate_in_video(st)}
+            outs[tag] = (masks, st)
+    decisions, O.DECISION_LOG = O.DECISION_LOG, None
+    assert len(decisions) == 2
+    for d in decisions:
+        assert abs(d["stability"][0] - cfg.dynamic_multimask_stability_thresh) > 0.01, d
+        assert d["stable"][0] or d["iou_top2_margin"][0] > 0.03, d
+    for f in (1, 2):
+        oc = outs["cuda"][1]["output_dict"]["non_cond_frame_outputs"][f]
+        oo = outs["oracle"][1]["output_dict"]["non_cond_frame_outputs"][f]
+        assert _rel(oc["pred_masks"], oo["pred_masks"]) < 0.06, (name, f)
+        assert _rel(oc["maskmem_features"].float(), oo["maskmem_features"].float()) < 0.02, (name, f)
+        assert _rel(oc["obj_ptr"], oo["obj_ptr"]) < 0.08, (name, f)
+        assert (oc["object_score_logits"].cpu() - oo["object_score_logits"]).abs().max() < 0.1, (name, f)
+        assert tuple(outs["cuda"][0][f].shape) == (2, 1, hw[0], hw[1])
+        assert _rel(outs["cuda"][0][f], outs["oracle"][0][f]) < 0.06, (name, f)
+
+
+def test_config3_preload_bank_constant_memory_stream(tmp_path):
+    """configs[2] at reduced length: base_plus, 720p, bank built with detect_interval = 1 and nothing released
+    (det_sam2_RT.py:67-68), pickled, then a 48-frame stream in chunks of 6 with reverse window M = 12 and
+    state window S = 12 against the preloaded bank, no further detections (detect_interval = -1)."""
+    from detsam2_b200.predictor import SAM2VideoPredictor
+    from detsam2_b200.synthetic import BilliardVideo, GroundTruthDetector
+    from detsam2_b200.video_processor import VideoProcessor
+    cfg, sd, eng = _engine("base_plus")
+    H, W, nobj, pre, live = 720, 1280, 3, 4, 48
+    vid = BilliardVideo(num_objects=nobj, height=H, width=W, num_frames=pre + live, seed=9)
+    bank = str(tmp_path / "bank.pkl")
+    with torch.inference_mode():
+        vp = VideoProcessor(predictor=SAM2VideoPredictor(eng, fill_hole_area=8),
+                            detector=GroundTruthDetector(vid, detect_interval=1), frame_buffer_size=pre,
+                            detect_interval=1, max_frame_num_to_track=pre, max_inference_state_frames=-1,
+                            save_inference_state_path=bank)
+        vp.run(frames=(vid.frame(t) for t in range(pre)))
+        assert sorted(vp.video_segments) == list(range(pre))
+        with open(bank, "rb") as f:
+            st = pickle.load(f)
+        assert sorted(st["output_dict"]["cond_frame_outputs"]) == list(range(pre))  # every bank frame is a cond frame
+        del st, vp
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+
+        mem = []
+        vp = VideoProcessor(predictor=SAM2VideoPredictor(eng, fill_hole_area=8), detector=None, frame_buffer_size=6,
+                            detect_interval=-1, max_frame_num_to_track=12, max_inference_state_frames=12,
+                            load_inference_state_path=bank)
+        orig = vp.Detect_and_SAM2_inference
+
+        def chunk(frame_idx):
+            orig(frame_idx)
+            torch.cuda.synchronize()
+            mem.append((torch.cuda.memory_allocated(), len(vp.inference_state["images_idx"]),
+                        len(vp.inference_state["output_dict"]["non_cond_frame_outputs"])))
+
+        vp.Detect_and_SAM2_inference = chunk
+        segs = vp.run(frames=(vid.frame(t) for t in range(pre, pre + live)))
+    assert sorted(segs) == list(range(live))                       # re-based past the preload frames
+    for t in range(live):
+        assert sorted(segs[t]) == list(range(nobj))
+        for m in segs[t].values():
+            assert m.shape == (1, H, W) and m.dtype == np.bool_
+    # the tracker keeps hold of the balls: the mask of an object overlaps its ground-truth disc late in the stream
+    t = live - 1
+    for oid, (x0, y0, x1, y1) in vid.boxes(pre + t).items():
+        assert segs[t][oid].any(), oid
+    # constant-memory window: the state never holds more than S frames / outputs beyond the bank ...
+    assert len(mem) == live // 6
+    assert max(m[1] for m in mem[2:]) <= 12 + pre and max(m[2] for m in mem[2:]) <= 12
+    # ... and allocated device memory is flat after the window has filled (chunk 3 on), SURVEY.md §8d config 3
+    base = mem[2][0]
+    assert max(m[0] for m in mem[2:]) <= base + 32 * 2 ** 20, [m[0] >> 20 for m in mem]
+
+
+def test_config5_64_objects_memory_attention_stress():
+    """configs[4]: 64 objects, large model.  Object 0 and object 63 tracked inside the 64-object batch must
+    equal the same objects tracked alone (no cross-object interaction, no batch-size-dependent path)."""
+    from detsam2_b200.predictor import SAM2VideoPredictor
+    from detsam2_b200.synthetic import BilliardVideo
+    cfg, sd, eng = _engine("large")
+    B = 64
+    vid = BilliardVideo(num_objects=B, height=1024, width=1024, num_frames=4, seed=12)
+    frames = list(vid.frames())
+
+    def run(ids):
+        pred = SAM2VideoPredictor(eng, fill_hole_area=8)
+        with torch.inference_mode():
+            st = pred.init_state(frames)
+            for oid in ids:
+                pred.add_new_points_or_box(st, 0, oid, box=vid.boxes(0)[oid])
+            last = None
+            for f, oids, m in pred.propagate_in_video(st):
+                last = m
+        o = st["output_dict"]["non_cond_frame_outputs"][3]
+        return last, {k: o[k].float().clone() for k in ("pred_masks", "obj_ptr", "maskmem_features", "object_score_logits")}
+
+    last, full = run(list(range(B)))
+    assert tuple(last.shape) == (B, 1, 1024, 1024) and bool(torch.isfinite(last).all())
+    assert tuple(full["maskmem_features"].shape) == (B, 64, 64, 64)
+    for k, v in full.items():
+        assert bool(torch.isfinite(v).all()), k
+    for oid in (0, 63):
+        _, solo = run([oid])
+        for k in full:
+            r = _rel(full[k][oid:oid + 1], solo[k])
+            assert r < 5e-3, (oid, k, r)
