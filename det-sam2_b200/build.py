@@ -18,6 +18,7 @@ SOURCES = [
     "gemm_tc.cu",
     "flash_tc.cu",
     "mha.cu",
+    "win_attn_tc.cu",
     "elementwise.cu",
     "conv.cu",
     "decoder.cu",

@@ -91,6 +91,7 @@ SYMBOLS = {
     "ds2_gemm": (C.c_int, [C.POINTER(GemmArgs), _P]),
     "ds2_flash_attn": (C.c_int, [C.POINTER(FlashArgs), _P]),
     "ds2_debug_flash_stalls": (C.c_int, [C.POINTER(C.c_ulonglong), C.c_int]),
+    "ds2_debug_win_times": (C.c_int, [C.POINTER(C.c_longlong)]),
     "ds2_mha": (C.c_int, [C.POINTER(MhaArgs), _P]),
     "ds2_layernorm": (C.c_int, [C.POINTER(LnArgs), _P]),
     "ds2_axpby": (C.c_int, [_P, _P, _L, _I, _I, _F, _F, _P, _P, _P]),

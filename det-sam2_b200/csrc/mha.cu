@@ -8,6 +8,7 @@
 // (These are <2 % of the frame's FLOPs; the d=256 memory attention uses the tcgen05 kernel in
 // flash_tc.cu.)
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.h"
 
@@ -329,6 +330,8 @@ static int launch_mha(const MhaParams& p, int nseq, int H, int Lq, cudaStream_t 
   return launch_mha_nw<DP, 4>(p, dim3(nseq, H, (Lq + 63) / 64), st);
 }
 
+int launch_win16_attn_tc(const ds2_mha_args* a, cudaStream_t st);  // win_attn_tc.cu (tcgen05)
+
 }  // namespace ds2
 
 extern "C" int ds2_mha(const ds2_mha_args* a, void* stream) {
@@ -387,6 +390,18 @@ extern "C" int ds2_mha(const ds2_mha_args* a, void* stream) {
   }
   DS2_REQUIRE((Lq + 63) / 64 <= 65535 && a->H <= 65535, DS2_E_ARG, "ds2_mha: grid too large");
   cudaStream_t st = as_stream(stream);
+  {
+    // Hiera stage-3 windows (16x16 tokens, head_dim 72) run on the tensor-memory kernel; DS2_WIN_TC=0 keeps
+    // them on the generic mma.sync kernel (A/B testing)
+    static const bool win_tc = [] {
+      const char* e = getenv("DS2_WIN_TC");
+      return !(e && e[0] == '0');
+    }();
+    if (win_tc) {
+      const int rc = launch_win16_attn_tc(a, st);
+      if (rc >= 0) return rc;
+    }
+  }
   const int D = a->D;
   if (D <= 16) return launch_mha<16>(p, nseq, a->H, Lq, st);
   if (D <= 32) return launch_mha<32>(p, nseq, a->H, Lq, st);

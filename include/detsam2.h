@@ -88,6 +88,9 @@ int ds2_flash_attn(const ds2_flash_args* args, void* stream);
  * [0] K-tile wait [1] V-tile wait [2] P wait [3] MMA-warp cycles [4] S wait [5] O wait [6] softmax-warp
  * cycles [7] CTAs.  Synchronises the device.  No reference counterpart. */
 int ds2_debug_flash_stalls(unsigned long long* out8, int reset);
+/* Tuning aid: phase timestamps (cycles since kernel start) of CTA 0 of the last windowed-attention launch made
+ * with DS2_WIN_DBG=1 in the environment.  Synchronises the device.  No reference counterpart. */
+int ds2_debug_win_times(long long* out16);
 
 /* ---- generic multi-head attention with optional window addressing (Hiera, mask decoder) ------
  * replaces F.scaled_dot_product_attention in MultiScaleAttention.forward

@@ -214,7 +214,9 @@ def _window_unpartition(win, w, pad_hw, hw):
 
 @pytest.mark.parametrize("Hm,w,heads,D,pool", [(32, 8, 2, 72, 0), (32, 8, 2, 72, 1), (16, 4, 4, 72, 0),
                                                 (16, 4, 2, 72, 1), (32, 16, 4, 72, 0), (32, 14, 2, 56, 0),
-                                                (32, 14, 2, 56, 1), (16, 7, 2, 96, 0)])
+                                                (32, 14, 2, 56, 1), (16, 7, 2, 96, 0),
+                                                # 16x16 windows with head_dim in (64, 80]: the tcgen05 kernel
+                                                (64, 16, 8, 72, 0), (32, 16, 3, 80, 0), (16, 16, 1, 72, 0)])
 def test_mha_window(ops, Hm, w, heads, D, pool):
     """qkv token-major [B, Hm*Wm, 3*heads*D] exactly as MultiScaleAttention consumes it
     (hieradet.py:57-82), including zero-pad windows whose pad tokens carry the qkv bias."""
