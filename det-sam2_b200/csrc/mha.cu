@@ -331,6 +331,7 @@ static int launch_mha(const MhaParams& p, int nseq, int H, int Lq, cudaStream_t 
 }
 
 int launch_win16_attn_tc(const ds2_mha_args* a, cudaStream_t st);  // win_attn_tc.cu (tcgen05)
+int launch_glob_attn_tc(const ds2_mha_args* a, cudaStream_t st);   // win_attn_tc.cu (tcgen05)
 
 }  // namespace ds2
 
@@ -391,14 +392,16 @@ extern "C" int ds2_mha(const ds2_mha_args* a, void* stream) {
   DS2_REQUIRE((Lq + 63) / 64 <= 65535 && a->H <= 65535, DS2_E_ARG, "ds2_mha: grid too large");
   cudaStream_t st = as_stream(stream);
   {
-    // Hiera stage-3 windows (16x16 tokens, head_dim 72) run on the tensor-memory kernel; DS2_WIN_TC=0 keeps
+    // Hiera stage-3 windows (16x16 tokens, head_dim 72) and global blocks run on the tensor-memory kernels; DS2_WIN_TC=0 keeps
     // them on the generic mma.sync kernel (A/B testing)
     static const bool win_tc = [] {
       const char* e = getenv("DS2_WIN_TC");
       return !(e && e[0] == '0');
     }();
     if (win_tc) {
-      const int rc = launch_win16_attn_tc(a, st);
+      int rc = launch_win16_attn_tc(a, st);
+      if (rc >= 0) return rc;
+      rc = launch_glob_attn_tc(a, st);
       if (rc >= 0) return rc;
     }
   }

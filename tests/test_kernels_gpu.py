@@ -182,7 +182,9 @@ def _mha_ref(q, k, v, scale, Lk_valid=None):
 
 
 @pytest.mark.parametrize("B,H,D,Lq,Lk,Lkv", [(2, 8, 16, 9, 4096, 0), (2, 8, 16, 4096, 16, 9), (3, 8, 32, 8, 16, 8),
-                                              (1, 8, 72, 1024, 1024, 0), (1, 2, 96, 100, 130, 0)])
+                                              (1, 8, 72, 1024, 1024, 0), (1, 2, 96, 100, 130, 0),
+                                              # head_dim in (64, 80], Lq / Lk multiples of 128: tcgen05 flash loop
+                                              (2, 4, 72, 256, 384, 0), (1, 2, 80, 128, 128, 0), (1, 8, 72, 4096, 4096, 0)])
 def test_mha_dense(ops, B, H, D, Lq, Lk, Lkv):
     torch.manual_seed(7)
     q = bf(torch.randn(B, Lq, H, D, device=DEV))
