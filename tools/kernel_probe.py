@@ -1,7 +1,7 @@
 """Isolated timing of the hot kernel shapes of the large model (back-to-back launches, CUDA events), and a
 one-launch-per-shape mode for `ncu --set full`.
 
-usage: python tools/kernel_probe.py [--iters 50] [--once] [--only NAME_SUBSTR]
+usage: python tools/kernel_probe.py [--iters 50] [--once] [--only NAME_SUBSTR[,NAME_SUBSTR...]]
 """
 import argparse
 import math
@@ -105,7 +105,7 @@ def main():
                   2.0 * 16 * 4096 * 4096 * 512, None))
     lines = []
     for name, fn, flops, nbytes in cases:
-        if args.only and args.only not in name:
+        if args.only and not any(o in name for o in args.only.split(",")):
             continue
         if args.once:
             fn()
