@@ -216,9 +216,13 @@ def run_ours(args):
         fm = _flops_model(cfg, B, N)
         avg_ms = sum(durs) / len(durs)
         achieved = fm["cross_exec_per_launch"] / (avg_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "flash_d256_tcgen05_kernel<DV=64> (memory cross-attention)",
+        roof = {"bound": "tensor", "kernel": "flash_d256_tcgen05_kernel<DV=64,BN=128,QT=1> (memory cross-attention, Q in TMEM)",
                 "achieved": round(achieved, 1), "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": round(achieved / peaks["tflops_sustained"], 4), "traffic": None,
+                "frac": round(achieved / peaks["tflops_sustained"], 4),
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture of the
+                # same shape (B=16, N=28736): profiles/r1_s8_attn_gemm_ncu_full_summary.txt; algorithmic 336 MB
+                "traffic": 379.9e6 if (B == 16 and N == 28736) else None, "traffic_unit": "bytes/launch",
+                "algorithmic_bytes_per_launch": int(2 * B * (T * 256 + N * 256 + N * 64 + T * 64)),
                 "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step)",
                 "avg_launch_ms": round(avg_ms, 4), "launches_timed": len(durs), "keys_N": N,
                 "flops_per_launch_executed": fm["cross_exec_per_launch"],
