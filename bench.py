@@ -116,7 +116,9 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)  # timing barrier / max only; no data-path collective
+        # timing barrier / max-over-ranks only: there is NO collective on the data path (one independent video
+        # stream per GPU), so the host-side gloo backend is enough — no NCCL communicator, kernels or banner
+        dist.init_process_group("gloo")
     from detsam2_b200 import ops
     from detsam2_b200.build_sam import build_sam2_video_predictor
     from detsam2_b200.synthetic import BilliardVideo
@@ -195,7 +197,7 @@ def run_ours(args):
             for tag, a, b, meta in timers:
                 kern.setdefault(tag, []).append((a.elapsed_time(b), meta))
         if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            t = torch.tensor([ms], dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = t.item()
         results[mode] = ms

@@ -1,6 +1,6 @@
 """Multi-GPU = independent video streams: the memory bank, prompts and outputs are per
 session, so stream s runs on rank s mod world_size, weights are replicated, and NO collective sits on
-the data path.  ``torch.distributed`` (nccl on GPUs, gloo in the CPU tests) is used only for the
+the data path.  ``torch.distributed`` (host-side gloo: no NCCL communicator is ever created) is used only for the
 timing barrier and the max-over-ranks reduction of the measured time.
 """
 import os
