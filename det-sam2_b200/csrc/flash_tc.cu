@@ -38,6 +38,13 @@ constexpr int kQM = 128;
 struct FlashParams {
   int B, Lq, Lk;
   float scale_log2;
+  // Tail split: the grid is 1-D; the first n_full CTAs each own one (query tile, batch) item and all its key
+  // tiles; the remaining items (the partial last wave) are split `nsplit` ways over the key tiles so that
+  // the tail wave takes 1/nsplit of a full item.  Split parts leave (O, max, sum) partials in `ws`; the part that
+  // arrives last (atomic counter per item) combines them in part order and writes the output.
+  int n_full, nsplit, q_tiles;
+  float* ws;               // [tail items][nsplit][128 rows][DV + 4] f32
+  unsigned int* ws_count;  // [tail items], zero between launches
   int dbg;                 // timing experiments only (impl 5/6): 1 = load half of each K tile, 2 = skip the exps
   const __nv_bfloat16* q;  // QT kernels read the query rows straight from global memory
   long long ldq, bsq;
@@ -109,9 +116,18 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * (kQM * NQ);
-  const int b = blockIdx.y;
-  const int n_tiles = (p.Lk + BN - 1) / BN;
+  int item = blockIdx.x, kv_part = 0, kv_parts = 1;
+  if (item >= p.n_full) {
+    const int t = item - p.n_full;
+    item = p.n_full + t / p.nsplit;
+    kv_part = t % p.nsplit;
+    kv_parts = p.nsplit;
+  }
+  const int q0 = (item % p.q_tiles) * (kQM * NQ);
+  const int b = item / p.q_tiles;
+  const int all_tiles = (p.Lk + BN - 1) / BN;
+  const int j0 = (all_tiles * kv_part) / kv_parts;                     // first key tile of this CTA
+  const int n_tiles = (all_tiles * (kv_part + 1)) / kv_parts - j0;    // its number of key tiles (>= 1)
 
   if (warp == 0 && lane == 0) {
     if (!QT) tc::prefetch_tmap(&tmap_q);
@@ -175,7 +191,7 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tc::mbar_expect_tx(bar(o_kfull, s), nkk * (BN * 128));
         const uint32_t sk = sk0 + s * Cfg::kKBytes;
         for (int kk = 0; kk < nkk; ++kk)
-          tc::tma_load_3d(sk + kk * (BN * 128), &tmap_k, bar(o_kfull, s), kk * 64, j * BN, b);
+          tc::tma_load_3d(sk + kk * (BN * 128), &tmap_k, bar(o_kfull, s), kk * 64, (j0 + j) * BN, b);
       }
       {
         const int s = j % VS;
@@ -183,7 +199,7 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tc::mbar_expect_tx(bar(o_vfull, s), Cfg::kVBytes);
         const uint32_t sv = sv0 + s * Cfg::kVBytes;
         for (int nn = 0; nn < DV / 64; ++nn)
-          tc::tma_load_3d(sv + nn * (BN * 128), &tmap_v, bar(o_vfull, s), nn * 64, j * BN, b);
+          tc::tma_load_3d(sv + nn * (BN * 128), &tmap_v, bar(o_vfull, s), nn * 64, (j0 + j) * BN, b);
       }
     }
   } else if (warp == 1 && tc::elect_one()) {
@@ -303,7 +319,7 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tc::tmem_ld32(ts + part * CW + c * 32, chunk);
       }
       tc::tmem_ld_wait();
-      const int valid = p.Lk - j * BN - part * CW;  // columns >= valid are TMA zero fill -> mask
+      const int valid = p.Lk - (j0 + j) * BN - part * CW;  // columns >= valid are TMA zero fill -> mask
       if (valid < CW) {
 #pragma unroll
         for (int i = 0; i < CW; ++i)
@@ -410,8 +426,78 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     // epilogue: O / l -> bf16 -> global
     tc::mbar_wait(bar(o_odone, h), (n_tiles - 1) & 1);
     tc::tc_fence_after();
-    const float inv = 1.0f / l;
     __nv_bfloat16* orow = p.out + static_cast<long long>(b) * p.bso + static_cast<long long>(row) * p.ldo + part * OW;
+    if (kv_parts > 1) {
+      // ---- split item: leave this part's (O, m, l) in the workspace; the last part to arrive combines ----
+      constexpr int WS_ROW = DV + 4;  // O row + (max, sum), padded to keep rows 16-byte aligned
+      const int slot = item - p.n_full;
+      float* wrow = p.ws + (static_cast<size_t>(slot * kv_parts + kv_part) * (NQ * kQM) + rloc) * WS_ROW;
+#pragma unroll
+      for (int c = 0; c < OW / 32; ++c) {
+        uint32_t o[32];
+        tc::tmem_ld32(to + c * 32, o);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          reinterpret_cast<uint4*>(wrow + part * OW + c * 32)[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+      }
+      if (part == 0) {
+        wrow[DV] = m_ref * p.scale_log2;
+        wrow[DV + 1] = l;
+      }
+      __threadfence();
+      asm volatile("bar.sync 15, %0;" ::"n"(128 * NQ * SP) : "memory");
+      const uint32_t flag = xch_base;  // the exchange buffer is idle now
+      if (warp == 2 && lane == 0) {
+        const unsigned int old = atomicAdd(p.ws_count + slot, 1u);
+        const unsigned int last = (old == static_cast<unsigned int>(kv_parts - 1)) ? 1u : 0u;
+        if (last) p.ws_count[slot] = 0u;  // every part has arrived: ready for the next launch
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(flag), "r"(last) : "memory");
+      }
+      asm volatile("bar.sync 15, %0;" ::"n"(128 * NQ * SP) : "memory");
+      unsigned int last;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(last) : "r"(flag) : "memory");
+      if (last) {
+        __threadfence();
+        const float* base = p.ws + (static_cast<size_t>(slot * kv_parts) * (NQ * kQM) + rloc) * WS_ROW;
+        const size_t pstride = static_cast<size_t>(NQ * kQM) * WS_ROW;
+        float mmax = -INFINITY;
+        for (int q = 0; q < kv_parts; ++q) mmax = fmaxf(mmax, __ldcg(base + q * pstride + DV));
+        float lt = 0.f;
+        for (int q = 0; q < kv_parts; ++q) lt += __ldcg(base + q * pstride + DV + 1) * ex2_approx(__ldcg(base + q * pstride + DV) - mmax);
+        const float inv = 1.0f / lt;
+#pragma unroll
+        for (int c = 0; c < OW / 32; ++c) {
+          float acc[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+          for (int q = 0; q < kv_parts; ++q) {  // fixed part order: the result does not depend on arrival order
+            const float w = ex2_approx(__ldcg(base + q * pstride + DV) - mmax);
+            const float4* src = reinterpret_cast<const float4*>(base + q * pstride + part * OW + c * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 v4 = __ldcg(src + i);
+              acc[4 * i] = fmaf(v4.x, w, acc[4 * i]);
+              acc[4 * i + 1] = fmaf(v4.y, w, acc[4 * i + 1]);
+              acc[4 * i + 2] = fmaf(v4.z, w, acc[4 * i + 2]);
+              acc[4 * i + 3] = fmaf(v4.w, w, acc[4 * i + 3]);
+            }
+          }
+          if (row < p.Lq) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 t;
+              t.x = tc::pack_bf16(acc[8 * i] * inv, acc[8 * i + 1] * inv);
+              t.y = tc::pack_bf16(acc[8 * i + 2] * inv, acc[8 * i + 3] * inv);
+              t.z = tc::pack_bf16(acc[8 * i + 4] * inv, acc[8 * i + 5] * inv);
+              t.w = tc::pack_bf16(acc[8 * i + 6] * inv, acc[8 * i + 7] * inv);
+              reinterpret_cast<uint4*>(orow + c * 32)[i] = t;
+            }
+          }
+        }
+      }
+    } else {
+    const float inv = 1.0f / l;
 #pragma unroll
     for (int c = 0; c < OW / 32; ++c) {
       uint32_t o[32];
@@ -429,6 +515,7 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
       }
     }
+    }  // unsplit item
   }
 
   tc::tc_fence_before();
@@ -521,7 +608,56 @@ static int launch_flash(const ds2_flash_args* a, cudaStream_t st) {
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   p.ldo = a->ldo;
   p.bso = a->bso;
-  dim3 grid((a->Lq + kQM * NQ - 1) / (kQM * NQ), a->B);
+  // ---- grid: full items + tail items split over the key tiles (see FlashParams) ----
+  p.q_tiles = (a->Lq + kQM * NQ - 1) / (kQM * NQ);
+  const int items = p.q_tiles * a->B;
+  const int sms = sm_count();
+  DS2_REQUIRE(sms > 0, DS2_E_NODEVICE, "ds2_flash_attn: no CUDA device");
+  const int all_tiles = (a->Lk + BN - 1) / BN;
+  int tail = items % sms, nsplit = 1;
+  // Opt-in (impl == 10): the split makes the summation order depend on the batch size and the SM count, which
+  // costs the engine its "an object tracked in a batch == tracked alone" invariant (differences at bf16-noise
+  // level, ~1e-2 relative) for ~10 % of this kernel's time; the default keeps one CTA per item.
+  if (NQ == 1 && tail > 0 && a->impl == 10) {
+    nsplit = sms / tail;
+    if (nsplit > 4) nsplit = 4;
+    if (nsplit > all_tiles) nsplit = all_tiles;
+  }
+  if (nsplit < 2) {
+    nsplit = 1;
+    tail = 0;
+  }
+  p.n_full = items - tail;
+  p.nsplit = nsplit;
+  p.ws = nullptr;
+  p.ws_count = nullptr;
+  if (tail > 0) {
+    // grow-only workspace owned by the library (one stream at a time, like every handle-less entry point);
+    // allocated on an eager call — the engine runs every new shape eagerly before capturing it into a graph
+    static float* ws = nullptr;
+    static unsigned int* ws_count = nullptr;
+    static size_t ws_bytes = 0;
+    const size_t need = static_cast<size_t>(tail) * nsplit * (NQ * kQM) * (DV + 4) * sizeof(float);
+    if (need > ws_bytes) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(st, &cs);
+      DS2_REQUIRE(cs == cudaStreamCaptureStatusNone, DS2_E_ARG,
+                  "ds2_flash_attn: first use of a larger split workspace inside a stream capture");
+      cudaStreamSynchronize(st);
+      if (ws) cudaFree(ws);
+      cudaError_t e = cudaMalloc(&ws, need);
+      DS2_REQUIRE(e == cudaSuccess, static_cast<int>(e), "ds2_flash_attn: workspace: %s", cudaGetErrorString(e));
+      ws_bytes = need;
+    }
+    if (!ws_count) {
+      cudaError_t e = cudaMalloc(&ws_count, 1024 * sizeof(unsigned int));
+      DS2_REQUIRE(e == cudaSuccess, static_cast<int>(e), "ds2_flash_attn: workspace: %s", cudaGetErrorString(e));
+      cudaMemset(ws_count, 0, 1024 * sizeof(unsigned int));
+    }
+    p.ws = ws;
+    p.ws_count = ws_count;
+  }
+  const int grid = p.n_full + tail * nsplit;
   DS2_LAUNCH((flash_d256_tcgen05_kernel<DV, BN, NQ, KS, VS, SP, QT>), grid, Cfg::kThreads, Cfg::kSmem, st, tq, tk, tv, p);
   return post_launch("flash_d256_tcgen05_kernel");
 }
@@ -561,6 +697,7 @@ extern "C" int ds2_flash_attn(const ds2_flash_args* a, void* stream) {
   //           tensor-bound; its bf16-rounded running max changes P by rounding noise, so not the default)
   //       2 = Q as a shared-memory operand (SS MMA), 3 = two query tiles per CTA / 64-key tiles (SS)
   //       5, 6, 8 = timing experiments (half K loads, no exps, barrier-stall accounting)
+  //       10 = default kernel with the partial last wave split over the key tiles (see launch_flash)
   if (a->DV == 64) {
     if (a->impl == 3) return launch_flash<64, 64, 2, 2, 3, 1, 0>(a, st);
     if (a->impl == 2) return launch_flash<64, 128, 1, 2, 2, 1, 0>(a, st);

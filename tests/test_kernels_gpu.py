@@ -145,7 +145,10 @@ def test_gemm_rejects_cpu_and_misaligned(ops):
     (2, 300, 517, 64, 2, 1.0), (2, 512, 1000, 256, 2, 1.0), (2, 256, 3000, 64, 2, 6.0),
     (1, 200, 128 + 3, 64, 9, 1.0), (1, 200, 128 + 67, 64, 9, 3.0), (1, 130, 64 + 5, 256, 9, 1.0),
     (1, 130, 64 + 37, 256, 9, 3.0), (2, 300, 517, 64, 9, 1.0), (2, 512, 1000, 256, 9, 1.0),
-    (2, 256, 3000, 64, 9, 6.0), (1, 200, 128 + 67, 64, 0, 3.0), (1, 130, 64 + 37, 256, 0, 3.0)])
+    (2, 256, 3000, 64, 9, 6.0), (1, 200, 128 + 67, 64, 0, 3.0), (1, 130, 64 + 37, 256, 0, 3.0),
+    # impl 10 = tail items split over the key tiles, partials combined by the last part to arrive
+    (2, 300, 517, 64, 10, 1.0), (2, 512, 1000, 256, 10, 1.0), (2, 256, 3000, 64, 10, 6.0),
+    (1, 4096, 4 + 4096, 64, 10, 1.0), (1, 4096, 4096, 256, 10, 1.0), (16, 1024, 1000, 64, 10, 3.0)])
 def test_flash(ops, B, Lq, Lk, DV, impl, qmul):
     torch.manual_seed(5)
     q = bf(qmul * torch.randn(B, Lq, 256, device=DEV))
