@@ -4,6 +4,8 @@
 // so the 1024^2 high-resolution mask is never written to HBM).
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.h"
 
 namespace ds2 {
@@ -64,10 +66,11 @@ __global__ void im2col_k3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
 }
 
 // ---- depth-wise 7x7, pad 3, channels-last f32 ---------------------------------------------------
-// One thread = one channel x DWX consecutive output pixels of one row: the 7 x (DWX+6) input window
-// slides through registers (7*(DWX+6)/DWX = 9.6 loads per output at DWX = 16 instead of 49); threads
-// of a warp are consecutive channels, so every load / store is one coalesced 128-byte line.
-template <int DWX>
+// One thread = one channel x (DWY rows x DWX columns) of outputs: each of the DWY+6 input rows of the patch is
+// loaded once (DWX+6 values) and feeds every output row it overlaps, so a thread issues
+// (DWY+6)(DWX+6)/(DWY*DWX) = 3.4 loads per output at 4 x 16 (9.6 with one output row, 49 naively); threads of
+// a warp are consecutive channels, so every load / store is one coalesced 128-byte line.
+template <int DWX, int DWY>
 __global__ void __launch_bounds__(256) dwconv7_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, float* __restrict__ y, int B,
                                                       int Hm, int Wm, int C) {
@@ -75,39 +78,53 @@ __global__ void __launch_bounds__(256) dwconv7_kernel(const float* __restrict__ 
   const int c = blockIdx.y * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const int tiles_x = (Wm + DWX - 1) / DWX;
+  const int tiles_y = (Hm + DWY - 1) / DWY;
   int t = blockIdx.x;
   const int tx = t % tiles_x;
   t /= tiles_x;
-  const int py = t % Hm;
-  const int b = t / Hm;
-  const int x0 = tx * DWX;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int x0 = tx * DWX, y0 = ty * DWY;
   float wr[49];
 #pragma unroll
   for (int i = 0; i < 49; ++i) wr[i] = __ldg(w + c * 49 + i);
-  float acc[DWX];
+  float acc[DWY][DWX];
   const float bv = bias ? __ldg(bias + c) : 0.f;
 #pragma unroll
-  for (int o = 0; o < DWX; ++o) acc[o] = bv;
+  for (int r = 0; r < DWY; ++r)
 #pragma unroll
-  for (int ky = 0; ky < 7; ++ky) {
-    const int iy = py - 3 + ky;
-    if (iy < 0 || iy >= Hm) continue;
-    const float* rowp = x + (static_cast<long long>(b) * Hm + iy) * Wm * C + c;
+    for (int o = 0; o < DWX; ++o) acc[r][o] = bv;
+#pragma unroll
+  for (int ri = 0; ri < DWY + 6; ++ri) {
+    const int iy = y0 - 3 + ri;
+    // no early-out on rows outside the map: with straight-line code the scheduler hoists the loads of row
+    // ri + 1 above the FMAs of row ri (zero rows contribute nothing)
+    const bool rv = iy >= 0 && iy < Hm;
+    const float* rowp = x + (static_cast<long long>(b) * Hm + (rv ? iy : 0)) * Wm * C + c;
     float row[DWX + 6];
 #pragma unroll
     for (int j = 0; j < DWX + 6; ++j) {
       const int ix = x0 - 3 + j;
-      row[j] = (ix >= 0 && ix < Wm) ? rowp[static_cast<long long>(ix) * C] : 0.f;
+      row[j] = (rv && ix >= 0 && ix < Wm) ? __ldg(rowp + static_cast<long long>(ix) * C) : 0.f;
     }
 #pragma unroll
-    for (int o = 0; o < DWX; ++o)
+    for (int r = 0; r < DWY; ++r) {
+      const int ky = ri - r;  // input row ri is tap row ky of output row r
+      if (ky < 0 || ky > 6) continue;
 #pragma unroll
-      for (int kx = 0; kx < 7; ++kx) acc[o] = fmaf(row[o + kx], wr[ky * 7 + kx], acc[o]);
+      for (int o = 0; o < DWX; ++o)
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) acc[r][o] = fmaf(row[o + kx], wr[ky * 7 + kx], acc[r][o]);
+    }
   }
-  float* yp = y + ((static_cast<long long>(b) * Hm + py) * Wm + x0) * C + c;
 #pragma unroll
-  for (int o = 0; o < DWX; ++o)
-    if (x0 + o < Wm) yp[static_cast<long long>(o) * C] = acc[o];
+  for (int r = 0; r < DWY; ++r) {
+    if (y0 + r >= Hm) continue;
+    float* yp = y + ((static_cast<long long>(b) * Hm + y0 + r) * Wm + x0) * C + c;
+#pragma unroll
+    for (int o = 0; o < DWX; ++o)
+      if (x0 + o < Wm) yp[static_cast<long long>(o) * C] = acc[r][o];
+  }
 }
 
 // ---- mask down-sampler stage 1 (fused) -----------------------------------------------------------
@@ -240,9 +257,14 @@ int ds2_dwconv7(const float* x, const float* w, const float* bias, float* y, int
   using namespace ds2;
   DS2_REQUIRE(x && w && y && B > 0 && Hm > 0 && Wm > 0 && C > 0, DS2_E_ARG, "ds2_dwconv7: bad args");
   constexpr int kDwx = 16;
+  static const int dwy = [] {
+    const char* e = getenv("DS2_DWCONV_DWY");  // tuning switch: output rows per thread (2 or 4)
+    return (e && e[0] == '2') ? 2 : 4;
+  }();
   const int threads = C >= 256 ? 256 : ((C + 31) / 32) * 32;
-  dim3 grid(static_cast<unsigned>(B) * Hm * ((Wm + kDwx - 1) / kDwx), (C + threads - 1) / threads);
-  DS2_LAUNCH((dwconv7_kernel<kDwx>), grid, threads, 0, as_stream(stream), x, w, bias, y, B, Hm, Wm, C);
+  dim3 grid(static_cast<unsigned>(B) * ((Hm + dwy - 1) / dwy) * ((Wm + kDwx - 1) / kDwx), (C + threads - 1) / threads);
+  if (dwy == 2) DS2_LAUNCH((dwconv7_kernel<kDwx, 2>), grid, threads, 0, as_stream(stream), x, w, bias, y, B, Hm, Wm, C);
+  else DS2_LAUNCH((dwconv7_kernel<kDwx, 4>), grid, threads, 0, as_stream(stream), x, w, bias, y, B, Hm, Wm, C);
   return post_launch("dwconv7_kernel");
 }
 

@@ -363,7 +363,8 @@ class CudaEngine:
 
         def mlp3(dst, prefixes):
             for j in range(3):
-                f32(f"{dst}.w{j + 1}", torch.stack([sd[f"{q_}layers.{j}.weight"] for q_ in prefixes]))
+                # input-major [set, in, out]: consecutive threads of ds2_mlp3 = consecutive outputs
+                f32(f"{dst}.w{j + 1}", torch.stack([sd[f"{q_}layers.{j}.weight"].t() for q_ in prefixes]))
                 f32(f"{dst}.b{j + 1}", torch.stack([sd[f"{q_}layers.{j}.bias"] for q_ in prefixes]))
 
         nmt = cfg.num_multimask_outputs + 1

@@ -190,7 +190,9 @@ def mlp3(x, w1, b1, w2, b2, w3, b3, y, *, rows, nmlp, gather=None, sigmoid_out=F
     a.x, a.ldx = x.data_ptr(), x.stride(0)
     a.gather = gather.data_ptr() if gather is not None else None
     a.rows, a.nmlp = rows, nmlp
-    a.din, a.dh, a.dout = w1.shape[-1], w1.shape[-2], w3.shape[-2]
+    # weights are input-major: w1 [nmlp, din, dh], w2 [nmlp, dh, dh], w3 [nmlp, dh, dout]
+    a.din, a.dh, a.dout = w1.shape[-2], w1.shape[-1], w3.shape[-1]
+    assert w2.shape[-2] == a.dh and w2.shape[-1] == a.dh and w3.shape[-2] == a.dh
     a.w1, a.b1, a.w2, a.b2, a.w3, a.b3 = (t.data_ptr() for t in (w1, b1, w2, b2, w3, b3))
     a.sigmoid_out = int(sigmoid_out)
     a.y, a.ldy = y.data_ptr(), y.stride(0)

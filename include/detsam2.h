@@ -177,7 +177,9 @@ int ds2_upscale2_masks(const float* g, const float* bias, const float* skip, con
                        void* stream);
 /* batched 3-layer MLP on small inputs: y[i] = W3 act(W2 act(W1 x[idx[i]] + b1) + b2) + b3
  * (hypernetwork / IoU / object-score / obj_ptr heads, sam2_utils.py:121-145).
- * nmlp independent weight sets laid out back to back; item i uses weight set i % nmlp.         */
+ * nmlp independent weight sets laid out back to back; item i uses weight set i % nmlp.
+ * Weights are INPUT-major: w1 [nmlp][din][dh], w2 [nmlp][dh][dh], w3 [nmlp][dh][dout] (the transpose of
+ * nn.Linear.weight), dh, dout <= 256.                                                          */
 typedef struct ds2_mlp3_args {
   const float* x; int64_t ldx; const int32_t* gather; /* optional row indices */
   int32_t rows, nmlp, din, dh, dout;

@@ -354,9 +354,9 @@ def test_im2col_k3s2_matches_conv(ops):
     assert (out - ref).abs().max().item() < 1e-3
 
 
-def test_dwconv7(ops):
+@pytest.mark.parametrize("B,Hm,C", [(2, 16, 64), (1, 18, 256), (3, 7, 32)])
+def test_dwconv7(ops, B, Hm, C):
     torch.manual_seed(14)
-    B, Hm, C = 2, 16, 64
     x = torch.randn(B, Hm, Hm, C, device=DEV)
     w, b = torch.randn(C, 1, 7, 7, device=DEV) / 7, torch.randn(C, device=DEV)
     y = torch.empty_like(x)
@@ -437,7 +437,8 @@ def test_mlp3(ops):
     w2, b2 = torch.randn(n, 256, 256, device=DEV) / 16, torch.randn(n, 256, device=DEV) * 0.1
     w3, b3 = torch.randn(n, 32, 256, device=DEV) / 16, torch.randn(n, 32, device=DEV) * 0.1
     y = torch.empty(B * n, 32, device=DEV)
-    ops.mlp3(x, w1, b1, w2, b2, w3, b3, y, rows=B * n, nmlp=n, sigmoid_out=True)
+    tr = lambda w: w.transpose(-1, -2).contiguous()  # the kernel takes input-major weights [set, in, out]
+    ops.mlp3(x, tr(w1), b1, tr(w2), b2, tr(w3), b3, y, rows=B * n, nmlp=n, sigmoid_out=True)
     xs = x.view(B, n, 256)
     h = torch.relu(torch.einsum("bnk,nok->bno", xs, w1) + b1)
     h = torch.relu(torch.einsum("bnk,nok->bno", h, w2) + b2)
@@ -445,7 +446,14 @@ def test_mlp3(ops):
     assert (y - ref).abs().max().item() < 1e-4
     gather = torch.tensor([3, 3, 0, 7], device=DEV, dtype=torch.int32)
     y2 = torch.empty(4, 32, device=DEV)
-    ops.mlp3(x, w1[:1], b1[:1], w2[:1], b2[:1], w3[:1], b3[:1], y2, rows=4, nmlp=1, gather=gather)
+    ops.mlp3(x, tr(w1[:1]), b1[:1], tr(w2[:1]), b2[:1], tr(w3[:1]), b3[:1], y2, rows=4, nmlp=1, gather=gather)
+    # narrow heads (IoU: 4 outputs, object score: 1): the K range is sliced over the spare threads
+    for dout in (4, 1):
+        w3n, b3n = torch.randn(1, dout, 256, device=DEV) / 16, torch.randn(1, dout, device=DEV) * 0.1
+        y3 = torch.empty(B * n, dout, device=DEV)
+        ops.mlp3(x, tr(w1[:1]), b1[:1], tr(w2[:1]), b2[:1], tr(w3n), b3n, y3, rows=B * n, nmlp=1)
+        hh = torch.relu(torch.relu(x @ w1[0].t() + b1[0]) @ w2[0].t() + b2[0])
+        assert (y3 - (hh @ w3n[0].t() + b3n[0])).abs().max().item() < 1e-4
     xg = x[gather.long()]
     h = torch.relu(xg @ w1[0].t() + b1[0])
     h = torch.relu(h @ w2[0].t() + b2[0])

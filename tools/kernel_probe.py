@@ -87,6 +87,15 @@ def main():
     xo2 = torch.zeros(65536, 256, device=dev, dtype=BF16)
     cases.append(("ln 65536x256", lambda: ops.layernorm(x2, g2, b2, 1e-5, out_bf16=xo2), 0.0, 65536 * 256 * 6))
 
+    xd = torch.randn(16, 64, 64, 256, device=dev)
+    wd, bd = torch.randn(256, 49, device=dev) / 7, torch.randn(256, device=dev)
+    yd = torch.empty_like(xd)
+    cases.append(("dwconv7 16x64x64x256", lambda: ops.dwconv7(xd, wd, bd, yd, 16, 64, 64, 256), 2.0 * 49 * xd.numel(), None))
+    hs = torch.randn(16 * 8, 256, device=dev)
+    mw = [torch.randn(4, 256, 256, device=dev) / 16, torch.randn(4, 256, device=dev), torch.randn(4, 256, 256, device=dev) / 16,
+          torch.randn(4, 256, device=dev), torch.randn(4, 256, 32, device=dev) / 16, torch.randn(4, 32, device=dev)]
+    ym = torch.empty(64, 32, device=dev)
+    cases.append(("mlp3 hyper 64 items", lambda: ops.mlp3(hs, *mw, ym, rows=64, nmlp=4), 2.0 * 64 * (2 * 65536 + 8192), None))
     q = torch.randn(16, 4096, 256, device=dev).to(BF16)
     k = torch.randn(16, 28736, 256, device=dev).to(BF16)
     v = torch.randn(16, 28736, 64, device=dev).to(BF16)
