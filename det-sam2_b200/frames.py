@@ -64,24 +64,70 @@ def load_video_frames(video_path, image_size, offload_video_to_cpu=True, compute
             "unsupported frame source: pass a JPEG folder, a list of image paths, one image path, "
             "an RGB uint8 ndarray or a list of them")
     n = len(arrays) if arrays is not None else len(paths)
-    images = torch.zeros(n, 3, image_size, image_size, dtype=torch.float16)
+    to_device = not offload_video_to_cpu and compute_device is not None
+    pinned = (pin or to_device) and torch.cuda.is_available()
+    images = torch.empty(n, 3, image_size, image_size, dtype=torch.float16, pin_memory=pinned)
+    # Every pixel goes through the same three roundings as in the reference (u8/255 in float64 -> fp16, `-= mean`
+    # and `/= std` each rounded to fp16), but there are only 3 x 256 distinct inputs: the per-channel table is
+    # built ONCE with exactly the reference's tensor operations and the frame is a gather through it — bit-identical
+    # to the arithmetic path (tests/test_frames.py) at ~1/8 of its host time (float64 division and fp16 CPU
+    # arithmetic over 3 M values per frame were a third of the wall time of the streaming driver).
+    lut = _normalize_lut(tuple(img_mean), tuple(img_std))
+    out16 = images.numpy().view(np.uint16)
     if arrays is not None:
         for i, fr in enumerate(arrays):
-            a = _resize_u8(fr, image_size) / 255.0
-            images[i] = torch.from_numpy(a).permute(2, 0, 1)
+            _gather_frame(_resize_u8(fr, image_size), lut, out16[i])
         vh, vw = arrays[0].shape[:2]
     else:
         vh = vw = None
         for i, p in enumerate(paths):
             a, vh, vw = _load_path(p, image_size)
-            images[i] = torch.from_numpy(a / 255.0).permute(2, 0, 1)
-    mean = torch.tensor(img_mean, dtype=torch.float32)[:, None, None]
-    std = torch.tensor(img_std, dtype=torch.float32)[:, None, None]
-    if not offload_video_to_cpu and compute_device is not None:
-        images = images.to(compute_device)
-        mean, std = mean.to(compute_device), std.to(compute_device)
-    images -= mean
-    images /= std
-    if pin and images.device.type == "cpu" and torch.cuda.is_available():
-        images = images.pin_memory()
+            _gather_frame(a, lut, out16[i])
+    if to_device:
+        images = images.to(compute_device, non_blocking=True)
+        torch.cuda.current_stream(compute_device).synchronize()
     return images, vh, vw
+
+
+def normalize_frames_arithmetic(frames_u8, img_mean=IMG_MEAN, img_std=IMG_STD):
+    """The reference's arithmetic (misc.py:336-359) on already-resized uint8 frames [N,S,S,3] -> fp16 [N,3,S,S]:
+    /255 in float64, store to fp16, in-place `-= mean`, `/= std`.  Used to build the gather table and as the
+    ground truth of its test."""
+    frames_u8 = np.asarray(frames_u8)
+    images = torch.zeros(frames_u8.shape[0], 3, frames_u8.shape[1], frames_u8.shape[2], dtype=torch.float16)
+    for i in range(frames_u8.shape[0]):
+        images[i] = torch.from_numpy(frames_u8[i] / 255.0).permute(2, 0, 1)
+    images -= torch.tensor(img_mean, dtype=torch.float32)[:, None, None]
+    images /= torch.tensor(img_std, dtype=torch.float32)[:, None, None]
+    return images
+
+
+_LUTS = {}
+_SCRATCH = {}
+
+
+def _normalize_lut(img_mean, img_std):
+    """uint16 [3, 256]: fp16 bit pattern of the normalised value of byte v in channel c."""
+    key = (img_mean, img_std)
+    if key not in _LUTS:
+        ramp = np.repeat(np.arange(256, dtype=np.uint8).reshape(1, 256, 1, 1), 3, axis=3)   # [1, 256, 1, 3]
+        t = normalize_frames_arithmetic(ramp, img_mean, img_std)                            # [1, 3, 256, 1]
+        _LUTS[key] = np.ascontiguousarray(t.numpy().view(np.uint16).reshape(3, 256))
+    return _LUTS[key]
+
+
+def _gather_frame(frame_u8, lut, out16):
+    """frame_u8 [S,S,3] uint8 -> out16 [3,S,S] (uint16 view of the fp16 destination)."""
+    if frame_u8.dtype != np.uint8 or frame_u8.ndim != 3 or frame_u8.shape[2] != 3:
+        raise RuntimeError(f"expected an RGB uint8 frame [H,W,3], got {frame_u8.dtype} {frame_u8.shape}")
+    import cv2
+    # de-interleave into a re-used scratch (fresh outputs cost 10x more in page faults than the split itself)
+    key = frame_u8.shape[:2]
+    planes = _SCRATCH.get(key)
+    if planes is None:
+        planes = _SCRATCH[key] = [np.empty(key, dtype=np.uint8) for _ in range(3)]
+        if len(_SCRATCH) > 4:
+            _SCRATCH.pop(next(iter(_SCRATCH)))
+    cv2.split(np.ascontiguousarray(frame_u8), planes)
+    for c in range(3):
+        cv2.LUT(planes[c], lut[c], dst=out16[c])   # vectorised byte -> 16-bit table lookup, written in place

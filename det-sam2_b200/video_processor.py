@@ -146,14 +146,36 @@ class VideoProcessor:
                 self.inference_state = self.Detect_2_SAM2_Prompt(detection_results_json)
             else:
                 raise
+        pending = []
         for out_frame_idx, out_obj_ids, out_mask_logits in self.predictor.propagate_in_video(
                 self.inference_state, start_frame_idx=frame_idx,
                 max_frame_num_to_track=self.max_frame_num_to_track, reverse=True):
             if out_frame_idx >= self.pre_frames:
-                self.video_segments[out_frame_idx] = self._masks_to_host(out_obj_ids, out_mask_logits)
+                if out_mask_logits.is_cuda:
+                    # threshold on the device, copy into pinned memory WITHOUT synchronising: a blocking copy
+                    # per frame (det_sam2_RT.py:396-399) idles the GPU while the host prepares the next step
+                    pending.append((out_frame_idx, list(out_obj_ids), self._masks_to_pinned(out_mask_logits, len(pending))))
+                else:
+                    self.video_segments[out_frame_idx] = self._masks_to_host(out_obj_ids, out_mask_logits)
+        if pending:
+            torch.cuda.current_stream().synchronize()
+            for out_frame_idx, ids, host in pending:
+                m = host.numpy().copy()   # the pinned buffers are re-used by the next chunk
+                self.video_segments[out_frame_idx] = {oid: m[i] for i, oid in enumerate(ids)}
         if self.max_inference_state_frames != -1:
             self.predictor.release_old_frames(self.inference_state, frame_idx, self.max_inference_state_frames,
                                               self.pre_frames, release_images=self.vis_frame_stride == -1)
+
+    def _masks_to_pinned(self, mask_logits, slot):
+        """(logits > 0) -> pinned host buffer `slot` of a per-chunk ring, asynchronously on the current stream."""
+        ring = self.__dict__.setdefault("_pinned_ring", [])
+        shape = tuple(mask_logits.shape)
+        while len(ring) <= slot:
+            ring.append(None)
+        if ring[slot] is None or tuple(ring[slot].shape) != shape:
+            ring[slot] = torch.empty(shape, dtype=torch.bool).pin_memory()
+        ring[slot].copy_(mask_logits > 0.0, non_blocking=True)
+        return ring[slot]
 
     @staticmethod
     def _masks_to_host(obj_ids, mask_logits):
