@@ -119,6 +119,7 @@ SYMBOLS = {
     "ds2_fill_holes": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "ds2_resize_bilinear": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "ds2_threshold_pack": (C.c_int, [_P, _P, _L, _P]),
+    "ds2_mask_pack_stats": (C.c_int, [_P, _P, _P, _I, _I, _I, _P]),
 }
 
 

@@ -176,6 +176,55 @@ __global__ void threshold_pack_kernel(const float* __restrict__ x, uint8_t* __re
   bits[byte] = static_cast<uint8_t>(v);
 }
 
+// ---- thresholded masks -> packed bits + per-object area and coordinate sums (integer path) ----------
+// One warp per row chunk of 256 pixels: lane l owns pixels [8l, 8l+8) -> one output byte (bit e = pixel 8l+e, the
+// numpy.packbits(bitorder="little") convention of ds2_threshold_pack); popcounts and the coordinate sums of the
+// set pixels are reduced with shuffles and added to stats[obj] = {area, sum_x, sum_y} with 64-bit integer atomics
+// (exact and order-independent, so the result is bit-reproducible).
+__global__ void __launch_bounds__(256) mask_pack_stats_kernel(const float* __restrict__ x, uint8_t* __restrict__ bits,
+                                                              unsigned long long* __restrict__ stats, int N, int H, int W) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
+  const int chunks = (W + 255) / 256;
+  const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = static_cast<long long>(N) * H * chunks;
+  if (wid >= total) return;
+  const int ch = static_cast<int>(wid % chunks);
+  const int y = static_cast<int>((wid / chunks) % H);
+  const int n = static_cast<int>(wid / (static_cast<long long>(chunks) * H));
+  const int x0 = ch * 256 + lane * 8;
+  const float* row = x + (static_cast<long long>(n) * H + y) * W;
+  unsigned v = 0;
+  if (x0 + 7 < W && ((reinterpret_cast<uintptr_t>(row + x0) & 15) == 0)) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(row + x0));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(row + x0) + 1);
+    v = (a.x > 0.f) | ((a.y > 0.f) << 1) | ((a.z > 0.f) << 2) | ((a.w > 0.f) << 3) | ((b.x > 0.f) << 4) |
+        ((b.y > 0.f) << 5) | ((b.z > 0.f) << 6) | ((b.w > 0.f) << 7);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (x0 + e < W && row[x0 + e] > 0.f) v |= 1u << e;
+  }
+  if (bits && x0 < W) {
+    // rows are packed independently when W is not a multiple of 8 (W/8 rounded up bytes per row)
+    bits[(static_cast<long long>(n) * H + y) * ((W + 7) / 8) + (x0 >> 3)] = static_cast<uint8_t>(v);
+  }
+  unsigned cnt = __popc(v);
+  unsigned sx = 0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sx += ((v >> e) & 1u) * static_cast<unsigned>(x0 + e);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);
+  }
+  if (lane == 0 && cnt && stats) {
+    atomicAdd(stats + 3 * n, static_cast<unsigned long long>(cnt));
+    atomicAdd(stats + 3 * n + 1, static_cast<unsigned long long>(sx));
+    atomicAdd(stats + 3 * n + 2, static_cast<unsigned long long>(cnt) * static_cast<unsigned long long>(y));
+  }
+}
+
 static inline unsigned nblocks(long long n, int bs) { return static_cast<unsigned>((n + bs - 1) / bs); }
 
 }  // namespace ds2
@@ -244,6 +293,20 @@ int ds2_resize_bilinear(const float* x, float* y, int32_t N, int32_t Hi, int32_t
   DS2_LAUNCH((resize_bilinear_kernel), nblocks(total, 256), 256, 0, as_stream(stream), 
       x, y, N, Hi, Wi, Ho, Wo, static_cast<float>(Hi) / Ho, static_cast<float>(Wi) / Wo);
   return post_launch("resize_bilinear_kernel");
+}
+
+int ds2_mask_pack_stats(const float* x, uint8_t* bits, uint64_t* stats, int32_t N, int32_t H, int32_t W, void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(x && (bits || stats) && N > 0 && H > 0 && W > 0, DS2_E_ARG, "ds2_mask_pack_stats: bad args");
+  cudaStream_t st = as_stream(stream);
+  if (stats) {
+    cudaError_t e = cudaMemsetAsync(stats, 0, static_cast<size_t>(N) * 3 * sizeof(uint64_t), st);
+    DS2_REQUIRE(e == cudaSuccess, static_cast<int>(e), "ds2_mask_pack_stats: memset: %s", cudaGetErrorString(e));
+  }
+  const long long warps = static_cast<long long>(N) * H * ((W + 255) / 256);
+  DS2_LAUNCH((mask_pack_stats_kernel), nblocks(warps * 32, 256), 256, 0, st, x, bits,
+             reinterpret_cast<unsigned long long*>(stats), N, H, W);
+  return post_launch("mask_pack_stats_kernel");
 }
 
 int ds2_threshold_pack(const float* x, uint8_t* bits, int64_t n, void* stream) {

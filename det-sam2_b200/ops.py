@@ -269,5 +269,21 @@ def threshold_pack(x, bits):
     _chk(_lib().ds2_threshold_pack(_p(x), _p(bits), x.numel(), _stream()), "ds2_threshold_pack")
 
 
+def mask_pack_stats(masks, bits=None, stats=None):
+    """masks f32 [N, 1, H, W] or [N, H, W] on CUDA -> (bits uint8 [N, H, ceil(W/8)], stats int64 [N, 3] = area, sum_x,
+    sum_y); pass preallocated outputs to avoid allocations on the hot path."""
+    _req(masks, F32, "mask_pack_stats.masks")
+    m = masks.contiguous()
+    N, H, W = m.shape[0], m.shape[-2], m.shape[-1]
+    if bits is False:
+        bits = None   # statistics only
+    elif bits is None:
+        bits = torch.empty((N, H, (W + 7) // 8), dtype=torch.uint8, device=m.device)
+    if stats is None:
+        stats = torch.empty((N, 3), dtype=torch.int64, device=m.device)
+    _chk(_lib().ds2_mask_pack_stats(_p(m), _p(bits), _p(stats), N, H, W, _stream()), "ds2_mask_pack_stats")
+    return bits, stats
+
+
 def launch_count():
     return int(_lib().ds2_launch_count())

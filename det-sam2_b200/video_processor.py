@@ -49,7 +49,7 @@ class VideoProcessor:
                  detect_model_weights=None, detect_confidence=0.85, skip_classes=frozenset({11, 14, 15, 19}),
                  vis_frame_stride=-1, visualize_prompt=False, frame_buffer_size=30, detect_interval=30,
                  max_frame_num_to_track=60, max_inference_state_frames=60, load_inference_state_path=None,
-                 save_inference_state_path=None, *, predictor=None, detector=None, device="cuda"):
+                 save_inference_state_path=None, *, predictor=None, detector=None, device="cuda", object_stats=False):
         if vis_frame_stride != -1 or visualize_prompt:
             raise NotImplementedError("matplotlib rendering is outside the hot path; use vis_frame_stride=-1")
         if save_inference_state_path is not None:
@@ -83,6 +83,11 @@ class VideoProcessor:
             detector = _yolo_detector(detect_model_weights, detect_confidence)
         self.detect_model = detector
         self.video_segments = {}
+        # addition: per frame and object (area, centroid x, centroid y) of the thresholded mask,
+        # computed on the GPU in integer arithmetic (ds2_mask_pack_stats) — what Det-SAM2's post-processor derives
+        # from the boolean masks with cv2.moments (postprocess_det_sam2.py:331-343); None for an empty mask
+        self.object_stats = bool(object_stats)
+        self.video_stats = {}
         self.inference_state = None
         if output_dir:
             os.makedirs(output_dir, exist_ok=True)
@@ -154,14 +159,21 @@ class VideoProcessor:
                 if out_mask_logits.is_cuda:
                     # threshold on the device, copy into pinned memory WITHOUT synchronising: a blocking copy
                     # per frame (det_sam2_RT.py:396-399) idles the GPU while the host prepares the next step
-                    pending.append((out_frame_idx, list(out_obj_ids), self._masks_to_pinned(out_mask_logits, len(pending))))
+                    stats = self._stats_to_pinned(out_mask_logits, len(pending)) if self.object_stats else None
+                    pending.append((out_frame_idx, list(out_obj_ids), self._masks_to_pinned(out_mask_logits, len(pending)),
+                                    stats))
                 else:
                     self.video_segments[out_frame_idx] = self._masks_to_host(out_obj_ids, out_mask_logits)
         if pending:
             torch.cuda.current_stream().synchronize()
-            for out_frame_idx, ids, host in pending:
+            for out_frame_idx, ids, host, stats in pending:
                 m = host.numpy().copy()   # the pinned buffers are re-used by the next chunk
                 self.video_segments[out_frame_idx] = {oid: m[i] for i, oid in enumerate(ids)}
+                if stats is not None:
+                    st_ = stats.numpy()
+                    self.video_stats[out_frame_idx] = {
+                        oid: (None if st_[i, 0] == 0 else (int(st_[i, 0]), st_[i, 1] / st_[i, 0], st_[i, 2] / st_[i, 0]))
+                        for i, oid in enumerate(ids)}
         if self.max_inference_state_frames != -1:
             self.predictor.release_old_frames(self.inference_state, frame_idx, self.max_inference_state_frames,
                                               self.pre_frames, release_images=self.vis_frame_stride == -1)
@@ -176,6 +188,20 @@ class VideoProcessor:
             ring[slot] = torch.empty(shape, dtype=torch.bool).pin_memory()
         ring[slot].copy_(mask_logits > 0.0, non_blocking=True)
         return ring[slot]
+
+    def _stats_to_pinned(self, mask_logits, slot):
+        from . import ops
+        ring = self.__dict__.setdefault("_stats_ring", [])
+        B = mask_logits.shape[0]
+        while len(ring) <= slot:
+            ring.append(None)
+        if ring[slot] is None or ring[slot][0].shape[0] != B:
+            ring[slot] = (torch.empty((B, 3), dtype=torch.int64, device=mask_logits.device),
+                          torch.empty((B, 3), dtype=torch.int64).pin_memory())
+        dev, host = ring[slot]
+        ops.mask_pack_stats(mask_logits, bits=False, stats=dev)
+        host.copy_(dev, non_blocking=True)
+        return host
 
     @staticmethod
     def _masks_to_host(obj_ids, mask_logits):
@@ -198,6 +224,7 @@ class VideoProcessor:
         self.pre_frames = 0
         self.special_classes_detection = []
         self.video_segments = {}
+        self.video_stats = {}
         self.inference_state = None
 
     # ---- preload bank (det_sam2_RT.py:489-503) -----------------------------------------------------
@@ -264,6 +291,7 @@ class VideoProcessor:
         # results are re-based so that they do not count the preload frames (det_sam2_RT.py:612)
         self.video_segments = {idx - self.pre_frames: seg for idx, seg in self.video_segments.items()
                                if idx >= self.pre_frames}
+        self.video_stats = {idx - self.pre_frames: v for idx, v in self.video_stats.items() if idx >= self.pre_frames}
         if output_video_segments_pkl_path:
             with open(output_video_segments_pkl_path, "wb") as f:
                 pickle.dump(self.video_segments, f)

@@ -252,6 +252,13 @@ int ds2_resize_bilinear(const float* x, float* y, int32_t N, int32_t Hi, int32_t
                         int32_t Wo, void* stream);
 /* (x > 0) bit-packed, 8 pixels per byte, little-endian bit order (det_sam2_RT.py:396-399) */
 int ds2_threshold_pack(const float* x, uint8_t* bits, int64_t n, void* stream);
+/* The result hand-off one step further: thresholds N masks [N, H, W] f32 at > 0 and emits
+ * (a) bits: [N, H, ceil(W/8)] bytes, bit e of byte j of a row = pixel 8j+e (numpy.packbits bitorder "little"), and/or
+ * (b) stats: uint64 [N][3] = {area, sum of x, sum of y} over the set pixels, i.e. the raw moments m00, m10, m01 that
+ * Det-SAM2's post-processor obtains with cv2.moments on the host (postprocess_det_sam2.py:331-343); the centroid is
+ * (sum_x / area, sum_y / area).  Integer arithmetic, bit-reproducible.  Either output may be NULL.             */
+int ds2_mask_pack_stats(const float* x, uint8_t* bits, uint64_t* stats, int32_t N, int32_t H, int32_t W,
+                        void* stream);
 
 #ifdef __cplusplus
 }

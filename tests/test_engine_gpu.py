@@ -128,6 +128,35 @@ def test_cuda_video_processor_matches_reference_golden():
     assert float(np.mean(ious)) >= calib["iou_mean"] - 5e-3, (float(np.mean(ious)), calib["iou_mean"])
 
 
+def test_video_processor_object_stats_match_masks():
+    """(area, centroid) per object from the GPU integer kernel == the raw moments of the
+    boolean masks the driver hands out (what postprocess_det_sam2.py computes with cv2.moments)."""
+    from detsam2_b200.engine import CudaEngine
+    from detsam2_b200.predictor import SAM2VideoPredictor
+    from detsam2_b200.synthetic import BilliardVideo, GroundTruthDetector
+    from detsam2_b200.video_processor import VideoProcessor
+    from detsam2_b200.weights import synthetic_state_dict
+    cfg = scenarios.scenario_config("video_processor")
+    eng = CudaEngine(cfg, synthetic_state_dict(cfg, 0), device="cuda:0")
+    vid = BilliardVideo(num_objects=3, height=160, width=224, num_frames=9, seed=5)
+    vp = VideoProcessor(predictor=SAM2VideoPredictor(eng, fill_hole_area=8), detector=GroundTruthDetector(vid, detect_interval=4),
+                        frame_buffer_size=4, detect_interval=4, max_frame_num_to_track=6, max_inference_state_frames=6,
+                        skip_classes=set(), object_stats=True)
+    with torch.inference_mode():
+        segs = vp.run(frames=(vid.frame(t) for t in range(9)))
+    assert sorted(vp.video_stats) == sorted(segs) == list(range(9))
+    ys, xs = np.mgrid[0:160, 0:224]
+    for t, per_obj in segs.items():
+        for oid, m in per_obj.items():
+            got = vp.video_stats[t][oid]
+            area = int(m.sum())
+            if area == 0:
+                assert got is None
+            else:
+                assert got[0] == area
+                assert got[1] == (m[0] * xs).sum() / area and got[2] == (m[0] * ys).sum() / area
+
+
 def test_graph_replay_is_bit_identical_to_eager_launches():
     """The captured-graph path launches exactly the kernels of the eager path: same bits out.  A reduced
     pointer window makes the memory-bank signature reach steady state after 6 frames so that all four

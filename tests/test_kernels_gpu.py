@@ -3,6 +3,7 @@ restatement of the same op on the same seeded inputs (floating point -> toleranc
 integer work -> bit exact)."""
 import math
 
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -516,6 +517,26 @@ def test_threshold_pack(ops):
     import numpy as np
     exp = np.packbits((x > 0).cpu().numpy(), bitorder="little")
     assert (bits.cpu().numpy() == exp).all()
+
+
+@pytest.mark.parametrize("N,H,W", [(3, 64, 256), (2, 37, 100), (16, 256, 1024)])
+def test_mask_pack_stats_exact(ops, N, H, W):
+    """Integer path: packed bits == numpy.packbits(little) per row, stats == exact raw moments (cv2.moments m00/m10/m01)."""
+    torch.manual_seed(21)
+    x = torch.randn(N, 1, H, W, device=DEV)
+    x[0, 0, : H // 2] = -1.0           # empty region
+    if N > 1:
+        x[1] = -1.0                    # an object with an empty mask: area 0, sums 0
+    bits, stats = ops.mask_pack_stats(x)
+    m = (x[:, 0] > 0).cpu().numpy()
+    ref_bits = np.packbits(m, axis=-1, bitorder="little")
+    assert np.array_equal(bits.cpu().numpy(), ref_bits)
+    ys, xs = np.mgrid[0:H, 0:W]
+    ref = np.stack([m.sum((1, 2)), (m * xs).sum((1, 2)), (m * ys).sum((1, 2))], 1).astype(np.int64)
+    assert np.array_equal(stats.cpu().numpy(), ref)
+    # run twice: atomics on integers are order-independent
+    bits2, stats2 = ops.mask_pack_stats(x)
+    assert torch.equal(bits, bits2) and torch.equal(stats, stats2)
 
 
 def test_connected_components_and_fill_holes(ops):
