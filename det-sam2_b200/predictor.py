@@ -270,6 +270,59 @@ class SAM2VideoPredictor:
         return self.add_new_points_or_box(*args, **kwargs)
 
     @torch.inference_mode()
+    def add_new_boxes(self, inference_state, frame_idx, boxes, normalize_coords=True):
+        """Addition: box prompts for several objects of ONE frame in one B-wide decoder
+        call.  Equivalent to calling ``add_new_points_or_box(frame_idx, obj_id, box=...)`` for the items of
+        ``boxes`` ({obj_id: xyxy}) in order — the reference's driver does exactly that, one B = 1 decode and one
+        consolidation per detection (det_sam2_RT.py:285-316, svp:485-498) — and returns what the last of those
+        calls would return.  The batched path applies when the frame has not been tracked yet and no object has an
+        earlier prompt result on it (the detector case); otherwise it falls back to the sequential calls."""
+        st = inference_state
+        items = list(boxes.items())
+        if not items:
+            raise ValueError("boxes must hold at least one {obj_id: box} item")
+        obj_idxs = [self._obj_id_to_idx(st, oid) for oid, _ in items]   # same registration order / side effects
+        batched = frame_idx not in st["frames_already_tracked"] and len(set(obj_idxs)) == len(obj_idxs) and len(items) > 1
+        if batched:
+            for oi in obj_idxs:
+                for d in (st["temp_output_dict_per_obj"][oi], st["output_dict_per_obj"][oi]):
+                    if frame_idx in d["cond_frame_outputs"] or frame_idx in d["non_cond_frame_outputs"]:
+                        batched = False
+        if not batched:
+            out = None
+            for oid, box in items:
+                out = self.add_new_points_or_box(st, frame_idx, oid, box=box, normalize_coords=normalize_coords)
+            return out
+        scale = torch.tensor([st["video_width"], st["video_height"]], dtype=torch.float32)
+        pts, lbs = [], []
+        for (oid, box), oi in zip(items, obj_idxs):
+            b = box if isinstance(box, torch.Tensor) else torch.tensor(box, dtype=torch.float32)
+            p = b.to(torch.float32).reshape(1, 2, 2)
+            if normalize_coords:
+                p = p / scale
+            p = (p * self.image_size).to(st["device"])
+            l = torch.tensor([2, 3], dtype=torch.int32).reshape(1, 2).to(st["device"])
+            st["point_inputs_per_obj"][oi][frame_idx] = {"point_coords": p, "point_labels": l}
+            st["mask_inputs_per_obj"][oi].pop(frame_idx, None)
+            pts.append(p)
+            lbs.append(l)
+        point_inputs = {"point_coords": torch.cat(pts, 0), "point_labels": torch.cat(lbs, 0)}
+        # an un-tracked frame is an initial conditioning frame: no memory is read, so the per-object output dict that
+        # _run_single_frame_inference would consult for memory is irrelevant and one batched call is exact
+        current_out, _ = self._run_single_frame_inference(
+            st, st["output_dict_per_obj"][obj_idxs[0]], frame_idx, batch_size=len(items), is_init_cond_frame=True,
+            point_inputs=point_inputs, mask_inputs=None, reverse=False, run_mem_encoder=False, prev_sam_mask_logits=None)
+        for i, oi in enumerate(obj_idxs):
+            sl = slice(i, i + 1)
+            st["temp_output_dict_per_obj"][oi]["cond_frame_outputs"][frame_idx] = {
+                "maskmem_features": None, "maskmem_pos_enc": None, "pred_masks": current_out["pred_masks"][sl],
+                "obj_ptr": current_out["obj_ptr"][sl], "object_score_logits": current_out["object_score_logits"][sl]}
+        consolidated = self._consolidate_temp_output_across_obj(st, frame_idx, is_cond=True, run_mem_encoder=False,
+                                                                consolidate_at_video_res=True)
+        _, video_res_masks = self._get_orig_video_res_output(st, consolidated["pred_masks_video_res"])
+        return frame_idx, st["obj_ids"], video_res_masks
+
+    @torch.inference_mode()
     def add_new_mask(self, inference_state, frame_idx, obj_id, mask):
         """svp:527-600."""
         st = inference_state

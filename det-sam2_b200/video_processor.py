@@ -125,13 +125,23 @@ class VideoProcessor:
             return self.inference_state
         for key, detections in detection_results_json.items():
             ann_frame_idx = int(key.replace("frame_", ""))
+            boxes = {}
             for det in detections:
                 obj_class = int(np.asarray(det["class"]).reshape(-1)[0])
                 if obj_class in self.skip_classes:
                     continue
-                self.predictor.add_new_points_or_box(
-                    inference_state=self.inference_state, frame_idx=ann_frame_idx, obj_id=obj_class,
-                    box=np.array(det["coordinates"], dtype=np.float32))
+                # a later detection of the same class replaces the earlier one, as the reference's sequential
+                # add_new_points_or_box(..., clear_old_points=True) calls do; first occurrence fixes the id order
+                boxes[obj_class] = np.array(det["coordinates"], dtype=np.float32)
+            if not boxes:
+                continue
+            if hasattr(self.predictor, "add_new_boxes"):
+                # all boxes of the frame in one B-wide decoder call
+                self.predictor.add_new_boxes(self.inference_state, ann_frame_idx, boxes)
+            else:
+                for obj_class, box in boxes.items():
+                    self.predictor.add_new_points_or_box(inference_state=self.inference_state, frame_idx=ann_frame_idx,
+                                                         obj_id=obj_class, box=box)
         return self.inference_state
 
     # ---- one chunk (det_sam2_RT.py:342-411) --------------------------------------------------------
