@@ -120,6 +120,8 @@ SYMBOLS = {
     "ds2_resize_bilinear": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "ds2_threshold_pack": (C.c_int, [_P, _P, _L, _P]),
     "ds2_mask_pack_stats": (C.c_int, [_P, _P, _P, _I, _I, _I, _P]),
+    "ds2_downsample4_aa": (C.c_int, [_P, _P, _I, _I, _F, _F, _P]),
+    "ds2_mask_prompt_embed": (C.c_int, [_P, _I, _I] + [_P] * 10 + [_P, _P]),
 }
 
 

@@ -110,6 +110,111 @@ __global__ void memenc_finish_kernel(const float* __restrict__ x, const float* _
   out[i] = __float2bfloat16(x[i] + add);
 }
 
+// ---- dense mask prompt (sam2_base.py:399-448, prompt_encoder.py:97-100) -------------------------------
+// (1) low = antialiased bilinear x1/4 of (mask * scale + bias)  — F.interpolate(..., antialias=True):
+//     triangle filter of support 4 input pixels around centre 4(i + 0.5), taps clipped at the border and
+//     renormalised (ATen UpSampleKernel _compute_indices_weights_aa), separable.
+__global__ void __launch_bounds__(256) downsample4_aa_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int S,
+                                                             float scale, float bias) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
+  const int So = S / 4;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(B) * So * So) return;
+  const int ox = static_cast<int>(i % So), oy = static_cast<int>((i / So) % So), b = static_cast<int>(i / (static_cast<long long>(So) * So));
+  float wx[8], wy[8];
+  int x0, y0, nx, ny;
+  auto taps = [&](int o, float(&w)[8], int& lo, int& n) {
+    const float c = 4.0f * (o + 0.5f);
+    lo = max(static_cast<int>(c - 4.0f + 0.5f), 0);
+    const int hi = min(static_cast<int>(c + 4.0f + 0.5f), S);
+    n = hi - lo;
+    float tot = 0.f;
+    for (int j = 0; j < 8; ++j) {
+      float v = 0.f;
+      if (j < n) v = fmaxf(1.0f - fabsf((j + lo - c + 0.5f) * 0.25f), 0.f);
+      w[j] = v;
+      tot += v;
+    }
+    for (int j = 0; j < 8; ++j) w[j] /= tot;
+  };
+  taps(ox, wx, x0, nx);
+  taps(oy, wy, y0, ny);
+  const float* src = x + static_cast<long long>(b) * S * S;
+  float acc = 0.f;
+  for (int r = 0; r < ny; ++r) {
+    float h = 0.f;
+    for (int c = 0; c < nx; ++c) h = fmaf(wx[c], fmaf(src[static_cast<long long>(y0 + r) * S + x0 + c], scale, bias), h);
+    acc = fmaf(wy[r], h, acc);
+  }
+  y[i] = acc;
+}
+
+// (2) mask_downsample (Conv2d 1->1, k4 s4) followed by the prompt encoder's mask_downscaling up to its last
+//     1x1 conv: Conv2d(1->4, k2 s2) LN2d GELU Conv2d(4->16, k2 s2) LN2d GELU.  All strides equal the kernel sizes,
+//     so one output token depends on one 16x16 patch of the mask: one thread per token, 16 bf16 features out
+//     (the 16->256 1x1 conv is a ds2_gemm).
+struct MaskEmbedParams {
+  const float* mask;  // [B, S, S]
+  int B, S;
+  const float *wds, *bds;             // [16], [1]
+  const float *w0, *b0, *g0, *be0;    // [4][4], [4], LN [4]
+  const float *w3, *b3, *g3, *be3;    // [16][16] ((cin, ky, kx) per output), [16], LN [16]
+  __nv_bfloat16* out;                 // [B * (S/16)^2, 16]
+};
+__device__ __forceinline__ float gelu_erf_p(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__global__ void __launch_bounds__(128) mask_prompt_embed_kernel(const MaskEmbedParams p) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
+  const int So = p.S / 16;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(p.B) * So * So) return;
+  const int ox = static_cast<int>(i % So), oy = static_cast<int>((i / So) % So), b = static_cast<int>(i / (static_cast<long long>(So) * So));
+  const float* src = p.mask + (static_cast<long long>(b) * p.S + oy * 16) * p.S + ox * 16;
+  // k4 s4: 4 x 4 values of the 1/4-resolution mask
+  float ds[4][4];
+  for (int qy = 0; qy < 4; ++qy)
+    for (int qx = 0; qx < 4; ++qx) {
+      float a = p.bds[0];
+      for (int ky = 0; ky < 4; ++ky)
+        for (int kx = 0; kx < 4; ++kx) a = fmaf(src[static_cast<long long>(qy * 4 + ky) * p.S + qx * 4 + kx], p.wds[ky * 4 + kx], a);
+      ds[qy][qx] = a;
+    }
+  // k2 s2 1 -> 4, LN over the 4 channels, GELU: 2 x 2 positions
+  float h0[2][2][4];
+  for (int ry = 0; ry < 2; ++ry)
+    for (int rx = 0; rx < 2; ++rx) {
+      float v[4], u = 0.f;
+      for (int c = 0; c < 4; ++c) {
+        float a = p.b0[c];
+        for (int ky = 0; ky < 2; ++ky)
+          for (int kx = 0; kx < 2; ++kx) a = fmaf(ds[ry * 2 + ky][rx * 2 + kx], p.w0[c * 4 + ky * 2 + kx], a);
+        v[c] = a;
+        u += a;
+      }
+      u *= 0.25f;
+      float s2 = 0.f;
+      for (int c = 0; c < 4; ++c) s2 += (v[c] - u) * (v[c] - u);
+      const float rstd = 1.0f / sqrtf(s2 * 0.25f + 1e-6f);
+      for (int c = 0; c < 4; ++c) h0[ry][rx][c] = gelu_erf_p((v[c] - u) * rstd * p.g0[c] + p.be0[c]);
+    }
+  // k2 s2 4 -> 16, LN over the 16 channels, GELU
+  float v[16], u = 0.f;
+  for (int o = 0; o < 16; ++o) {
+    float a = p.b3[o];
+    for (int c = 0; c < 4; ++c)
+      for (int ky = 0; ky < 2; ++ky)
+        for (int kx = 0; kx < 2; ++kx) a = fmaf(h0[ky][kx][c], p.w3[o * 16 + c * 4 + ky * 2 + kx], a);
+    v[o] = a;
+    u += a;
+  }
+  u *= (1.0f / 16.0f);
+  float s2 = 0.f;
+  for (int o = 0; o < 16; ++o) s2 += (v[o] - u) * (v[o] - u);
+  const float rstd = 1.0f / sqrtf(s2 * (1.0f / 16.0f) + 1e-6f);
+  __nv_bfloat16* po = p.out + i * 16;
+  for (int o = 0; o < 16; ++o) po[o] = __float2bfloat16(gelu_erf_p((v[o] - u) * rstd * p.g3[o] + p.be3[o]));
+}
+
 }  // namespace ds2
 
 extern "C" {
@@ -149,3 +254,39 @@ int ds2_memenc_finish(const float* x, const float* score, const float* no_obj_em
 }
 
 }  // extern "C"
+
+extern "C" int ds2_downsample4_aa(const float* x, float* y, int32_t B, int32_t S, float scale, float bias, void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(x && y && B > 0 && S >= 4 && (S % 4) == 0, DS2_E_ARG, "ds2_downsample4_aa: bad args");
+  const long long n = static_cast<long long>(B) * (S / 4) * (S / 4);
+  DS2_LAUNCH((downsample4_aa_kernel), static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream), x, y, B, S, scale, bias);
+  return post_launch("downsample4_aa_kernel");
+}
+
+extern "C" int ds2_mask_prompt_embed(const float* mask, int32_t B, int32_t S, const float* wds, const float* bds,
+                                     const float* w0, const float* b0, const float* ln0_w, const float* ln0_b,
+                                     const float* w3, const float* b3, const float* ln3_w, const float* ln3_b,
+                                     void* out_bf16, void* stream) {
+  using namespace ds2;
+  DS2_REQUIRE(mask && wds && bds && w0 && b0 && ln0_w && ln0_b && w3 && b3 && ln3_w && ln3_b && out_bf16 && B > 0 &&
+                  S >= 16 && (S % 16) == 0,
+              DS2_E_ARG, "ds2_mask_prompt_embed: bad args");
+  MaskEmbedParams p;
+  p.mask = mask;
+  p.B = B;
+  p.S = S;
+  p.wds = wds;
+  p.bds = bds;
+  p.w0 = w0;
+  p.b0 = b0;
+  p.g0 = ln0_w;
+  p.be0 = ln0_b;
+  p.w3 = w3;
+  p.b3 = b3;
+  p.g3 = ln3_w;
+  p.be3 = ln3_b;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  const long long n = static_cast<long long>(B) * (S / 16) * (S / 16);
+  DS2_LAUNCH((mask_prompt_embed_kernel), static_cast<unsigned>((n + 127) / 128), 128, 0, as_stream(stream), p);
+  return post_launch("mask_prompt_embed_kernel");
+}

@@ -310,6 +310,18 @@ class CudaEngine:
         f32("point_emb", torch.cat([sd[pe_ + f"point_embeddings.{i}.weight"] for i in range(4)]))
         f32("not_a_point", sd[pe_ + "not_a_point_embed.weight"].reshape(-1))
         f32("no_mask_embed", sd[pe_ + "no_mask_embed.weight"].reshape(1, -1))
+        # dense mask prompts (add_new_mask): mask_downsample (k4 s4) + PromptEncoder.mask_downscaling
+        md = pe_ + "mask_downscaling."
+        f32("mp.wds", sd["mask_downsample.weight"].reshape(-1))
+        f32("mp.bds", sd["mask_downsample.bias"].reshape(-1))
+        f32("mp.w0", sd[md + "0.weight"].reshape(4, 4))
+        f32("mp.b0", sd[md + "0.bias"])
+        ln("mp.ln0", md + "1")
+        f32("mp.w3", sd[md + "3.weight"].reshape(16, 16))
+        f32("mp.b3", sd[md + "3.bias"])
+        ln("mp.ln3", md + "4")
+        w16("mp.w6", sd[md + "6.weight"].reshape(sd[md + "6.weight"].shape[0], -1))
+        f32("mp.b6", sd[md + "6.bias"])
         dpe = _dense_pe(gauss, fs)
         f32("dense_pe", dpe)
         # ---- mask decoder ----
@@ -683,7 +695,7 @@ class CudaEngine:
             self._ws[key] = v
         return v
 
-    def _sam_heads_body(self, inp, pix, B, P, multimask_output):
+    def _sam_heads_body(self, inp, pix, B, P, multimask_output, dense=None):
         cfg, p = self.cfg, self.p
         T = cfg.feat_size * cfg.feat_size
         D = cfg.hidden_dim
@@ -698,7 +710,10 @@ class CudaEngine:
                           cfg.image_size, qpe)
         keys = self._buf("dec_keys", (B * T, D), F32)
         keys16 = self._buf("dec_keys16", (B * T, D), BF16)
-        ops.axpby(pix, p["no_mask_embed"], 1.0, 1.0, b_row_mod=1, out_f32=keys, out_bf16=keys16)
+        if dense is None:
+            ops.axpby(pix, p["no_mask_embed"], 1.0, 1.0, b_row_mod=1, out_f32=keys, out_bf16=keys16)
+        else:  # dense mask-prompt embedding [B*T, D] instead of the broadcast no_mask_embed (prompt_encoder.py:163-170)
+            ops.axpby(pix, dense, 1.0, 1.0, out_f32=keys, out_bf16=keys16)
         qf = self._buf("dec_q", (R, D), F32)       # queries (f32 residual stream)
         q16 = self._buf("dec_q16", (R, D), BF16)   # bf16(queries)
         qp16 = self._buf("dec_qp16", (R, D), BF16)  # bf16(queries + query_pe)
@@ -794,19 +809,46 @@ class CudaEngine:
         return low, iou_out, obj_ptr, score
 
     def mask_as_output(self, feats, mask_inputs):
-        """sam2_base.py:399-448.  Only the all-zero mask is needed on the Det-SAM2 path
-        (_get_empty_mask_ptr, svp:769-804, for objects missing from a prompted frame): with
-        fixed_no_obj_ptr the pointer of an empty mask is exactly no_obj_ptr, whatever SAM computes."""
-        if bool((mask_inputs != 0).any()):
-            raise NotImplementedError("mask prompts (add_new_mask) are not implemented by the CUDA engine yet")
+        """sam2_base.py:399-448 (_use_mask_as_output): the prompt mask itself becomes the output (logits +-10,
+        antialiased x1/4 for the low-resolution copy), and the object pointer comes from a SAM decode that takes
+        the mask as a DENSE prompt.  mask_inputs: [B, 1, S, S] 0/1 floats at the model resolution."""
+        cfg, p = self.cfg, self.p
         B = mask_inputs.shape[0]
-        S4 = 4 * self.cfg.feat_size
-        return {
-            "pred_masks": torch.full((B, 1, S4, S4), -10.0, dtype=F32, device=self.device),
-            "ious": torch.ones((B, 1), dtype=F32, device=self.device),
-            "obj_ptr": self.p["no_obj_ptr"].reshape(1, -1).expand(B, -1).contiguous(),
-            "object_score_logits": torch.full((B, 1), -10.0, dtype=F32, device=self.device),
-        }
+        S = cfg.image_size
+        S4 = 4 * cfg.feat_size
+        T = cfg.feat_size * cfg.feat_size
+        D = cfg.hidden_dim
+        if tuple(mask_inputs.shape) != (B, 1, S, S):
+            raise Ds2Error(f"mask prompt must be [B,1,{S},{S}], got {tuple(mask_inputs.shape)}")
+        m = mask_inputs.to(device=self.device, dtype=F32).contiguous().view(B, S, S)
+        _, stats = ops.mask_pack_stats(m, bits=False)
+        if not bool((stats[:, 0] > 0).any()):
+            # all-empty prompt (_get_empty_mask_ptr, svp:769-804, for objects missing from a prompted frame): with
+            # fixed_no_obj_ptr the pointer of an empty mask is exactly no_obj_ptr, whatever SAM computes
+            return {
+                "pred_masks": torch.full((B, 1, S4, S4), -10.0, dtype=F32, device=self.device),
+                "ious": torch.ones((B, 1), dtype=F32, device=self.device),
+                "obj_ptr": p["no_obj_ptr"].reshape(1, -1).expand(B, -1).contiguous(),
+                "object_score_logits": torch.full((B, 1), -10.0, dtype=F32, device=self.device),
+            }
+        low = torch.empty((B, 1, S4, S4), dtype=F32, device=self.device)
+        ops.downsample4_aa(m, low.view(B, S4, S4), 20.0, -10.0)
+        f16 = self._buf("mp_f16", (B * T, 16), BF16)
+        ops.mask_prompt_embed(m, p["mp.wds"], p["mp.bds"], p["mp.w0"], p["mp.b0"], p["mp.ln0.w"], p["mp.ln0.b"],
+                              p["mp.w3"], p["mp.b3"], p["mp.ln3.w"], p["mp.ln3.b"], f16)
+        dense = self._buf("mp_dense", (B * T, D), F32)
+        ops.gemm(f16, p["mp.w6"], bias=p["mp.b6"], out_f32=dense)
+        # SAM decode without point prompts (one padding point), single-mask output, raw backbone features
+        pix = feats.vis_f32.reshape(1, T, D).expand(B, T, D).contiguous().view(B * T, D)
+        coords, labels = self._noprompt(B)
+        _, _, obj_ptr, _ = self._sam_heads_body({"coords": coords, "labels": labels, "s0": feats.feat_s0, "s1": feats.feat_s1},
+                                                pix, B, 1, False, dense=dense)
+        # lambda = mask non-empty (sam2_base.py:433-447): score = +-10, pointer mixed once more with no_obj_ptr
+        score = ((stats[:, 0:1] > 0).to(F32) * 20.0 - 10.0).contiguous()
+        obj_ptr = obj_ptr.clone()
+        ops.objptr_mix(obj_ptr, score, p["no_obj_ptr"], B, D)
+        return {"pred_masks": low, "ious": torch.ones((B, 1), dtype=F32, device=self.device), "obj_ptr": obj_ptr,
+                "object_score_logits": score}
 
     # ---------------------------------------------------------------------------------------------
     # seam 4: memory encoder

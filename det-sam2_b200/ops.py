@@ -269,6 +269,20 @@ def threshold_pack(x, bits):
     _chk(_lib().ds2_threshold_pack(_p(x), _p(bits), x.numel(), _stream()), "ds2_threshold_pack")
 
 
+def downsample4_aa(x, y, scale, bias):
+    """x f32 [B, S, S] -> y f32 [B, S/4, S/4]: antialiased bilinear of x * scale + bias."""
+    _req(x, F32, "downsample4_aa.x"); _req(y, F32, "downsample4_aa.y")
+    _chk(_lib().ds2_downsample4_aa(_p(x), _p(y), x.shape[0], x.shape[-1], float(scale), float(bias), _stream()),
+         "ds2_downsample4_aa")
+
+
+def mask_prompt_embed(mask, wds, bds, w0, b0, ln0_w, ln0_b, w3, b3, ln3_w, ln3_b, out_bf16):
+    _req(mask, F32, "mask_prompt_embed.mask"); _req(out_bf16, BF16, "mask_prompt_embed.out")
+    _chk(_lib().ds2_mask_prompt_embed(_p(mask), mask.shape[0], mask.shape[-1], _p(wds), _p(bds), _p(w0), _p(b0), _p(ln0_w),
+                                      _p(ln0_b), _p(w3), _p(b3), _p(ln3_w), _p(ln3_b), _p(out_bf16), _stream()),
+         "ds2_mask_prompt_embed")
+
+
 def mask_pack_stats(masks, bits=None, stats=None):
     """masks f32 [N, 1, H, W] or [N, H, W] on CUDA -> (bits uint8 [N, H, ceil(W/8)], stats int64 [N, 3] = area, sum_x,
     sum_y); pass preallocated outputs to avoid allocations on the hot path."""

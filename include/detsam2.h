@@ -257,6 +257,19 @@ int ds2_threshold_pack(const float* x, uint8_t* bits, int64_t n, void* stream);
  * (b) stats: uint64 [N][3] = {area, sum of x, sum of y} over the set pixels, i.e. the raw moments m00, m10, m01 that
  * Det-SAM2's post-processor obtains with cv2.moments on the host (postprocess_det_sam2.py:331-343); the centroid is
  * (sum_x / area, sum_y / area).  Integer arithmetic, bit-reproducible.  Either output may be NULL.             */
+/* ---- dense mask prompts (add_new_mask, svp:527-600 -> SAM2Base._use_mask_as_output sam2_base.py:399-448) ------ */
+/* y[B, S/4, S/4] = F.interpolate(x * scale + bias, scale 1/4, mode="bilinear", antialias=True, align_corners=False)
+ * for x [B, S, S] f32 (the low-resolution logits that stand in for SAM's output, sam2_base.py:407-413)           */
+int ds2_downsample4_aa(const float* x, float* y, int32_t B, int32_t S, float scale, float bias, void* stream);
+/* mask_downsample (Conv2d 1->1 k4 s4, sam2_base.py:185-187,419) + PromptEncoder.mask_downscaling without its final
+ * 1x1 conv (prompt_encoder.py:52-60: Conv 1->4 k2 s2, LayerNorm2d, GELU, Conv 4->16 k2 s2, LayerNorm2d, GELU):
+ * mask [B, S, S] f32 -> bf16 [B * (S/16)^2, 16] token-major features; the 16 -> 256 conv is a ds2_gemm.
+ * w0 [4][1][2][2], w3 [16][4][2][2] in Conv2d layout.                                                           */
+int ds2_mask_prompt_embed(const float* mask, int32_t B, int32_t S, const float* wds, const float* bds,
+                          const float* w0, const float* b0, const float* ln0_w, const float* ln0_b,
+                          const float* w3, const float* b3, const float* ln3_w, const float* ln3_b,
+                          void* out_bf16, void* stream);
+
 int ds2_mask_pack_stats(const float* x, uint8_t* bits, uint64_t* stats, int32_t N, int32_t H, int32_t W,
                         void* stream);
 

@@ -49,7 +49,7 @@ def deviations(got, ref):
 def main():
     torch.set_num_threads(os.cpu_count() or 1)
     res = {}
-    for name in ("stream", "preload", "offline"):
+    for name in ("stream", "preload", "offline", "mask_prompt"):
         cfg = scenarios.scenario_config(name)
         sd = synthetic_state_dict(cfg, 0)
         ref = ref_shim.build_reference_predictor(cfg, sd, device="cpu")

@@ -13,6 +13,7 @@ Scenarios
             init_state(chunk) / update_state(chunk), box prompts on the last frame of each chunk,
             reverse propagate with max_frame_num_to_track, an online NEW object id while tracking
             (svp:250-327), release_old_frames with release_images (svp:1215-1277).
+  mask_prompt  add_new_mask with a disc, a box on the same frame and an empty mask, then tracking (svp:527-600).
   preload   preload memory bank (det_sam2_RT.py:489-503, svp:123-156): every frame of a short clip is
             a conditioning frame, state is pickled, re-loaded, init_preloading_state, new frames
             appended with update_state and tracked against the bank.
@@ -134,6 +135,31 @@ def run_preload(predictor, pre=3, extra=3, height=192, width=256, seed=7):
     return rec
 
 
+def run_mask_prompt(predictor, num_frames=3, height=192, width=256, seed=9):
+    """Dense mask prompt (svp:527-600 add_new_mask -> sam2_base.py:399-448 _use_mask_as_output): object 0 is
+    prompted with its ground-truth disc as a boolean video-resolution mask (antialiased resize to the model
+    resolution + 0.5 threshold inside the predictor), object 1 with a box on the same frame, object 2 with an
+    EMPTY mask (never appears: pointer = no_obj_ptr, score -10); then forward tracking."""
+    vid = BilliardVideo(num_objects=2, height=height, width=width, num_frames=num_frames, seed=seed)
+    rec = {}
+    with torch.inference_mode():
+        st = predictor.init_state([vid.frame(t) for t in range(num_frames)])
+        x0, y0, x1, y1 = [float(v) for v in vid.boxes(0)[0]]
+        yy, xx = np.mgrid[0:height, 0:width]
+        cx, cy, r = (x0 + x1) / 2, (y0 + y1) / 2, (x1 - x0) / 2 - 2
+        disc = ((xx - cx) ** 2 + (yy - cy) ** 2) <= r * r
+        f, ids, m = predictor.add_new_mask(st, 0, 0, disc)
+        rec["prompt.mask.video_res_masks"] = _np(m)
+        f, ids, m = predictor.add_new_points_or_box(st, 0, 1, box=np.asarray(vid.boxes(0)[1], dtype=np.float32))
+        rec["prompt.box.video_res_masks"] = _np(m)
+        f, ids, m = predictor.add_new_mask(st, 0, 2, np.zeros((height, width), dtype=bool))
+        rec["prompt.empty.video_res_masks"] = _np(m)
+        for f, ids, m in predictor.propagate_in_video(st):
+            _record_frame(rec, "track", st, f, m)
+        rec["obj_ids"] = np.asarray(list(st["obj_ids"]), dtype=np.int64)
+    return rec
+
+
 def run_video_processor(make_vp, num_frames=11, height=160, width=224, seed=11):
     """Det-SAM2's own driver (det_sam2_RT.py VideoProcessor.run) over a frame folder: K = 4 frames per
     chunk, detection every 4 frames, reverse window M = 6, state window S = 6 with image release, a
@@ -189,7 +215,7 @@ def load_golden(name):
     return d, d.pop("__weights_fingerprint")
 
 
-SCENARIOS = {"offline": run_offline, "stream": run_stream, "preload": run_preload}
+SCENARIOS = {"offline": run_offline, "stream": run_stream, "preload": run_preload, "mask_prompt": run_mask_prompt}
 
 
 def compare(got, ref, rtol_rms, iou_min=None, int_exact=True):

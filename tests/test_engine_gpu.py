@@ -60,7 +60,7 @@ def _kind_errors(got, gold):
     return per_kind
 
 
-@pytest.mark.parametrize("name", ["stream", "preload", "offline"])
+@pytest.mark.parametrize("name", ["stream", "preload", "offline", "mask_prompt"])
 def test_cuda_engine_matches_reference_golden(name):
     gold, _ = scenarios.load_golden(name)
     calib = _calib()[name]

@@ -519,6 +519,42 @@ def test_threshold_pack(ops):
     assert (bits.cpu().numpy() == exp).all()
 
 
+def test_downsample4_aa_matches_torch_antialias(ops):
+    """F.interpolate(x*20-10, 1/4, bilinear, antialias=True) (sam2_base.py:407-413), borders included."""
+    torch.manual_seed(22)
+    x = (torch.rand(3, 64, 64, device=DEV) > 0.6).float()
+    y = torch.empty(3, 16, 16, device=DEV)
+    ops.downsample4_aa(x, y, 20.0, -10.0)
+    ref = F.interpolate((x * 20.0 - 10.0)[:, None], size=(16, 16), mode="bilinear", align_corners=False, antialias=True)[:, 0]
+    assert (y - ref).abs().max().item() < 1e-4
+
+
+def test_mask_prompt_embed_matches_conv_stack(ops):
+    """mask_downsample (k4 s4) + PromptEncoder.mask_downscaling up to its 1x1 conv (prompt_encoder.py:52-60)."""
+    torch.manual_seed(23)
+    B, S = 2, 128
+    m = (torch.rand(B, 1, S, S, device=DEV) > 0.5).float()
+    wds, bds = torch.randn(1, 1, 4, 4, device=DEV) / 4, torch.randn(1, device=DEV)
+    w0, b0 = torch.randn(4, 1, 2, 2, device=DEV) / 2, torch.randn(4, device=DEV)
+    g0, be0 = torch.rand(4, device=DEV) + 0.5, torch.randn(4, device=DEV) * 0.1
+    w3, b3 = torch.randn(16, 4, 2, 2, device=DEV) / 4, torch.randn(16, device=DEV)
+    g3, be3 = torch.rand(16, device=DEV) + 0.5, torch.randn(16, device=DEV) * 0.1
+    out = torch.empty(B * (S // 16) ** 2, 16, device=DEV, dtype=torch.bfloat16)
+    ops.mask_prompt_embed(m.view(B, S, S).contiguous(), wds.reshape(-1).contiguous(), bds, w0.reshape(4, 4).contiguous(), b0, g0, be0,
+                          w3.reshape(16, 16).contiguous(), b3, g3, be3, out)
+    x = F.conv2d(m, wds, bds, stride=4)
+    x = F.gelu(_ln2d_b(F.conv2d(x, w0, b0, stride=2), g0, be0))
+    x = F.gelu(_ln2d_b(F.conv2d(x, w3, b3, stride=2), g3, be3))
+    ref = x.permute(0, 2, 3, 1).reshape(-1, 16)
+    assert (out.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+
+
+def _ln2d_b(x, w, b):
+    u = x.mean(1, keepdim=True)
+    s = (x - u).pow(2).mean(1, keepdim=True)
+    return w[None, :, None, None] * ((x - u) / torch.sqrt(s + 1e-6)) + b[None, :, None, None]
+
+
 @pytest.mark.parametrize("N,H,W", [(3, 64, 256), (2, 37, 100), (16, 256, 1024)])
 def test_mask_pack_stats_exact(ops, N, H, W):
     """Integer path: packed bits == numpy.packbits(little) per row, stats == exact raw moments (cv2.moments m00/m10/m01)."""
