@@ -242,10 +242,19 @@ class VideoProcessor:
         directory = os.path.dirname(save_path)
         if directory and not os.path.exists(directory):
             os.makedirs(directory)
+        if str(save_path).endswith(".ds2bank"):
+            # compact, versioned format (bank_format.py); any other suffix keeps the reference's pickle so that
+            # banks stay exchangeable with Det-SAM2
+            from .bank_format import save_bank
+            save_bank(self.inference_state, save_path)
+            return
         with open(save_path, "wb") as f:
             pickle.dump(self.inference_state, f)
 
     def load_inference_state(self, load_path):
+        if str(load_path).endswith(".ds2bank"):
+            from .bank_format import load_bank
+            return load_bank(load_path)
         with open(load_path, "rb") as f:
             return pickle.load(f)
 
