@@ -25,6 +25,7 @@ SOURCES = [
     "post.cu",
     "prompt.cu",
     "bank.cu",
+    "ingest.cu",
 ]
 
 NVCC_FLAGS = [

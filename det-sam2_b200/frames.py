@@ -4,6 +4,12 @@
 rounded to fp16).  Frames stay on the host by default (``offload_video_to_cpu``); when a CUDA engine
 is in use the host tensor is pinned so the per-step upload (sam2_video_predictor.py:1184-1186) is an
 asynchronous DMA.
+
+With a CUDA compute device, ndarray frames are ingested ON THE DEVICE (``ds2_ingest_frames``, csrc/ingest.cu): the raw
+uint8 frames are staged through pinned memory, resized with OpenCV's exact 8-bit bilinear arithmetic and normalised
+through the same 3 x 256 table in one kernel, and the fp16 result is either kept in HBM
+(``offload_video_to_cpu=False``) or copied back into the pinned host tensor — bit-identical to the host path
+(tests/test_ingest.py) at a fraction of its time.  ``DS2_HOST_INGEST=1`` forces the host path.
 """
 import os
 
@@ -35,13 +41,14 @@ def _is_path(p):
 
 
 def load_video_frames(video_path, image_size, offload_video_to_cpu=True, compute_device=None,
-                      img_mean=IMG_MEAN, img_std=IMG_STD, async_loading_frames=False, pin=False):
+                      img_mean=IMG_MEAN, img_std=IMG_STD, async_loading_frames=False, pin=False, device_ingest=None):
     """Returns (images fp16 [N,3,S,S], video_height, video_width).
 
     ``video_path``: a JPEG directory ("<index>.jpg"), a list of image paths, one image path, one RGB
     uint8 ndarray [H,W,3] or a list of them (misc.py:254-303).  ``async_loading_frames`` is accepted
     for signature compatibility; loading is synchronous (the reference's async loader yields the same
-    tensor values).
+    tensor values).  ``device_ingest``: None = on the device whenever ``compute_device`` is CUDA and the frames are
+    ndarrays (unless DS2_HOST_INGEST=1), False = host, True = device (raises without CUDA).
     """
     arrays = None
     paths = None
@@ -66,6 +73,17 @@ def load_video_frames(video_path, image_size, offload_video_to_cpu=True, compute
     n = len(arrays) if arrays is not None else len(paths)
     to_device = not offload_video_to_cpu and compute_device is not None
     pinned = (pin or to_device) and torch.cuda.is_available()
+    on_cuda = compute_device is not None and torch.device(compute_device).type == "cuda"
+    if device_ingest is None:
+        device_ingest = on_cuda and arrays is not None and os.environ.get("DS2_HOST_INGEST", "0") != "1"
+    if device_ingest:
+        if arrays is None or not on_cuda:
+            raise RuntimeError("device ingest needs ndarray frames and a CUDA compute device")
+        lut = _normalize_lut(tuple(img_mean), tuple(img_std))
+        images = _ingest_on_device(arrays, image_size, lut, torch.device(compute_device), keep_on_device=to_device,
+                                   pin=pinned)
+        vh, vw = arrays[0].shape[:2]
+        return images, vh, vw
     images = torch.empty(n, 3, image_size, image_size, dtype=torch.float16, pin_memory=pinned)
     # Every pixel goes through the same three roundings as in the reference (u8/255 in float64 -> fp16, `-= mean`
     # and `/= std` each rounded to fp16), but there are only 3 x 256 distinct inputs: the per-channel table is
@@ -87,6 +105,68 @@ def load_video_frames(video_path, image_size, offload_video_to_cpu=True, compute
         images = images.to(compute_device, non_blocking=True)
         torch.cuda.current_stream(compute_device).synchronize()
     return images, vh, vw
+
+
+_STAGE = {}
+_DEV_LUTS = {}
+_INGEST_BATCH = 16     # frames per staging round: bounds the pinned staging buffer (16 x 1080p = 100 MB)
+
+
+def _check_frame(fr):
+    if not isinstance(fr, np.ndarray) or fr.dtype != np.uint8 or fr.ndim != 3 or fr.shape[2] != 3:
+        raise RuntimeError(f"expected an RGB uint8 frame [H,W,3], got "
+                           f"{getattr(fr, 'dtype', type(fr))} {getattr(fr, 'shape', '')}")
+
+
+def _ingest_on_device(arrays, image_size, lut, device, keep_on_device, pin):
+    """uint8 RGB ndarrays -> fp16 [N,3,S,S] through ds2_ingest_frames.  Frames go through a re-used pinned staging
+    buffer in rounds of ``_INGEST_BATCH``; consecutive frames of one size share a launch.  The result stays on the
+    device (``keep_on_device``) or is copied back into a (pinned) host tensor, one stream synchronisation in total."""
+    from . import ops
+    n = len(arrays)
+    for fr in arrays:
+        _check_frame(fr)
+    stream = torch.cuda.current_stream(device)
+    key = (str(device), lut.tobytes())
+    dev_lut = _DEV_LUTS.get(key)
+    if dev_lut is None:     # fp16 bit patterns travel as int16 (torch has no arithmetic-free uint16 path on every op)
+        dev_lut = _DEV_LUTS[key] = torch.from_numpy(lut.view(np.int16).copy()).to(device)
+    with torch.cuda.device(device):
+        dst = torch.empty(n, 3, image_size, image_size, dtype=torch.float16, device=device)
+        i = 0
+        rounds = []
+        while i < n:
+            shape = arrays[i].shape
+            j = i
+            while j < n and j - i < _INGEST_BATCH and arrays[j].shape == shape:
+                j += 1
+            nbytes = (j - i) * shape[0] * shape[1] * 3
+            # two staging buffers alternate so that filling round r+1 overlaps the DMA of round r
+            slot = len(rounds) & 1
+            stage = _STAGE.get(slot)
+            if stage is None or stage.numel() < nbytes:
+                stage = _STAGE[slot] = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, pin_memory=True)
+            if len(rounds) >= 2:
+                rounds[-2].synchronize()       # the DMA that last read this slot
+            view = stage[:nbytes].view(j - i, shape[0], shape[1], 3)
+            host = view.numpy()
+            for k in range(i, j):
+                np.copyto(host[k - i], arrays[k])
+            dev_u8 = view.to(device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            rounds.append(ev)
+            ops.ingest_frames(dev_u8, dev_lut, dst[i:j])
+            i = j
+        if keep_on_device:
+            stream.synchronize()
+            return dst
+        # always pinned: a pageable destination would turn the copy into a synchronous bounce through the driver's
+        # staging buffer (torch's host allocator re-uses the block once the previous chunk's tensor is gone)
+        images = torch.empty(n, 3, image_size, image_size, dtype=torch.float16, pin_memory=True)
+        images.copy_(dst, non_blocking=True)
+        stream.synchronize()
+    return images
 
 
 def normalize_frames_arithmetic(frames_u8, img_mean=IMG_MEAN, img_std=IMG_STD):

@@ -299,5 +299,21 @@ def mask_pack_stats(masks, bits=None, stats=None):
     return bits, stats
 
 
+def ingest_frames(src_u8, lut, out):
+    """Frame ingest (misc.py:336-359 on the device): src_u8 uint8 [N, Hv, Wv, 3] RGB (rows / frames may be strided),
+    lut int16 [3, 256] = fp16 bit patterns of the normalised byte values, out fp16 [N, 3, S, S] contiguous."""
+    for t, dt, nm in ((src_u8, torch.uint8, "src_u8"), (lut, torch.int16, "lut"), (out, torch.float16, "out")):
+        _req(t, dt, f"ingest_frames.{nm}")
+    if src_u8.dim() != 4 or src_u8.shape[3] != 3 or src_u8.stride(3) != 1 or src_u8.stride(2) != 3:
+        raise capi.Ds2Error(f"ingest_frames: src must be [N, Hv, Wv, 3] with packed RGB pixels, got {tuple(src_u8.shape)}")
+    N, Hv, Wv, _ = src_u8.shape
+    S = out.shape[-1]
+    if tuple(out.shape) != (N, 3, S, S) or not out.is_contiguous() or tuple(lut.shape) != (3, 256) or not lut.is_contiguous():
+        raise capi.Ds2Error("ingest_frames: out must be contiguous [N, 3, S, S] and lut contiguous [3, 256]")
+    _chk(_lib().ds2_ingest_frames(_p(src_u8), N, Hv, Wv, src_u8.stride(1), src_u8.stride(0) if N > 1 else max(src_u8.stride(0), src_u8.stride(1) * Hv),
+                                  _p(lut), _p(out), S, _stream()), "ds2_ingest_frames")
+    return out
+
+
 def launch_count():
     return int(_lib().ds2_launch_count())

@@ -124,6 +124,10 @@ class SAM2VideoPredictor:
         st = inference_state
         if offload_video_to_cpu:
             st["images"] = st["images"].to("cpu")
+        elif self.device.type == "cuda":
+            # addition: a bank saved from a host-frames session continues with its frames in HBM
+            st["images"] = st["images"].to(self.device)
+            st["offload_video_to_cpu"] = False
         st["device"] = self.device
         st["storage_device"] = torch.device("cpu") if offload_state_to_cpu else self.device
         dev = st["storage_device"]
@@ -149,9 +153,20 @@ class SAM2VideoPredictor:
         st["images_idx"].extend(range(last + 1, last + 1 + len(new_images)))
         images = st["images"]
         assert images.shape[1:] == new_images.shape[1:]
-        st["images"] = torch.cat((images, new_images.to(images.device)), dim=0)
+        st["images"] = torch.cat((images, new_images.to(images.device)), dim=0,
+                                 out=self._host_frames_like(images, len(images) + len(new_images)))
         st["num_frames"] += len(new_images)
         return st
+
+    def _host_frames_like(self, images, n):
+        """Destination for the per-chunk re-packing of the session's frame tensor (svp:196 torch.cat, svp:1262
+        index_select).  Host-resident frames of a CUDA session go into PINNED memory: a fresh pageable 0.5 GB tensor
+        costs ~0.4 s of first-touch page faults per chunk (more than the chunk's GPU work), while torch's caching host
+        allocator hands the block of the previous chunk back, and the per-step upload (svp:1184-1186) becomes an
+        asynchronous DMA.  Device-resident frames and CPU sessions use the default allocation (None)."""
+        if images.is_cuda or self.device.type != "cuda" or not torch.cuda.is_available():
+            return None
+        return torch.empty((n,) + tuple(images.shape[1:]), dtype=images.dtype, pin_memory=True)
 
     # ---- object ids ------------------------------------------------------------------------------
     def _obj_id_to_idx(self, st, obj_id):
@@ -692,7 +707,8 @@ class SAM2VideoPredictor:
             if old_imgs:
                 keep_rows = [r for r, i in enumerate(st["images_idx"]) if i not in old_imgs]
                 idx = torch.tensor(keep_rows, dtype=torch.long, device=st["images"].device)
-                st["images"] = torch.index_select(st["images"], 0, idx)
+                st["images"] = torch.index_select(st["images"], 0, idx,
+                                                  out=self._host_frames_like(st["images"], len(keep_rows)))
                 st["images_idx"] = [i for i in st["images_idx"] if i not in old_imgs]
                 for i in list(st["cached_features"].keys()):
                     if i in old_imgs:

@@ -49,7 +49,8 @@ class VideoProcessor:
                  detect_model_weights=None, detect_confidence=0.85, skip_classes=frozenset({11, 14, 15, 19}),
                  vis_frame_stride=-1, visualize_prompt=False, frame_buffer_size=30, detect_interval=30,
                  max_frame_num_to_track=60, max_inference_state_frames=60, load_inference_state_path=None,
-                 save_inference_state_path=None, *, predictor=None, detector=None, device="cuda", object_stats=False):
+                 save_inference_state_path=None, *, predictor=None, detector=None, device="cuda", object_stats=False,
+                 frames_on_device=None):
         if vis_frame_stride != -1 or visualize_prompt:
             raise NotImplementedError("matplotlib rendering is outside the hot path; use vis_frame_stride=-1")
         if save_inference_state_path is not None:
@@ -87,6 +88,14 @@ class VideoProcessor:
         # computed on the GPU in integer arithmetic (ds2_mask_pack_stats) — what Det-SAM2's post-processor derives
         # from the boolean masks with cv2.moments (postprocess_det_sam2.py:331-343); None for an empty mask
         self.object_stats = bool(object_stats)
+        # addition: keep the session's fp16 frames in HBM (the reference's `offload_video_to_cpu=False`, svp:44-53)
+        # instead of its default host tensor: frames are ingested on the device (ds2_ingest_frames) and neither the
+        # per-chunk torch.cat (svp:196) nor the per-step upload (svp:1184-1186) touches host memory.  A window of
+        # S + K = 90 frames is 0.57 GB of the 180 GB.  None = on for a CUDA predictor; False = the reference's
+        # host-resident frames (then re-packed in pinned memory, predictor._host_frames_like).
+        if frames_on_device is None:
+            frames_on_device = getattr(getattr(predictor, "device", None), "type", "cpu") == "cuda"
+        self.frames_on_device = bool(frames_on_device)
         self.video_stats = {}
         self.inference_state = None
         if output_dir:
@@ -149,7 +158,8 @@ class VideoProcessor:
         past_num_frames = self.inference_state["num_frames"] if self.inference_state else 0
         detection_results_json = self.detect_predict(self.frame_buffer, past_num_frames)
         if self.inference_state is None:
-            self.inference_state = self.predictor.init_state(video_path=self.frame_buffer)
+            self.inference_state = self.predictor.init_state(video_path=self.frame_buffer,
+                                                             offload_video_to_cpu=not self.frames_on_device)
         else:
             self.inference_state = self.predictor.update_state(video_path=self.frame_buffer,
                                                                inference_state=self.inference_state)
@@ -279,7 +289,10 @@ class VideoProcessor:
             st["preloading_memory_non_cond_frames_idx"] = list(st["output_dict"]["non_cond_frame_outputs"].keys())
             self.pre_frames = st["num_frames"]
             self.inference_state = st
-            self.predictor.init_preloading_state(st)
+            if self.frames_on_device:
+                self.predictor.init_preloading_state(st, offload_video_to_cpu=False)
+            else:
+                self.predictor.init_preloading_state(st)
 
         def stream():
             if frames is not None:

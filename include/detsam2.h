@@ -273,6 +273,17 @@ int ds2_mask_prompt_embed(const float* mask, int32_t B, int32_t S, const float* 
 int ds2_mask_pack_stats(const float* x, uint8_t* bits, uint64_t* stats, int32_t N, int32_t H, int32_t W,
                         void* stream);
 
+/* ---- frame ingest ------------------------------------------------------------------------
+ * load_video_frames, ndarray branches (sam2/utils/misc.py:336-359): per frame `cv2.resize(frame_rgb, (S, S)) / 255.0`
+ * stored into the fp16 `images` tensor, then `images -= mean; images /= std` in fp16.
+ * src_u8: N RGB frames uint8 [Hv][Wv][3] (row pitch and frame stride in bytes);  dst_f16: fp16 [N][3][S][S].
+ * The resize is OpenCV's 8-bit INTER_LINEAR reproduced bit for bit (11-bit fixed-point weights; the exact 2x
+ * decimation is a 2x2 box mean; equal sizes copy), see oracle/resize_oracle.py.  lut_3x256: uint16 [3][256], the fp16
+ * bit pattern of the normalised value of byte v in channel c, built by the caller with the reference's arithmetic
+ * (the three roundings have only 3 x 256 distinct inputs).                                                        */
+int ds2_ingest_frames(const uint8_t* src_u8, int32_t N, int32_t Hv, int32_t Wv, int64_t pitch_bytes,
+                      int64_t frame_stride_bytes, const uint16_t* lut_3x256, void* dst_f16, int32_t S, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

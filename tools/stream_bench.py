@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--objects", type=int, default=16)
     ap.add_argument("--model", default="large")
     ap.add_argument("--cache", type=int, default=64, help="backbone-feature cache (frames); the reference keeps 1")
+    ap.add_argument("--skip-single-cache", action="store_true", help="only run the --cache setting")
+    ap.add_argument("--frames-on-device", type=int, default=1, help="keep the session's fp16 frames in HBM")
     args = ap.parse_args()
     from detsam2_b200.build_sam import build_sam2_video_predictor
     from detsam2_b200.synthetic import BilliardVideo, GroundTruthDetector
@@ -31,7 +33,7 @@ def main():
     yaml = {"tiny": "t", "small": "s", "base_plus": "b+", "large": "l"}[args.model]
     dev = torch.device("cuda", 0)
     res = {}
-    for cache in (1, args.cache):
+    for cache in ((args.cache,) if args.skip_single_cache else (1, args.cache)):
         predictor = build_sam2_video_predictor(f"configs/sam2.1/sam2.1_hiera_{yaml}.yaml", device=dev, seed=0,
                                                feature_cache_frames=cache)
         S = predictor.cfg.image_size
@@ -46,11 +48,32 @@ def main():
             return orig(*a, **kw)
 
         predictor._run_single_frame_inference = counted
+        # coarse host-side wall time per predictor entry point (GPU work is asynchronous: a phase that synchronises
+        # also absorbs the device time still queued before it)
+        phase = {}
+
+        def timed(name):
+            fn = getattr(predictor, name)
+
+            def wrap(*a, **kw):
+                t = time.perf_counter()
+                try:
+                    return fn(*a, **kw)
+                finally:
+                    phase[name] = phase.get(name, 0.0) + time.perf_counter() - t
+            setattr(predictor, name, wrap)
+
+        for name in ("init_state", "update_state", "add_new_boxes", "add_new_points_or_box",
+                     "propagate_in_video_preflight", "release_old_frames"):
+            if hasattr(predictor, name):
+                timed(name)
         for rep in range(2):   # first pass warms up graphs / allocator; second is timed
             steps[0] = 0
+            phase.clear()
             vp = VideoProcessor(predictor=predictor, detector=GroundTruthDetector(vid, detect_interval=30),
                                 frame_buffer_size=30, detect_interval=30, max_frame_num_to_track=60,
-                                max_inference_state_frames=60, skip_classes=set())
+                                max_inference_state_frames=60, skip_classes=set(),
+                                frames_on_device=bool(args.frames_on_device))
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             with torch.inference_mode():
@@ -64,11 +87,13 @@ def main():
                   flush=True)
         res[f"feature_cache_{cache}"] = {"video_fps": round(args.frames / dt, 2), "track_steps_per_s": round(steps[0] / dt, 2),
                                          "track_steps": steps[0], "wall_s": round(dt, 3),
-                                         "frames_with_result": len(segs)}
+                                         "frames_with_result": len(segs),
+                                         "host_phase_s": {k: round(v, 3) for k, v in phase.items()}}
         del predictor, vp
         torch.cuda.empty_cache()
     line = {"mode": "Det-SAM2 stream (VideoProcessor: K=30, detect every 30, M=60, S=60, reverse)", "model": args.model,
-            "objects": args.objects, "frames": args.frames, "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2), **res}
+            "objects": args.objects, "frames": args.frames, "frames_on_device": bool(args.frames_on_device),
+            "host_ingest": os.environ.get("DS2_HOST_INGEST", "0") == "1", "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2), **res}
     print(json.dumps(line))
     with open(os.path.join(ROOT, "gpurun_out", "stream_bench.json"), "w") as f:
         f.write(json.dumps(line) + "\n")
