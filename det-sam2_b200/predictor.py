@@ -18,6 +18,7 @@ Engine seams (each mirrors one reference function; see engine.py):
   fill_holes(pred_masks, max_area), resize_masks(masks, H, W)        svp:1341-1348, 618-642
 """
 import gc
+import os
 from collections import OrderedDict
 
 import torch
@@ -153,20 +154,12 @@ class SAM2VideoPredictor:
         st["images_idx"].extend(range(last + 1, last + 1 + len(new_images)))
         images = st["images"]
         assert images.shape[1:] == new_images.shape[1:]
-        st["images"] = torch.cat((images, new_images.to(images.device)), dim=0,
-                                 out=self._host_frames_like(images, len(images) + len(new_images)))
+        # (re-packing host-resident frames into pinned memory was measured and dropped: 21.7 against 28.0 video
+        # frames/s in stream mode, profiles/r1_s16_stream_modes.txt; frames in HBM — offload_video_to_cpu=False — is
+        # the fast configuration)
+        st["images"] = torch.cat((images, new_images.to(images.device)), dim=0)
         st["num_frames"] += len(new_images)
         return st
-
-    def _host_frames_like(self, images, n):
-        """Destination for the per-chunk re-packing of the session's frame tensor (svp:196 torch.cat, svp:1262
-        index_select).  Host-resident frames of a CUDA session go into PINNED memory: a fresh pageable 0.5 GB tensor
-        costs ~0.4 s of first-touch page faults per chunk (more than the chunk's GPU work), while torch's caching host
-        allocator hands the block of the previous chunk back, and the per-step upload (svp:1184-1186) becomes an
-        asynchronous DMA.  Device-resident frames and CPU sessions use the default allocation (None)."""
-        if images.is_cuda or self.device.type != "cuda" or not torch.cuda.is_available():
-            return None
-        return torch.empty((n,) + tuple(images.shape[1:]), dtype=images.dtype, pin_memory=True)
 
     # ---- object ids ------------------------------------------------------------------------------
     def _obj_id_to_idx(self, st, obj_id):
@@ -707,14 +700,17 @@ class SAM2VideoPredictor:
             if old_imgs:
                 keep_rows = [r for r, i in enumerate(st["images_idx"]) if i not in old_imgs]
                 idx = torch.tensor(keep_rows, dtype=torch.long, device=st["images"].device)
-                st["images"] = torch.index_select(st["images"], 0, idx,
-                                                  out=self._host_frames_like(st["images"], len(keep_rows)))
+                st["images"] = torch.index_select(st["images"], 0, idx)
                 st["images_idx"] = [i for i in st["images_idx"] if i not in old_imgs]
                 for i in list(st["cached_features"].keys()):
                     if i in old_imgs:
                         st["cached_features"].pop(i)
             assert len(st["images"]) == len(st["images_idx"])
-        gc.collect()
+        # the reference ends with gc.collect() (svp:1277).  Nothing here is cyclic — tensors die with their dict
+        # entries by reference count — and a full collection costs 40-80 ms per chunk with torch loaded, so it is
+        # only kept for CPU sessions, where it is what the reference does
+        if self.device.type != "cuda":
+            gc.collect()
 
     @torch.inference_mode()
     def remove_object(self, inference_state, obj_id, strict=False, need_output=True):

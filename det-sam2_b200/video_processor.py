@@ -16,6 +16,7 @@ loaded from ultralytics only when ``detect_model_weights`` is given and no detec
 matplotlib rendering (``vis_frame_stride``, ``visualize_prompt``) is not provided.
 """
 import os
+import time
 import pickle
 
 import numpy as np
@@ -92,11 +93,12 @@ class VideoProcessor:
         # instead of its default host tensor: frames are ingested on the device (ds2_ingest_frames) and neither the
         # per-chunk torch.cat (svp:196) nor the per-step upload (svp:1184-1186) touches host memory.  A window of
         # S + K = 90 frames is 0.57 GB of the 180 GB.  None = on for a CUDA predictor; False = the reference's
-        # host-resident frames (then re-packed in pinned memory, predictor._host_frames_like).
+        # host-resident frames.
         if frames_on_device is None:
             frames_on_device = getattr(getattr(predictor, "device", None), "type", "cpu") == "cuda"
         self.frames_on_device = bool(frames_on_device)
         self.video_stats = {}
+        self.timings = {}
         self.inference_state = None
         if output_dir:
             os.makedirs(output_dir, exist_ok=True)
@@ -155,14 +157,18 @@ class VideoProcessor:
 
     # ---- one chunk (det_sam2_RT.py:342-411) --------------------------------------------------------
     def Detect_and_SAM2_inference(self, frame_idx):
+        tm = self.timings
+        t0 = time.perf_counter()
         past_num_frames = self.inference_state["num_frames"] if self.inference_state else 0
         detection_results_json = self.detect_predict(self.frame_buffer, past_num_frames)
+        t1 = time.perf_counter()
         if self.inference_state is None:
             self.inference_state = self.predictor.init_state(video_path=self.frame_buffer,
                                                              offload_video_to_cpu=not self.frames_on_device)
         else:
             self.inference_state = self.predictor.update_state(video_path=self.frame_buffer,
                                                                inference_state=self.inference_state)
+        t2 = time.perf_counter()
         try:
             self.inference_state = self.Detect_2_SAM2_Prompt(detection_results_json)
         except RuntimeError as e:
@@ -171,6 +177,7 @@ class VideoProcessor:
                 self.inference_state = self.Detect_2_SAM2_Prompt(detection_results_json)
             else:
                 raise
+        t3 = time.perf_counter()
         pending = []
         for out_frame_idx, out_obj_ids, out_mask_logits in self.predictor.propagate_in_video(
                 self.inference_state, start_frame_idx=frame_idx,
@@ -184,19 +191,39 @@ class VideoProcessor:
                                     stats))
                 else:
                     self.video_segments[out_frame_idx] = self._masks_to_host(out_obj_ids, out_mask_logits)
+        t4 = t5 = time.perf_counter()
         if pending:
             torch.cuda.current_stream().synchronize()
-            for out_frame_idx, ids, host, stats in pending:
-                m = host.numpy().copy()   # the pinned buffers are re-used by the next chunk
+            t5 = time.perf_counter()
+            # the pinned buffers are re-used by the next chunk, so every frame's [B,1,Hv,Wv] boolean block is copied
+            # out — 1 GB per chunk at 16 objects x 1024^2, first-touch page faults included.  numpy releases the GIL
+            # for these copies: a few worker threads bring the 0.18 s per chunk of a single thread down ~5x
+            copies = list(self._copy_pool().map(lambda p: p[2].numpy().copy(), pending))
+            for (out_frame_idx, ids, host, stats), m in zip(pending, copies):
                 self.video_segments[out_frame_idx] = {oid: m[i] for i, oid in enumerate(ids)}
                 if stats is not None:
                     st_ = stats.numpy()
                     self.video_stats[out_frame_idx] = {
                         oid: (None if st_[i, 0] == 0 else (int(st_[i, 0]), st_[i, 1] / st_[i, 0], st_[i, 2] / st_[i, 0]))
                         for i, oid in enumerate(ids)}
+        t6 = time.perf_counter()
         if self.max_inference_state_frames != -1:
             self.predictor.release_old_frames(self.inference_state, frame_idx, self.max_inference_state_frames,
                                               self.pre_frames, release_images=self.vis_frame_stride == -1)
+        t7 = time.perf_counter()
+        # host wall time per phase of the chunk (the device runs asynchronously: "gpu_wait" is how long the host
+        # idled at the end of the propagate loop for queued device work, i.e. the chunk was device-bound by that much)
+        for k, v in (("detect", t1 - t0), ("frames", t2 - t1), ("prompt", t3 - t2), ("propagate_enqueue", t4 - t3),
+                     ("gpu_wait", t5 - t4), ("hand_off", t6 - t5), ("release", t7 - t6)):
+            tm[k] = tm.get(k, 0.0) + v
+
+    def _copy_pool(self):
+        pool = self.__dict__.get("_pool")
+        if pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            pool = self._pool = ThreadPoolExecutor(max_workers=max(1, min(8, os.cpu_count() or 1)),
+                                                   thread_name_prefix="ds2-handoff")
+        return pool
 
     def _masks_to_pinned(self, mask_logits, slot):
         """(logits > 0) -> pinned host buffer `slot` of a per-chunk ring, asynchronously on the current stream."""

@@ -69,6 +69,8 @@ def main():
                 timed(name)
         for rep in range(2):   # first pass warms up graphs / allocator; second is timed
             steps[0] = 0
+            gr = predictor.engine.graphs
+            g0 = (gr.captures, gr.replays, sum(gr.hits.values()))
             phase.clear()
             vp = VideoProcessor(predictor=predictor, detector=GroundTruthDetector(vid, detect_interval=30),
                                 frame_buffer_size=30, detect_interval=30, max_frame_num_to_track=60,
@@ -88,7 +90,11 @@ def main():
         res[f"feature_cache_{cache}"] = {"video_fps": round(args.frames / dt, 2), "track_steps_per_s": round(steps[0] / dt, 2),
                                          "track_steps": steps[0], "wall_s": round(dt, 3),
                                          "frames_with_result": len(segs),
-                                         "host_phase_s": {k: round(v, 3) for k, v in phase.items()}}
+                                         "host_phase_s": {k: round(v, 3) for k, v in phase.items()},
+                                         "chunk_phase_s": {k: round(v, 3) for k, v in vp.timings.items()},
+                                         "graphs_in_timed_pass": {"captured": gr.captures - g0[0], "replays": gr.replays - g0[1],
+                                                                  "eager_seam_runs": sum(gr.hits.values()) - g0[2],
+                                                                  "graphs_total": len(gr.graphs)}}
         del predictor, vp
         torch.cuda.empty_cache()
     line = {"mode": "Det-SAM2 stream (VideoProcessor: K=30, detect every 30, M=60, S=60, reverse)", "model": args.model,
