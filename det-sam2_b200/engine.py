@@ -446,77 +446,103 @@ class CudaEngine:
                                                        self._encode_image_body, (True, True, True, True))
         return FrameFeats(vis, vis16, feat_s0, feat_s1)
 
-    def _encode_image_body(self, inp):
+    def encode_images(self, images_f16):
+        """Several frames through ONE pass of the encoder: fp16 [n,3,S,S] -> list of n FrameFeats.
+
+        The frames of a chunk (or of an offline video) are all known before they are tracked, and the backbone does
+        not depend on the tracker, so the predictor encodes the next few frames of its processing order together
+        (predictor._get_image_feature).  Every kernel of the encoder treats rows / windows / (frame, head) pairs
+        independently, so each frame's features are bit-identical to ``encode_image`` on that frame alone
+        (tests/test_engine_gpu.py::test_batched_encoder_is_bit_identical); what changes is the shape of the work:
+        at one frame the Hiera stage-3 GEMMs have M = 4096 rows (32 row tiles for 148 SMs, ~20 us launches dominated by
+        fill/drain), at four frames the same launches carry four times the rows."""
+        cfg = self.cfg
+        S = cfg.image_size
+        n = images_f16.shape[0]
+        if images_f16.dtype != torch.float16 or tuple(images_f16.shape[1:]) != (3, S, S):
+            raise Ds2Error(f"encode_images expects fp16 [n,3,{S},{S}] frames, got {images_f16.dtype} {tuple(images_f16.shape)}")
+        if n == 1:
+            return [self.encode_image(images_f16[0])]
+        body = lambda inp: self._encode_image_body(inp, n)  # noqa: E731
+        vis, vis16, feat_s0, feat_s1 = self.graphs.run(("enc", n), {"img": images_f16.contiguous()}, body,
+                                                       (True, True, True, True))
+        return [FrameFeats(*(t.view(n, t.shape[0] // n, t.shape[1])[i] for t in (vis, vis16, feat_s0, feat_s1)))
+                for i in range(n)]
+
+    def _encode_image_body(self, inp, nb=1):
+        """Token-major throughout: activations are [nb * tokens, C] with frame f in rows [f * tokens, (f + 1) * tokens)."""
         cfg, p = self.cfg, self.p
         S = cfg.image_size
-        img = inp["img"]
+        img = inp["img"].view(nb, 3, S, S)
         Hc = Wc = S // 4
         T = Hc * Wc
         E = cfg.embed_dim
         kpad = p["pe.w"].shape[1]
-        cols = self._buf("im2col", (T, kpad), BF16)
-        ops.im2col_patch(img, cols, S, kpad)
-        x = self._buf("x0", (T, E), F32)
-        ops.gemm(cols, p["pe.w"], bias=p["pe.b"], residual=p["pos_embed"], out_f32=x)
+        cols = self._buf("im2col", (nb * T, kpad), BF16)
+        x = self._buf("x0", (nb * T, E), F32)
+        for f in range(nb):
+            ops.im2col_patch(img[f], cols[f * T:(f + 1) * T], S, kpad)
+            ops.gemm(cols[f * T:(f + 1) * T], p["pe.w"], bias=p["pe.b"], residual=p["pos_embed"],
+                     out_f32=x[f * T:(f + 1) * T])
         stage_out = []
         ends = cfg.stage_ends
         for i, b in enumerate(self.blocks):
             dim, do, heads, ws, pool = b["dim"], b["dim_out"], b["heads"], b["window"], b["q_pool"]
             T = Hc * Wc
-            xn = self._buf("xn", (T, dim), BF16)
+            xn = self._buf("xn", (nb * T, dim), BF16)
             ops.layernorm(x, p[f"b{i}.n1.w"], p[f"b{i}.n1.b"], 1e-6, out_bf16=xn)
             if dim != do:
-                sp = self._buf("sc_full", (T, do), F32)
+                sp = self._buf("sc_full", (nb * T, do), F32)
                 ops.gemm(xn, p[f"b{i}.sc.w"], bias=p[f"b{i}.sc.b"], out_f32=sp)
                 if pool:
-                    shortcut = self._buf(f"sc_pool{i}", (T // 4, do), F32)
-                    ops.maxpool2x2(sp, shortcut, 1, Hc, Wc, do)
+                    shortcut = self._buf(f"sc_pool{i}", (nb * T // 4, do), F32)
+                    ops.maxpool2x2(sp, shortcut, nb, Hc, Wc, do)
                 else:
                     shortcut = sp
             else:
                 shortcut = x
-            qkv = self._buf("qkv", (T, 3 * do), BF16)
+            qkv = self._buf("qkv", (nb * T, 3 * do), BF16)
             ops.gemm(xn, p[f"b{i}.qkv.w"], bias=p[f"b{i}.qkv.b"], out_bf16=qkv)
             Ho, Wo = (Hc // 2, Wc // 2) if pool else (Hc, Wc)
             Tq = Ho * Wo
-            att = self._buf("att", (Tq, do), BF16)
+            att = self._buf("att", (nb * Tq, do), BF16)
             hd = do // heads
             pad = None
             if ws > 0 and (Hc % ws or Wc % ws):
                 pr = p[f"b{i}.padrow"]
                 pad = (pr[:do], pr[do:2 * do], pr[2 * do:])
-            ops.mha(qkv, qkv[:, do:], qkv[:, 2 * do:], att, heads=heads, head_dim=hd, scale=1.0 / math.sqrt(hd), B=1,
+            ops.mha(qkv, qkv[:, do:], qkv[:, 2 * do:], att, heads=heads, head_dim=hd, scale=1.0 / math.sqrt(hd), B=nb,
                     Lq=Tq if ws == 0 else 0, Lk=T if ws == 0 else 0,
                     strides=(3 * do, 3 * do, 3 * do, do, T * 3 * do, T * 3 * do, T * 3 * do, Tq * do),
                     window=ws, Hm=Hc, Wm=Wc, q_pool=1 if pool else 0, pad=pad)
             if shortcut is x:
                 xo = x
             else:
-                xo = self._buf(f"x{i + 1}", (Tq, do), F32)
+                xo = self._buf(f"x{i + 1}", (nb * Tq, do), F32)
             ops.gemm(att, p[f"b{i}.proj.w"], bias=p[f"b{i}.proj.b"], residual=shortcut, out_f32=xo)
             x = xo
             Hc, Wc = Ho, Wo
-            xn2 = self._buf("xn", (Tq, do), BF16)
+            xn2 = self._buf("xn", (nb * Tq, do), BF16)
             ops.layernorm(x, p[f"b{i}.n2.w"], p[f"b{i}.n2.b"], 1e-6, out_bf16=xn2)
-            h = self._buf("mlp_h", (Tq, 4 * do), BF16)
+            h = self._buf("mlp_h", (nb * Tq, 4 * do), BF16)
             ops.gemm(xn2, p[f"b{i}.fc1.w"], bias=p[f"b{i}.fc1.b"], act=2, out_bf16=h)
             ops.gemm(h, p[f"b{i}.fc2.w"], bias=p[f"b{i}.fc2.b"], residual=x, out_f32=x)
             if i in ends:
-                so = self._buf(f"stage{len(stage_out)}", (Tq, do), BF16)
+                so = self._buf(f"stage{len(stage_out)}", (nb * Tq, do), BF16)
                 ops.cast_f32_bf16(x, so)
                 stage_out.append((so, Hc, Wc))
         (s1, h1, w1_), (s2, h2, w2_), (s3, h3, w3_), (s4, h4, w4_) = stage_out
-        lat3 = self._buf("lat3", (h4 * w4_, 256), F32)
+        lat3 = self._buf("lat3", (nb * h4 * w4_, 256), F32)
         ops.gemm(s4, p["neck3.w"], bias=p["neck3.b"], out_f32=lat3)
-        lat2 = self._buf("lat2", (h3 * w3_, 256), F32)
+        lat2 = self._buf("lat2", (nb * h3 * w3_, 256), F32)
         ops.gemm(s3, p["neck2.w"], bias=p["neck2.b"], out_f32=lat2)
-        vis = torch.empty((h3 * w3_, 256), dtype=F32, device=self.device)
-        ops.upsample2x_add(lat3, lat2, vis, 1, h4, w4_, 256)
-        vis16 = torch.empty((h3 * w3_, 256), dtype=BF16, device=self.device)
+        vis = torch.empty((nb * h3 * w3_, 256), dtype=F32, device=self.device)
+        ops.upsample2x_add(lat3, lat2, vis, nb, h4, w4_, 256)
+        vis16 = torch.empty((nb * h3 * w3_, 256), dtype=BF16, device=self.device)
         ops.cast_f32_bf16(vis, vis16)
-        feat_s1 = torch.empty((h2 * w2_, 64), dtype=F32, device=self.device)
+        feat_s1 = torch.empty((nb * h2 * w2_, 64), dtype=F32, device=self.device)
         ops.gemm(s2, p["s1.w"], bias=p["s1.b"], out_f32=feat_s1)
-        feat_s0 = torch.empty((h1 * w1_, 32), dtype=F32, device=self.device)
+        feat_s0 = torch.empty((nb * h1 * w1_, 32), dtype=F32, device=self.device)
         ops.gemm(s1, p["s0.w"], bias=p["s0.b"], out_f32=feat_s0)
         return vis, vis16, feat_s0, feat_s1
 

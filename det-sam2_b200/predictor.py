@@ -47,7 +47,7 @@ class SAM2VideoPredictor:
 
     def __init__(self, engine, fill_hole_area=0, non_overlap_masks=False, clear_non_cond_mem_around_input=False,
                  clear_non_cond_mem_for_multi_obj=False, add_all_frames_to_correct_as_cond=False,
-                 feature_cache_frames=1, verbose=False):
+                 feature_cache_frames=1, encoder_batch_frames=None, verbose=False):
         self.engine = engine
         self.cfg = engine.cfg
         self.fill_hole_area = fill_hole_area
@@ -58,6 +58,15 @@ class SAM2VideoPredictor:
         # the reference caches exactly one frame's backbone features (svp:1190); a larger cache is a
         # pure speed-up for Det-SAM2's reverse re-tracking (each frame is visited M/K times)
         self.feature_cache_frames = max(1, int(feature_cache_frames))
+        # frames encoded per pass of the image encoder while propagating: the frames still to be tracked are known
+        # (processing order of propagate_in_video) and their backbone features do not depend on the tracker, so the
+        # next few are encoded together (engine.encode_images; bit-identical per frame, a better shape for the GPU).
+        # 1 = the reference's frame-at-a-time behaviour; DS2_ENC_BATCH overrides the default of 4.
+        if encoder_batch_frames is None:
+            encoder_batch_frames = int(os.environ.get("DS2_ENC_BATCH", "4"))
+        self.encoder_batch_frames = max(1, int(encoder_batch_frames)) if hasattr(engine, "encode_images") else 1
+        self._upcoming = None      # (id(state), frames the running propagate call will still encode, in order)
+        self._prefetched = {}      # frame_idx -> features encoded ahead of their step (same propagate call only)
         self.verbose = verbose
 
     # ---- attributes callers read on the reference model ------------------------------------------
@@ -493,27 +502,36 @@ class SAM2VideoPredictor:
         else:
             end = min(start_frame_idx + max_frame_num_to_track, num_frames - 1)
             order = range(start_frame_idx, end + 1)
-        for frame_idx in order:
-            if frame_idx in cons["cond_frame_outputs"]:
-                key = "cond_frame_outputs"
-                current_out = output_dict[key][frame_idx]
-                pred_masks = current_out["pred_masks"]
-                if clear_non_cond_mem:
-                    self._clear_non_cond_mem_around_input(st, frame_idx)
-            elif frame_idx in cons["non_cond_frame_outputs"]:
-                key = "non_cond_frame_outputs"
-                current_out = output_dict[key][frame_idx]
-                pred_masks = current_out["pred_masks"]
-            else:
-                key = "non_cond_frame_outputs"
-                current_out, pred_masks = self._run_single_frame_inference(
-                    st, output_dict, frame_idx, batch_size=B, is_init_cond_frame=False, point_inputs=None,
-                    mask_inputs=None, reverse=reverse, run_mem_encoder=True)
-                output_dict[key][frame_idx] = current_out
-            self._add_output_per_object(st, frame_idx, current_out, key)
-            st["frames_already_tracked"][frame_idx] = {"reverse": reverse}
-            _, video_res_masks = self._get_orig_video_res_output(st, pred_masks)
-            yield frame_idx, obj_ids, video_res_masks
+        order = list(order)
+        if self.encoder_batch_frames > 1:
+            self._upcoming = (id(st), [f for f in order if f not in cons["cond_frame_outputs"]
+                                       and f not in cons["non_cond_frame_outputs"]])
+            self._prefetched = {}
+        try:
+            for frame_idx in order:
+                if frame_idx in cons["cond_frame_outputs"]:
+                    key = "cond_frame_outputs"
+                    current_out = output_dict[key][frame_idx]
+                    pred_masks = current_out["pred_masks"]
+                    if clear_non_cond_mem:
+                        self._clear_non_cond_mem_around_input(st, frame_idx)
+                elif frame_idx in cons["non_cond_frame_outputs"]:
+                    key = "non_cond_frame_outputs"
+                    current_out = output_dict[key][frame_idx]
+                    pred_masks = current_out["pred_masks"]
+                else:
+                    key = "non_cond_frame_outputs"
+                    current_out, pred_masks = self._run_single_frame_inference(
+                        st, output_dict, frame_idx, batch_size=B, is_init_cond_frame=False, point_inputs=None,
+                        mask_inputs=None, reverse=reverse, run_mem_encoder=True)
+                    output_dict[key][frame_idx] = current_out
+                self._add_output_per_object(st, frame_idx, current_out, key)
+                st["frames_already_tracked"][frame_idx] = {"reverse": reverse}
+                _, video_res_masks = self._get_orig_video_res_output(st, pred_masks)
+                yield frame_idx, obj_ids, video_res_masks
+        finally:
+            self._upcoming = None
+            self._prefetched = {}
 
     def _add_output_per_object(self, st, frame_idx, current_out, storage_key):
         """svp:1027-1058: per-object views sharing storage with the batched output."""
@@ -602,17 +620,58 @@ class SAM2VideoPredictor:
         view inside the engine (the reference expands with .expand, also views)."""
         cache = st["cached_features"]
         feats = cache.get(frame_idx, None)
+        if feats is not None:
+            return feats
+        if self._upcoming is not None and self._upcoming[0] == id(st):
+            feats = self._prefetched.pop(frame_idx, None)
         if feats is None:
-            row = st["images_idx"].index(frame_idx)
-            image = st["images"][row]
-            feats = self.engine.encode_image(image)
-            if self.feature_cache_frames <= 1:
-                st["cached_features"] = {frame_idx: feats}
+            batch = self._encoder_batch(st, frame_idx)
+            if len(batch) > 1:
+                rows = sorted((st["images_idx"].index(f), f) for f in batch)
+                r0, r1 = rows[0][0], rows[-1][0]
+                images = st["images"]
+                # neighbouring rows (the usual case, forward or reverse) are a view; anything else is gathered
+                stack = images[r0:r1 + 1] if r1 - r0 + 1 == len(rows) else images[[r for r, _ in rows]]
+                for (_, f), o in zip(rows, self.engine.encode_images(stack)):
+                    if f == frame_idx:
+                        feats = o
+                    else:
+                        self._prefetched[f] = o
             else:
-                while len(cache) >= self.feature_cache_frames:
-                    cache.pop(next(iter(cache)))
-                cache[frame_idx] = feats
+                row = st["images_idx"].index(frame_idx)
+                image = st["images"][row]
+                feats = self.engine.encode_image(image)
+        if self.feature_cache_frames <= 1:
+            st["cached_features"] = {frame_idx: feats}
+        else:
+            while len(cache) >= self.feature_cache_frames:
+                cache.pop(next(iter(cache)))
+            cache[frame_idx] = feats
         return feats
+
+    def drop_encoded_ahead(self):
+        """Forgets features that were encoded ahead of their step (bench.py calls this at the start of its timed region
+        so that every frame tracked inside the region is also encoded inside it)."""
+        self._prefetched = {}
+
+    def _encoder_batch(self, st, frame_idx):
+        """Frames to encode together with ``frame_idx``: the next ones of the running propagate call that have neither
+        cached nor prefetched features and whose pixels the session still holds."""
+        up = self._upcoming
+        E = self.encoder_batch_frames
+        if E <= 1 or up is None or up[0] != id(st) or frame_idx not in up[1]:
+            return [frame_idx]
+        todo = up[1]
+        pos = todo.index(frame_idx)
+        del todo[:pos + 1]             # everything before this frame has been handled
+        cache, have = st["cached_features"], set(st["images_idx"])
+        batch = [frame_idx]
+        for f in todo:
+            if len(batch) >= E:
+                break
+            if f not in cache and f not in self._prefetched and f in have:
+                batch.append(f)
+        return batch
 
     def _use_multimask(self, is_init_cond_frame, point_inputs):
         """sam2_base.py:922-932 (multimask_output_in_sam and multimask_output_for_tracking are true)."""

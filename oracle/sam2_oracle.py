@@ -590,6 +590,13 @@ class OracleEngine:
         bo = forward_image(self.sd, self.cfg, image_f16.float()[None])
         return {"fpn": bo["backbone_fpn"], "pos": bo["vision_pos_enc"]}
 
+    def encode_images(self, images_f16):
+        """Same seam for several frames (the product's engine batches them through one encoder pass; the backbone is
+        per-frame, so the oracle simply encodes one after the other).  Lets the CPU tests drive the predictor's
+        encode-ahead bookkeeping."""
+        self.encode_images_calls = getattr(self, "encode_images_calls", 0) + 1
+        return [self.encode_image(im) for im in images_f16]
+
     # seam 2: sam2_base.py:479-690
     def condition_on_memory(self, feats, B, frame_idx, is_init_cond_frame, output_dict, num_frames, reverse,
                             preload_idx):
