@@ -79,7 +79,11 @@ class VideoProcessor:
         self.special_classes_count = 0
         if predictor is None:
             from .build_sam import build_sam2_video_predictor
-            predictor = build_sam2_video_predictor(model_cfg, sam2_checkpoint, device=device)
+            # the reverse pass re-visits the last max_frame_num_to_track frames of every chunk: keep their backbone
+            # features (18 MB per 1024^2 frame) instead of the reference's single-frame cache (svp:1190), which
+            # re-encodes each frame M/K times
+            cache = max(1, max_frame_num_to_track + 4) if str(device).startswith("cuda") else 1
+            predictor = build_sam2_video_predictor(model_cfg, sam2_checkpoint, device=device, feature_cache_frames=cache)
         self.predictor = predictor
         if detector is None and detect_model_weights is not None:
             detector = _yolo_detector(detect_model_weights, detect_confidence)
