@@ -4,7 +4,8 @@ The GPU parity tests use these numbers as the calibration of "within bf16 tolera
 (bf16 operands, fp32 accumulation) must not deviate from the fp32 reference by more than the reference
 itself does when run the way Det-SAM2 runs it (torch.autocast bf16, det_sam2_RT.py:101-103).
 
-    python -m oracle.calibrate_bf16
+    python -m oracle.calibrate_bf16               # all scenarios
+    python -m oracle.calibrate_bf16 points_api    # only the named ones (the others keep their entries)
 """
 import json
 import os
@@ -48,8 +49,13 @@ def deviations(got, ref):
 
 def main():
     torch.set_num_threads(os.cpu_count() or 1)
+    path = os.path.join(ROOT, "tests", "golden", "ref_bf16_deviation.json")
+    names = sys.argv[1:] or ["stream", "preload", "offline", "mask_prompt", "points_api"]
     res = {}
-    for name in ("stream", "preload", "offline", "mask_prompt"):
+    if sys.argv[1:] and os.path.exists(path):     # re-calibrating some scenarios keeps the others
+        with open(path) as f:
+            res = json.load(f)["scenarios"]
+    for name in names:
         cfg = scenarios.scenario_config(name)
         sd = synthetic_state_dict(cfg, 0)
         ref = ref_shim.build_reference_predictor(cfg, sd, device="cpu")
@@ -66,7 +72,7 @@ def main():
         got = scenarios.SCENARIOS[name](ref)
         res[name] = deviations(got, gold)
         print(name, json.dumps(res[name], indent=1))
-    with open(os.path.join(ROOT, "tests", "golden", "ref_bf16_deviation.json"), "w") as f:
+    with open(path, "w") as f:
         json.dump({"what": "reference under torch.autocast(cpu, bf16) vs reference fp32, per scenario and array kind",
                    "torch": torch.__version__, "scenarios": res}, f, indent=1)
 

@@ -503,6 +503,9 @@ def forward_sam_heads(sd, cfg, backbone_features, point_coords=None, point_label
     tok = tokens[:, 0]
     if multimask_output:
         best = torch.argmax(ious, dim=-1)
+        if DECISION_LOG is not None:
+            top2 = torch.topk(ious, 2, dim=-1).values
+            DECISION_LOG.append({"multimask_top2_margin": (top2[:, 0] - top2[:, 1]).tolist()})
         bi = torch.arange(B)
         low, high = low_multi[bi, best].unsqueeze(1), high_multi[bi, best].unsqueeze(1)
         if tokens.shape[1] > 1:

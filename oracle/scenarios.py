@@ -14,6 +14,8 @@ Scenarios
             reverse propagate with max_frame_num_to_track, an online NEW object id while tracking
             (svp:250-327), release_old_frames with release_images (svp:1215-1277).
   mask_prompt  add_new_mask with a disc, a box on the same frame and an empty mask, then tracking (svp:527-600).
+  points_api  click prompts (one click / positive + negative / box + click), clear_all_prompts_in_frame,
+            remove_object, reset_state and a new object id afterwards (svp:344-520, 1061-1170, 1438-1553).
   preload   preload memory bank (det_sam2_RT.py:489-503, svp:123-156): every frame of a short clip is
             a conditioning frame, state is pickled, re-loaded, init_preloading_state, new frames
             appended with update_state and tracked against the bank.
@@ -160,6 +162,49 @@ def run_mask_prompt(predictor, num_frames=3, height=192, width=256, seed=9):
     return rec
 
 
+def run_points_api(predictor, num_frames=4, height=192, width=256, seed=23):
+    """Point prompts and session management through the public API (svp:344-520, 1061-1170, 1438-1553):
+    object 0 = ONE positive click (the multimask path of an initial conditioning frame, sam2_base.py:922-932),
+    object 1 = a positive and a negative click, object 2 = a box plus a positive click (box corners become the first
+    two points, svp:398-413); forward tracking; clear_all_prompts_in_frame + remove_object of object 1 (the state is
+    re-indexed, svp:1438-1553) and tracking again; reset_state, a click for a NEW object id on frame 1, tracking from
+    there."""
+    vid = BilliardVideo(num_objects=3, height=height, width=width, num_frames=num_frames, seed=seed)
+    rec = {}
+    pt = lambda xy: np.asarray([xy], dtype=np.float32)  # noqa: E731
+    with torch.inference_mode():
+        st = predictor.init_state([vid.frame(t) for t in range(num_frames)])
+        c = vid.centers(0)
+        f, ids, m = predictor.add_new_points_or_box(st, 0, 0, points=pt(c[0]), labels=np.array([1], np.int32))
+        rec["prompt.click.video_res_masks"] = _np(m)
+        f, ids, m = predictor.add_new_points_or_box(st, 0, 1, points=np.asarray([c[1], c[1] + 30.0], dtype=np.float32),
+                                                    labels=np.array([1, 0], np.int32))
+        rec["prompt.posneg.video_res_masks"] = _np(m)
+        f, ids, m = predictor.add_new_points_or_box(st, 0, 2, points=pt(c[2]), labels=np.array([1], np.int32),
+                                                    box=np.asarray(vid.boxes(0)[2], dtype=np.float32))
+        rec["prompt.boxclick.video_res_masks"] = _np(m)
+        rec["prompt.obj_ids"] = np.asarray(list(ids), dtype=np.int64)
+        for f, ids, m in predictor.propagate_in_video(st):
+            _record_frame(rec, "track", st, f, m)
+        predictor.clear_all_prompts_in_frame(st, 0, 1)
+        ids, _ = predictor.remove_object(st, 1)
+        rec["removed.obj_ids"] = np.asarray(list(ids), dtype=np.int64)
+        rec["removed.idx_map"] = np.asarray(sorted(st["obj_id_to_idx"].items()), dtype=np.int64)
+        for f, ids, m in predictor.propagate_in_video(st):
+            _record_frame(rec, "removed", st, f, m)
+            rec[f"removed.f{f}.obj_ids"] = np.asarray(list(ids), dtype=np.int64)
+        predictor.reset_state(st)
+        rec["reset.obj_ids"] = np.asarray(list(st["obj_ids"]), dtype=np.int64)
+        rec["reset.flags"] = np.asarray([int(st["tracking_has_started"]), len(st["output_dict"]["cond_frame_outputs"]),
+                                         len(st["output_dict"]["non_cond_frame_outputs"])], dtype=np.int64)
+        f, ids, m = predictor.add_new_points_or_box(st, 1, 5, points=pt(vid.centers(1)[0]), labels=np.array([1], np.int32))
+        rec["reset.prompt.video_res_masks"] = _np(m)
+        for f, ids, m in predictor.propagate_in_video(st):
+            _record_frame(rec, "reset", st, f, m)
+            rec[f"reset.f{f}.obj_ids"] = np.asarray(list(ids), dtype=np.int64)
+    return rec
+
+
 def run_video_processor(make_vp, num_frames=11, height=160, width=224, seed=11):
     """Det-SAM2's own driver (det_sam2_RT.py VideoProcessor.run) over a frame folder: K = 4 frames per
     chunk, detection every 4 frames, reverse window M = 6, state window S = 6 with image release, a
@@ -215,7 +260,8 @@ def load_golden(name):
     return d, d.pop("__weights_fingerprint")
 
 
-SCENARIOS = {"offline": run_offline, "stream": run_stream, "preload": run_preload, "mask_prompt": run_mask_prompt}
+SCENARIOS = {"offline": run_offline, "stream": run_stream, "preload": run_preload, "mask_prompt": run_mask_prompt,
+             "points_api": run_points_api}
 
 
 def compare(got, ref, rtol_rms, iou_min=None, int_exact=True):

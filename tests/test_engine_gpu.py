@@ -60,7 +60,15 @@ def _kind_errors(got, gold):
     return per_kind
 
 
-@pytest.mark.parametrize("name", ["stream", "preload", "offline", "mask_prompt"])
+# Scenarios whose reference-bf16 calibration is not pooled into the other scenarios' bounds.  points_api: under autocast the reference
+# sends click prompts through a bf16 random-Fourier matmul (prompt_encoder.py:73-95 -> position_encoding.py:131-140) and
+# deviates from its own fp32 run by rel-rms 0.5-0.76 on the prompted frames (tests/golden/ref_bf16_deviation.json) —
+# letting that into the cross-scenario "worst array" bound would loosen every other scenario's test.  The CUDA engine
+# builds the prompt tokens in fp32 and sits at 0.12 on the same arrays (profiles/r1_parity_points_api_vs_reference_golden.txt).
+_OWN_CALIBRATION_ONLY = {"points_api"}
+
+
+@pytest.mark.parametrize("name", ["stream", "preload", "offline", "mask_prompt", "points_api"])
 def test_cuda_engine_matches_reference_golden(name):
     gold, _ = scenarios.load_golden(name)
     calib = _calib()[name]
@@ -73,7 +81,8 @@ def test_cuda_engine_matches_reference_golden(name):
         if np.issubdtype(r.dtype, np.integer):
             assert np.array_equal(got[k], r), k
     errs = _kind_errors(got, gold)
-    allcal = _calib()
+    # "any scenario" for the worst-array bound: the noisy click-prompt calibration counts for its own scenario only
+    allcal = {n: c for n, c in _calib().items() if n == name or n not in _OWN_CALIBRATION_ONLY}
     report, bad = [], []
     for kind, d in errs.items():
         worst, wk = max(d["rel"])
