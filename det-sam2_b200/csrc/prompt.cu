@@ -165,15 +165,23 @@ __device__ __forceinline__ float gelu_erf_p(float x) { return 0.5f * x * (1.0f +
 
 __global__ void __launch_bounds__(128) mask_prompt_embed_kernel(const MaskEmbedParams p) {
   pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
-  const int So = p.S / 16;
+  // wds == nullptr: the input already IS the mask at the prompt encoder's input size (low-resolution logits of a
+  // previous decode fed back as a dense prompt, sam2_base.py:306-329) — no k4 s4 stage, 4 x 4 values per output token
+  const bool direct = (p.wds == nullptr);
+  const int blk = direct ? 4 : 16;
+  const int So = p.S / blk;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(p.B) * So * So) return;
   const int ox = static_cast<int>(i % So), oy = static_cast<int>((i / So) % So), b = static_cast<int>(i / (static_cast<long long>(So) * So));
-  const float* src = p.mask + (static_cast<long long>(b) * p.S + oy * 16) * p.S + ox * 16;
+  const float* src = p.mask + (static_cast<long long>(b) * p.S + oy * blk) * p.S + ox * blk;
   // k4 s4: 4 x 4 values of the 1/4-resolution mask
   float ds[4][4];
   for (int qy = 0; qy < 4; ++qy)
     for (int qx = 0; qx < 4; ++qx) {
+      if (direct) {
+        ds[qy][qx] = src[static_cast<long long>(qy) * p.S + qx];
+        continue;
+      }
       float a = p.bds[0];
       for (int ky = 0; ky < 4; ++ky)
         for (int kx = 0; kx < 4; ++kx) a = fmaf(src[static_cast<long long>(qy * 4 + ky) * p.S + qx * 4 + kx], p.wds[ky * 4 + kx], a);
@@ -268,8 +276,9 @@ extern "C" int ds2_mask_prompt_embed(const float* mask, int32_t B, int32_t S, co
                                      const float* w3, const float* b3, const float* ln3_w, const float* ln3_b,
                                      void* out_bf16, void* stream) {
   using namespace ds2;
-  DS2_REQUIRE(mask && wds && bds && w0 && b0 && ln0_w && ln0_b && w3 && b3 && ln3_w && ln3_b && out_bf16 && B > 0 &&
-                  S >= 16 && (S % 16) == 0,
+  const int blk = wds ? 16 : 4;
+  DS2_REQUIRE(mask && (wds != nullptr) == (bds != nullptr) && w0 && b0 && ln0_w && ln0_b && w3 && b3 && ln3_w && ln3_b &&
+                  out_bf16 && B > 0 && S >= blk && (S % blk) == 0,
               DS2_E_ARG, "ds2_mask_prompt_embed: bad args");
   MaskEmbedParams p;
   p.mask = mask;
@@ -286,7 +295,7 @@ extern "C" int ds2_mask_prompt_embed(const float* mask, int32_t B, int32_t S, co
   p.g3 = ln3_w;
   p.be3 = ln3_b;
   p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-  const long long n = static_cast<long long>(B) * (S / 16) * (S / 16);
+  const long long n = static_cast<long long>(B) * (S / blk) * (S / blk);
   DS2_LAUNCH((mask_prompt_embed_kernel), static_cast<unsigned>((n + 127) / 128), 128, 0, as_stream(stream), p);
   return post_launch("mask_prompt_embed_kernel");
 }

@@ -680,15 +680,26 @@ class CudaEngine:
 
     def sam_heads(self, pix_feat, feats, B, point_coords, point_labels, mask_inputs, multimask_output):
         cfg, p = self.cfg, self.p
-        if mask_inputs is not None:
-            raise NotImplementedError(
-                "dense mask prompts (refinement clicks on an already-segmented frame, add_new_mask) are not "
-                "on the Det-SAM2 streaming path and are not implemented by the CUDA engine yet")
         T = cfg.feat_size * cfg.feat_size
         D = cfg.hidden_dim
         pix = pix_feat.reshape(B * T, D)
         if not pix.is_contiguous():
             pix = pix.contiguous()
+        dense = None
+        if mask_inputs is not None:
+            # refinement click on a frame that already has a mask for this object: the previous low-resolution logits
+            # come back as a DENSE prompt (svp:463-480 -> sam2_base.py:306-329 -> PromptEncoder._embed_masks)
+            S4 = 4 * cfg.feat_size
+            if tuple(mask_inputs.shape) != (B, 1, S4, S4):
+                raise NotImplementedError(
+                    f"dense prompt of shape {tuple(mask_inputs.shape)}: only the prompt encoder's own input size "
+                    f"[B,1,{S4},{S4}] (previous low-resolution logits) is implemented by the CUDA engine")
+            m = mask_inputs.to(device=self.device, dtype=F32).contiguous().view(B, S4, S4)
+            f16 = self._buf("mp_f16", (B * T, 16), BF16)
+            ops.mask_prompt_embed(m, None, None, p["mp.w0"], p["mp.b0"], p["mp.ln0.w"], p["mp.ln0.b"],
+                                  p["mp.w3"], p["mp.b3"], p["mp.ln3.w"], p["mp.ln3.b"], f16)
+            dense = self._buf("mp_dense", (B * T, D), F32)
+            ops.gemm(f16, p["mp.w6"], bias=p["mp.b6"], out_f32=dense)
         if point_coords is not None:
             P = point_coords.shape[1]
             coords = point_coords.to(dtype=F32)
@@ -700,6 +711,12 @@ class CudaEngine:
             P = 1
             coords, labels = self._noprompt(B)
         mm = bool(multimask_output)
+        if dense is not None:
+            # rare interactive path: launched eagerly (the dense embedding lives in a workspace, not a graph input)
+            low, iou_out, obj_ptr, score = (t.clone() for t in self._sam_heads_body(
+                {"coords": coords.to(self.device), "labels": labels.to(self.device), "s0": feats.feat_s0, "s1": feats.feat_s1},
+                pix, B, P, mm, dense=dense))
+            return {"pred_masks": low, "ious": iou_out, "obj_ptr": obj_ptr, "object_score_logits": score}
         body = lambda inp: self._sam_heads_body(inp, pix, B, P, mm)  # noqa: E731
         low, iou_out, obj_ptr, score = self.graphs.run(
             ("sam", B, P, mm, pix.data_ptr()),

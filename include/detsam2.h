@@ -264,7 +264,10 @@ int ds2_downsample4_aa(const float* x, float* y, int32_t B, int32_t S, float sca
 /* mask_downsample (Conv2d 1->1 k4 s4, sam2_base.py:185-187,419) + PromptEncoder.mask_downscaling without its final
  * 1x1 conv (prompt_encoder.py:52-60: Conv 1->4 k2 s2, LayerNorm2d, GELU, Conv 4->16 k2 s2, LayerNorm2d, GELU):
  * mask [B, S, S] f32 -> bf16 [B * (S/16)^2, 16] token-major features; the 16 -> 256 conv is a ds2_gemm.
- * w0 [4][1][2][2], w3 [16][4][2][2] in Conv2d layout.                                                           */
+ * w0 [4][1][2][2], w3 [16][4][2][2] in Conv2d layout.
+ * wds == bds == NULL: `mask` is already at the prompt encoder's input size ([B, S, S] with S = 4 x the embedding
+ * side: the low-resolution logits of a previous decode fed back as a dense prompt by a refinement click,
+ * sam2_base.py:306-329, svp:463-480); only mask_downscaling runs and the output has B * (S/4)^2 rows.            */
 int ds2_mask_prompt_embed(const float* mask, int32_t B, int32_t S, const float* wds, const float* bds,
                           const float* w0, const float* b0, const float* ln0_w, const float* ln0_b,
                           const float* w3, const float* b3, const float* ln3_w, const float* ln3_b,

@@ -50,7 +50,7 @@ def deviations(got, ref):
 def main():
     torch.set_num_threads(os.cpu_count() or 1)
     path = os.path.join(ROOT, "tests", "golden", "ref_bf16_deviation.json")
-    names = sys.argv[1:] or ["stream", "preload", "offline", "mask_prompt", "points_api"]
+    names = sys.argv[1:] or ["stream", "preload", "offline", "mask_prompt", "points_api", "refine_click"]
     res = {}
     if sys.argv[1:] and os.path.exists(path):     # re-calibrating some scenarios keeps the others
         with open(path) as f:

@@ -16,6 +16,7 @@ Scenarios
   mask_prompt  add_new_mask with a disc, a box on the same frame and an empty mask, then tracking (svp:527-600).
   points_api  click prompts (one click / positive + negative / box + click), clear_all_prompts_in_frame,
             remove_object, reset_state and a new object id afterwards (svp:344-520, 1061-1170, 1438-1553).
+  refine_click  three accumulating clicks on one frame: the previous logits return as a dense prompt (svp:463-480).
   preload   preload memory bank (det_sam2_RT.py:489-503, svp:123-156): every frame of a short clip is
             a conditioning frame, state is pickled, re-loaded, init_preloading_state, new frames
             appended with update_state and tracked against the bank.
@@ -205,6 +206,34 @@ def run_points_api(predictor, num_frames=4, height=192, width=256, seed=23):
     return rec
 
 
+def run_refine_click(predictor, num_frames=3, height=192, width=256, seed=29):
+    """Interactive refinement on a prompted frame (svp:463-480): a second and a third click on the SAME frame with
+    clear_old_points=False — the previous low-resolution logits of that frame, clamped to [-32, 32], come back as a dense
+    prompt through PromptEncoder.mask_downscaling (sam2_base.py:306-329) and the clicks accumulate; then tracking."""
+    vid = BilliardVideo(num_objects=2, height=height, width=width, num_frames=num_frames, seed=seed)
+    rec = {}
+    with torch.inference_mode():
+        st = predictor.init_state([vid.frame(t) for t in range(num_frames)])
+        c = vid.centers(0)
+        f, ids, m = predictor.add_new_points_or_box(st, 0, 0, points=np.asarray([c[0]], dtype=np.float32),
+                                                    labels=np.array([1], np.int32))
+        rec["click1.video_res_masks"] = _np(m)
+        f, ids, m = predictor.add_new_points_or_box(st, 0, 0, points=np.asarray([c[0] + 4.0], dtype=np.float32),
+                                                    labels=np.array([1], np.int32), clear_old_points=False)
+        rec["click2.video_res_masks"] = _np(m)
+        f, ids, m = predictor.add_new_points_or_box(st, 0, 0, points=np.asarray([c[0] + 40.0], dtype=np.float32),
+                                                    labels=np.array([0], np.int32), clear_old_points=False)
+        rec["click3.video_res_masks"] = _np(m)
+        pts = st["point_inputs_per_obj"][0][0]
+        rec["clicks.point_labels"] = pts["point_labels"].detach().cpu().numpy().astype(np.int64)
+        f, ids, m = predictor.add_new_points_or_box(st, 0, 1, box=np.asarray(vid.boxes(0)[1], dtype=np.float32))
+        rec["box.video_res_masks"] = _np(m)
+        for f, ids, m in predictor.propagate_in_video(st):
+            _record_frame(rec, "track", st, f, m)
+        rec["obj_ids"] = np.asarray(list(st["obj_ids"]), dtype=np.int64)
+    return rec
+
+
 def run_video_processor(make_vp, num_frames=11, height=160, width=224, seed=11):
     """Det-SAM2's own driver (det_sam2_RT.py VideoProcessor.run) over a frame folder: K = 4 frames per
     chunk, detection every 4 frames, reverse window M = 6, state window S = 6 with image release, a
@@ -261,7 +290,7 @@ def load_golden(name):
 
 
 SCENARIOS = {"offline": run_offline, "stream": run_stream, "preload": run_preload, "mask_prompt": run_mask_prompt,
-             "points_api": run_points_api}
+             "points_api": run_points_api, "refine_click": run_refine_click}
 
 
 def compare(got, ref, rtol_rms, iou_min=None, int_exact=True):

@@ -68,7 +68,7 @@ def _kind_errors(got, gold):
 _OWN_CALIBRATION_ONLY = {"points_api"}
 
 
-@pytest.mark.parametrize("name", ["stream", "preload", "offline", "mask_prompt", "points_api"])
+@pytest.mark.parametrize("name", ["stream", "preload", "offline", "mask_prompt", "points_api", "refine_click"])
 def test_cuda_engine_matches_reference_golden(name):
     gold, _ = scenarios.load_golden(name)
     calib = _calib()[name]

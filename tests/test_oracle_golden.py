@@ -27,7 +27,7 @@ def oracle_predictor(name):
     return SAM2VideoPredictor(O.OracleEngine(cfg, sd, fill_holes=False), fill_hole_area=0), sd
 
 
-@pytest.mark.parametrize("name", ["stream", "preload", "offline", "mask_prompt", "points_api"])
+@pytest.mark.parametrize("name", ["stream", "preload", "offline", "mask_prompt", "points_api", "refine_click"])
 def test_oracle_matches_reference_golden(name):
     torch.set_num_threads(min(8, os.cpu_count() or 1))
     gold, fp = scenarios.load_golden(name)
