@@ -14,6 +14,15 @@ from .predictor import SAM2VideoPredictor
 from .weights import param_shapes, synthetic_state_dict
 
 
+# build_sam.py:33-66, the SAM 2.1 entries (the SAM 2.0 configurations are not restated in detsam2_b200.config)
+HF_MODEL_ID_TO_FILENAMES = {
+    "facebook/sam2.1-hiera-tiny": ("configs/sam2.1/sam2.1_hiera_t.yaml", "sam2.1_hiera_tiny.pt"),
+    "facebook/sam2.1-hiera-small": ("configs/sam2.1/sam2.1_hiera_s.yaml", "sam2.1_hiera_small.pt"),
+    "facebook/sam2.1-hiera-base-plus": ("configs/sam2.1/sam2.1_hiera_b+.yaml", "sam2.1_hiera_base_plus.pt"),
+    "facebook/sam2.1-hiera-large": ("configs/sam2.1/sam2.1_hiera_l.yaml", "sam2.1_hiera_large.pt"),
+}
+
+
 def load_state_dict(cfg, ckpt_path=None, seed=0):
     if ckpt_path is None:
         return synthetic_state_dict(cfg, seed)
@@ -49,3 +58,18 @@ def build_sam2_video_predictor(config_file, ckpt_path=None, device="cuda", mode=
         engine = CudaEngine(cfg, sd, device=device)
     fill = cfg.fill_hole_area if apply_postprocessing else 0
     return SAM2VideoPredictor(engine, fill_hole_area=fill, non_overlap_masks=cfg.non_overlap_masks, **kwargs)
+
+
+def _hf_download(model_id):
+    """build_sam.py:148-153."""
+    if model_id not in HF_MODEL_ID_TO_FILENAMES:
+        raise KeyError(f"unknown model id {model_id!r}; supported: {sorted(HF_MODEL_ID_TO_FILENAMES)}")
+    from huggingface_hub import hf_hub_download
+    config_name, checkpoint_name = HF_MODEL_ID_TO_FILENAMES[model_id]
+    return config_name, hf_hub_download(repo_id=model_id, filename=checkpoint_name)
+
+
+def build_sam2_video_predictor_hf(model_id, **kwargs):
+    """build_sam.py:159-163: checkpoint from the Hugging Face hub (or its local cache), then the factory above."""
+    config_name, ckpt_path = _hf_download(model_id)
+    return build_sam2_video_predictor(config_file=config_name, ckpt_path=ckpt_path, **kwargs)

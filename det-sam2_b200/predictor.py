@@ -69,6 +69,12 @@ class SAM2VideoPredictor:
         self._prefetched = {}      # frame_idx -> features encoded ahead of their step (same propagate call only)
         self.verbose = verbose
 
+    @classmethod
+    def from_pretrained(cls, model_id, **kwargs):
+        """svp:208-222: build from a Hugging Face model id (``facebook/sam2.1-hiera-{tiny,small,base-plus,large}``)."""
+        from .build_sam import build_sam2_video_predictor_hf
+        return build_sam2_video_predictor_hf(model_id, **kwargs)
+
     # ---- attributes callers read on the reference model ------------------------------------------
     @property
     def device(self):

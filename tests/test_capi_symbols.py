@@ -68,3 +68,25 @@ def test_product_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+def test_from_pretrained_maps_hub_ids_like_the_reference(monkeypatch):
+    """svp:208-222 / build_sam.py:148-163: model id -> (config, checkpoint file) -> factory; unknown ids are refused."""
+    import pytest
+    from detsam2_b200 import build_sam
+    from detsam2_b200.predictor import SAM2VideoPredictor
+    seen = {}
+
+    def fake_factory(config_file, ckpt_path=None, **kw):
+        seen.update(config_file=config_file, ckpt_path=ckpt_path, kw=kw)
+        return "predictor"
+
+    import huggingface_hub
+    monkeypatch.setattr(huggingface_hub, "hf_hub_download", lambda repo_id, filename: f"/cache/{repo_id}/{filename}")
+    monkeypatch.setattr(build_sam, "build_sam2_video_predictor", fake_factory)
+    assert SAM2VideoPredictor.from_pretrained("facebook/sam2.1-hiera-large", device="cuda") == "predictor"
+    assert seen["config_file"] == "configs/sam2.1/sam2.1_hiera_l.yaml"
+    assert seen["ckpt_path"] == "/cache/facebook/sam2.1-hiera-large/sam2.1_hiera_large.pt"
+    assert seen["kw"] == {"device": "cuda"}
+    with pytest.raises(KeyError):
+        SAM2VideoPredictor.from_pretrained("facebook/sam2-hiera-large")
