@@ -293,7 +293,9 @@ def _cpu_frame_time(args, sample_objects, steps, warmup, budget_s):
     Bs = sample_objects
     nfr = 2 + warmup + steps
     vid = BilliardVideo(num_objects=Bs, height=S, width=S, num_frames=nfr, seed=0)
-    pred = SAM2VideoPredictor(eng, fill_hole_area=8)
+    # frame-at-a-time encoder, as the reference runs it (the encode-ahead of the CUDA arm would put several frames'
+    # encoder time into one step of this per-step accounting)
+    pred = SAM2VideoPredictor(eng, fill_hole_area=8, encoder_batch_frames=1)
     enc_times, rest_times = [], []
     orig_encode = eng.encode_image
 
