@@ -3,7 +3,7 @@
 (/root/reference/sam2/modeling/sam2_base.py:25-98) plus the eval-time overrides applied by
 build_sam2_video_predictor (/root/reference/sam2/build_sam.py:121-141).
 """
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Tuple
 
 

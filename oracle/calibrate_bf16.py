@@ -9,7 +9,6 @@ itself does when run the way Det-SAM2 runs it (torch.autocast bf16, det_sam2_RT.
 """
 import json
 import os
-import re
 import sys
 
 import numpy as np

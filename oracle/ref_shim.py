@@ -128,7 +128,6 @@ def reference_video_processor_class(predictor, detector):
     ultralytics result interface the reference reads (det_sam2_RT.py:230-245)."""
     install()
     import numpy as np
-    import torch
 
     def stub(name, **attrs):
         m = types.ModuleType(name)

@@ -1,7 +1,6 @@
 """the compact preload-bank format (detsam2_b200/bank_format.py) is lossless w.r.t. the reference's
 pickle (det_sam2_RT.py:489-503), restores the aliasing between batched and per-object outputs, is several times smaller,
 and a stream continued from it gives the same result."""
-import io
 import os
 import pickle
 
