@@ -16,6 +16,7 @@
 // The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of
 // tile i+1.  BN is chosen per problem to minimise waves x tile width.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.h"
@@ -571,6 +572,16 @@ extern "C" int ds2_gemm(const ds2_gemm_args* a, void* stream) {
 
   // bf16 stores go out in 64-column boxes, so tiles must not end inside one
   p.BN = choose_bn(a->M, a->N, sms, p.store_mode == kStoreTmaBf16 ? 64 : 32);
+  {
+    // tuning aid: DS2_GEMM_BN=<n> forces the tile width of every multi-tile problem (N > 256) for A/B sweeps of the
+    // cost model in choose_bn; ignored unless n is a legal width for the store path
+    static const int force_bn = [] {
+      const char* e = getenv("DS2_GEMM_BN");
+      return e ? atoi(e) : 0;
+    }();
+    const int step = p.store_mode == kStoreTmaBf16 ? 64 : 32;
+    if (force_bn >= 64 && force_bn <= 256 && (force_bn % step) == 0 && a->N > 256) p.BN = force_bn;
+  }
   p.tiles_m = (a->M + kBM - 1) / kBM;
   p.tiles_n = (a->N + p.BN - 1) / p.BN;
   CUtensorMap ta, tw, tcm;
