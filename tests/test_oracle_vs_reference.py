@@ -47,3 +47,17 @@ def test_error_behaviour_matches_reference():
             next(iter(p.propagate_in_video(st)))                                             # no prompts yet
         with pytest.raises(AssertionError):
             p.update_state([np.zeros((64, 64, 3), np.uint8)], st)                            # size mismatch
+
+
+def test_non_overlapping_constraints_match_reference():
+    """sam2_base.py:934-952 (off by default; `non_overlap_masks=True` sessions): same tensor, value for value."""
+    ref_shim.install()
+    from sam2.modeling.sam2_base import SAM2Base
+    torch.manual_seed(0)
+    m = torch.randn(5, 1, 17, 23) * 8
+    m[:, :, :4] = m[0:1, :, :4]            # ties: argmax must pick the same (first) object on both sides
+    ref = SAM2Base._apply_non_overlapping_constraints(None, m.clone())
+    got = SAM2VideoPredictor._apply_non_overlapping_constraints(None, m.clone())
+    assert torch.equal(ref, got)
+    one = torch.randn(1, 1, 4, 4)
+    assert torch.equal(SAM2VideoPredictor._apply_non_overlapping_constraints(None, one), one)
