@@ -163,7 +163,10 @@ def _ingest_on_device(arrays, image_size, lut, device, keep_on_device, pin):
             return dst
         # always pinned: a pageable destination would turn the copy into a synchronous bounce through the driver's
         # staging buffer (torch's host allocator re-uses the block once the previous chunk's tensor is gone)
-        images = torch.empty(n, 3, image_size, image_size, dtype=torch.float16, pin_memory=True)
+        try:
+            images = torch.empty(n, 3, image_size, image_size, dtype=torch.float16, pin_memory=True)
+        except RuntimeError:   # host cannot lock that much memory: a pageable destination is only slower
+            images = torch.empty(n, 3, image_size, image_size, dtype=torch.float16)
         images.copy_(dst, non_blocking=True)
         stream.synchronize()
     return images
