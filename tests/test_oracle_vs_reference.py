@@ -61,3 +61,25 @@ def test_non_overlapping_constraints_match_reference():
     assert torch.equal(ref, got)
     one = torch.randn(1, 1, 4, 4)
     assert torch.equal(SAM2VideoPredictor._apply_non_overlapping_constraints(None, one), one)
+
+
+def test_select_closest_cond_frames_matches_reference_on_random_inputs():
+    """sam2_utils.py:19-66 incl. Det-SAM2's forced preload frames: same keys, same ORDER (the order is the memory row
+    order), for 400 random configurations."""
+    import random
+    ref_shim.install()
+    from sam2.modeling.sam2_utils import select_closest_cond_frames as ref_select
+    from detsam2_b200.memory_bank import select_closest_cond_frames as our_select
+    rnd = random.Random(7)
+    for _ in range(400):
+        n = rnd.randint(1, 40)
+        keys = rnd.sample(range(0, 120), n)
+        if rnd.random() < 0.5:
+            keys.sort()
+        cond = {t: ("out", t) for t in keys}
+        frame_idx = rnd.randint(0, 130)
+        cap = rnd.choice([-1, 2, 3, 5, 20])
+        preload = None if rnd.random() < 0.5 else rnd.sample(keys, rnd.randint(0, min(6, n)))
+        rs, ru = ref_select(frame_idx, dict(cond), cap, preload)
+        gs, gu = our_select(frame_idx, dict(cond), cap, preload)
+        assert list(rs.items()) == list(gs.items()) and list(ru.items()) == list(gu.items()), (keys, frame_idx, cap, preload)
