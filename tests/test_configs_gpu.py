@@ -34,7 +34,43 @@ def _engine(name):
     return cfg, sd, CudaEngine(cfg, sd, device="cuda:0")
 
 
-@pytest.mark.parametrize("name,hw,seed", [("small", (512, 640), 3), ("base_plus", (720, 1280), 2)])
+FAMILY_CASES = [("small", (512, 640), 3), ("base_plus", (720, 1280), 2)]
+
+
+def run_family_case(engine, cfg, hw, seed):
+    """Drive one engine (CUDA or oracle) through the family scenario: 2 objects, boxes on frame 0, two tracked
+    frames.  Shared with tests/test_family_decisions.py, which runs the ORACLE half on CPU in the build
+    container so a change of the oracle's decision log is caught before the GPU suite sees it."""
+    from detsam2_b200.predictor import SAM2VideoPredictor
+    from detsam2_b200.synthetic import BilliardVideo
+    vid = BilliardVideo(num_objects=2, height=hw[0], width=hw[1], num_frames=3, seed=seed)
+    frames = list(vid.frames())
+    with torch.inference_mode():
+        pred = SAM2VideoPredictor(engine, fill_hole_area=8)
+        st = pred.init_state(frames)
+        for oid, box in vid.boxes(0).items():
+            pred.add_new_points_or_box(st, 0, oid, box=box)
+        masks = {f: m.float().cpu() for f, _, m in pred.propagate_in_video(st)}
+    return masks, st
+
+
+def check_family_decisions(decisions, cfg):
+    """The oracle logs one entry per prompted decode ("stability" kind: single-mask output with the stability
+    fallback) and one per tracked frame ("multimask_top2_margin" kind: argmax over three predicted IoUs).
+    Both kinds are discrete choices a bf16 implementation may legitimately flip when they are near ties; the
+    seeds of FAMILY_CASES are chosen so that they are not."""
+    prompted = [d for d in decisions if "stability" in d]
+    tracked = [d for d in decisions if "multimask_top2_margin" in d]
+    assert len(prompted) == 2 and len(tracked) == 2, decisions
+    assert len(prompted) + len(tracked) == len(decisions), decisions
+    for d in prompted:
+        assert abs(d["stability"][0] - cfg.dynamic_multimask_stability_thresh) > 0.01, d
+        assert d["stable"][0] or d["iou_top2_margin"][0] > 0.03, d
+    for d in tracked:
+        assert len(d["multimask_top2_margin"]) == 2 and min(d["multimask_top2_margin"]) > 0.004, d
+
+
+@pytest.mark.parametrize("name,hw,seed", FAMILY_CASES)
 def test_model_family_tracked_frames_match_oracle(name, hw, seed):
     """2 objects, boxes on frame 0, two tracked frames; every stored output vs the fp32 oracle.  Tolerances
     are those of the large-model test (bf16 operands / fp32 accumulation against an fp32 reference).
@@ -44,28 +80,17 @@ def test_model_family_tracked_frames_match_oracle(name, hw, seed):
     near ties (base_plus, seed 3: top-2 IoU margin 0.008) and a bf16 implementation then legitimately picks
     the other mask, after which nothing is comparable.  The seeds are chosen so that the fp32 oracle's own
     margins are wide, and the test asserts that they are."""
-    from detsam2_b200.predictor import SAM2VideoPredictor
-    from detsam2_b200.synthetic import BilliardVideo
     from oracle import sam2_oracle as O
     cfg, sd, eng = _engine(name)
     torch.set_num_threads(os.cpu_count() or 1)
-    vid = BilliardVideo(num_objects=2, height=hw[0], width=hw[1], num_frames=3, seed=seed)
-    frames = list(vid.frames())
     outs = {}
+    outs["cuda"] = run_family_case(eng, cfg, hw, seed)
     O.DECISION_LOG = []
-    with torch.inference_mode():
-        for tag, e in (("cuda", eng), ("oracle", O.OracleEngine(cfg, sd, fill_holes=True))):
-            pred = SAM2VideoPredictor(e, fill_hole_area=8)
-            st = pred.init_state(frames)
-            for oid, box in vid.boxes(0).items():
-                pred.add_new_points_or_box(st, 0, oid, box=box)
-            masks = {f: m.float().cpu() for f, _, m in pred.propagate_in_video(st)}
-            outs[tag] = (masks, st)
-    decisions, O.DECISION_LOG = O.DECISION_LOG, None
-    assert len(decisions) == 2
-    for d in decisions:
-        assert abs(d["stability"][0] - cfg.dynamic_multimask_stability_thresh) > 0.01, d
-        assert d["stable"][0] or d["iou_top2_margin"][0] > 0.03, d
+    try:
+        outs["oracle"] = run_family_case(O.OracleEngine(cfg, sd, fill_holes=True), cfg, hw, seed)
+    finally:
+        decisions, O.DECISION_LOG = O.DECISION_LOG, None
+    check_family_decisions(decisions, cfg)
     for f in (1, 2):
         oc = outs["cuda"][1]["output_dict"]["non_cond_frame_outputs"][f]
         oo = outs["oracle"][1]["output_dict"]["non_cond_frame_outputs"][f]
