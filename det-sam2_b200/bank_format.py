@@ -38,11 +38,27 @@ def _storage_key(t):
     return (t.device.type, t.device.index, t.untyped_storage().data_ptr())
 
 
+def _is_expanded(t):
+    return t.dim() > 0 and t.shape[0] > 1 and t.stride(0) == 0
+
+
+def _layout_perm(t):
+    """Dim order of decreasing stride, or None when t is already laid out that way.  Writing ``t.permute(perm)`` keeps
+    the tensor's MEMORY order on disk (the CUDA engine stores ``maskmem_features`` token-major and exposes them as an
+    NCHW view, engine.encode_memory); load_bank applies the inverse permutation, so a loaded bank has the strides it
+    was saved with and the engine reads it without a transposing copy."""
+    if t.dim() < 2:
+        return None
+    perm = sorted(range(t.dim()), key=lambda d: (-t.stride(d), d))
+    return None if perm == list(range(t.dim())) else perm
+
+
 class _Writer:
     def __init__(self):
         self.arrays = OrderedDict()      # name -> np.ndarray
         self.by_storage = {}             # storage key -> list of (tensor, array name)
         self.tensors = []                # every tensor met, in walk order
+        self.perms = {}                  # array name -> dim permutation it was written in (memory order)
 
     def collect(self, obj):
         if isinstance(obj, torch.Tensor):
@@ -55,33 +71,51 @@ class _Writer:
                 self.collect(v)
 
     def plan(self):
-        """Largest tensor of every storage first: smaller tensors of the same storage become slices of it."""
+        """Largest tensor of every storage first: smaller tensors of the same storage become slices of it.  A tensor
+        whose leading stride is 0 (``x.expand(B, ...)``: every stored frame's ``maskmem_pos_enc`` is such a view of the
+        one copy in ``constants``, svp:1406-1435) is written as its single row and re-expanded on load."""
         groups = {}
         for t in self.tensors:
             if t.numel() > 0:
                 groups.setdefault(_storage_key(t), []).append(t)
         self.bases = {}                  # storage key -> list of (base tensor, name)
         for key, ts in groups.items():
-            ts = sorted(ts, key=lambda t: -t.numel())
+            ts = sorted(ts, key=lambda t: -(t[0:1].numel() if _is_expanded(t) else t.numel()))
             self.bases[key] = []
             for t in ts:
-                if self._as_slice(t) is None and not any(b is t for b, _ in self.bases[key]):
+                if self._as_slice(t) is None:
+                    b = t[0:1] if _is_expanded(t) else t
                     name = f"t{len(self.arrays)}"
-                    self.arrays[name] = self._to_numpy(t)
-                    self.bases[key].append((t, name))
+                    perm = _layout_perm(b)
+                    self.arrays[name] = self._to_numpy(b if perm is None else b.permute(perm))
+                    if perm is not None:
+                        self.perms[name] = perm
+                    self.bases[key].append((b, name))
 
     def _as_slice(self, t):
-        """(base name, start, length) if t == base[start:start+length] along dim 0 with the base's strides."""
+        """(base name, start, length, expand) if t == base[start:start+length] along dim 0 (same per-row strides);
+        expand = B > 0 when t is that single row broadcast B times (leading stride 0)."""
+        exp = _is_expanded(t)
         for b, name in self.bases.get(_storage_key(t), []):
             if b is t:
-                return (name, 0, b.shape[0]) if b.dim() > 0 else (name, -1, 0)
-            if b.dim() == 0 or t.dim() != b.dim() or t.dtype != b.dtype or t.shape[1:] != b.shape[1:] or t.stride() != b.stride():
+                return (name, 0, b.shape[0], 0) if b.dim() > 0 else (name, -1, 0, 0)
+            if b.dim() == 0 or t.dim() != b.dim() or t.dtype != b.dtype or t.shape[1:] != b.shape[1:]:
+                continue
+            if t.stride()[1:] != b.stride()[1:]:
+                continue
+            one_row = exp or t.shape[0] == 1     # the leading stride of a single row carries no information
+            if not one_row and t.stride(0) != b.stride(0):
                 continue
             off = t.storage_offset() - b.storage_offset()
+            if b.shape[0] == 1:
+                if off == 0 and one_row:
+                    return (name, 0, 1, t.shape[0] if exp else 0)
+                continue
             if b.stride(0) > 0 and off >= 0 and off % b.stride(0) == 0:
                 start = off // b.stride(0)
-                if start + t.shape[0] <= b.shape[0]:
-                    return (name, start, t.shape[0])
+                n = 1 if exp else t.shape[0]
+                if start + n <= b.shape[0]:
+                    return (name, start, n, t.shape[0] if exp else 0)
         return None
 
     @staticmethod
@@ -101,7 +135,9 @@ class _Writer:
             ref = self._as_slice(obj)
             if ref is None:
                 raise BankFormatError("internal error: tensor without a base")  # plan() covers every tensor
-            meta["base"], meta["start"], meta["len"] = ref
+            meta["base"], meta["start"], meta["len"], expand = ref
+            if expand:
+                meta["expand"] = expand
             return meta
         if isinstance(obj, torch.device):
             return {"__t": "device", "type": obj.type}
@@ -131,7 +167,7 @@ def save_bank(inference_state, path):
     w = _Writer()
     w.collect(st)
     w.plan()
-    meta = {"magic": MAGIC, "state": w.encode(st)}
+    meta = {"magic": MAGIC, "state": w.encode(st), "perms": w.perms}
     with zipfile.ZipFile(path, "w", compression=zipfile.ZIP_DEFLATED, compresslevel=4) as z:
         z.writestr("meta.json", json.dumps(meta))
         for name, arr in w.arrays.items():
@@ -152,6 +188,7 @@ def load_bank(path, map_location=None):
         if meta.get("magic") != MAGIC:
             raise BankFormatError(f"{path}: unknown bank format {meta.get('magic')!r}, this build reads {MAGIC!r}")
         cache = {}
+        perms = meta.get("perms", {})
 
         def base(name, dtype, device):
             key = (name, device)
@@ -160,7 +197,13 @@ def load_bank(path, map_location=None):
                 t = torch.from_numpy(arr)
                 if dtype == torch.bfloat16:
                     t = t.view(torch.bfloat16)
-                cache[key] = t.to(device)
+                t = t.to(device)
+                if name in perms:       # written in memory order: undo the permutation (a view, strides restored)
+                    inv = [0] * len(perms[name])
+                    for i, d in enumerate(perms[name]):
+                        inv[d] = i
+                    t = t.permute(inv)
+                cache[key] = t
             return cache[key]
 
         def device_of(kind):
@@ -179,7 +222,12 @@ def load_bank(path, map_location=None):
                 if "base" not in o:
                     return torch.empty(o["shape"], dtype=dtype, device=dev)
                 b = base(o["base"], dtype, dev)
-                return b if o["start"] < 0 else b[o["start"]:o["start"] + o["len"]]
+                if o["start"] < 0:
+                    return b
+                t = b[o["start"]:o["start"] + o["len"]]
+                if o.get("expand"):
+                    t = t.expand(o["expand"], *t.shape[1:])
+                return t
             if k == "device":
                 return device_of(o["type"])
             if k == "odict":

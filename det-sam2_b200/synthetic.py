@@ -94,9 +94,12 @@ class GroundTruthDetector:
     ``VideoProcessor``: called with the frames that fall on the ``detect_interval`` grid, in stream order, and
     returns one detection list per frame (class = object id, as Det-SAM2 uses the class as obj_id)."""
 
-    def __init__(self, video, detect_interval, first_frame=0, appear_at=None):
+    def __init__(self, video, detect_interval, first_frame=0, appear_at=None, repeat_class=None):
         self.video, self.interval, self.next_idx = video, detect_interval, first_frame
         self.appear_at = appear_at or {}  # obj_id -> first frame at which the detector reports it
+        # obj_id -> (dx, dy): the detector reports a SECOND box of that class, shifted, after all first boxes (YOLO does
+        # emit several instances of one class; Det-SAM2 then prompts the same obj_id twice on one frame)
+        self.repeat_class = repeat_class or {}
 
     def __call__(self, frames_bgr):
         out = []
@@ -105,6 +108,11 @@ class GroundTruthDetector:
             dets = [{"coordinates": np.asarray(b, np.float32), "class": np.asarray([float(oid)], np.float32),
                      "confidence": np.asarray([0.99], np.float32)}
                     for oid, b in self.video.boxes(t).items() if t >= self.appear_at.get(oid, 0)]
+            for oid, (dx, dy) in self.repeat_class.items():
+                if oid in self.video.boxes(t) and t >= self.appear_at.get(oid, 0):
+                    b = np.asarray(self.video.boxes(t)[oid], np.float32) + np.asarray([dx, dy, dx, dy], np.float32)
+                    dets.append({"coordinates": b, "class": np.asarray([float(oid)], np.float32),
+                                 "confidence": np.asarray([0.95], np.float32)})
             out.append(dets)
             self.next_idx += self.interval
         return out

@@ -140,23 +140,32 @@ class VideoProcessor:
             return self.inference_state
         for key, detections in detection_results_json.items():
             ann_frame_idx = int(key.replace("frame_", ""))
-            boxes = {}
+            boxes, repeats = {}, []
             for det in detections:
                 obj_class = int(np.asarray(det["class"]).reshape(-1)[0])
                 if obj_class in self.skip_classes:
                     continue
-                # a later detection of the same class replaces the earlier one, as the reference's sequential
-                # add_new_points_or_box(..., clear_old_points=True) calls do; first occurrence fixes the id order
-                boxes[obj_class] = np.array(det["coordinates"], dtype=np.float32)
+                box = np.array(det["coordinates"], dtype=np.float32)
+                if obj_class in boxes:
+                    # a second box of the same class on one frame is NOT a replacement in the reference: its
+                    # add_new_points_or_box finds the first call's temporary output and feeds those (clamped) mask
+                    # logits back as a dense prompt (det_sam2_RT.py:288-302 -> svp:470-482), so the repeats are
+                    # replayed one by one, in detection order, after the first occurrences
+                    repeats.append((obj_class, box))
+                else:
+                    boxes[obj_class] = box
             if not boxes:
                 continue
             if hasattr(self.predictor, "add_new_boxes"):
-                # all boxes of the frame in one B-wide decoder call
+                # all first-occurrence boxes of the frame in one B-wide decoder call
                 self.predictor.add_new_boxes(self.inference_state, ann_frame_idx, boxes)
             else:
                 for obj_class, box in boxes.items():
                     self.predictor.add_new_points_or_box(inference_state=self.inference_state, frame_idx=ann_frame_idx,
                                                          obj_id=obj_class, box=box)
+            for obj_class, box in repeats:
+                self.predictor.add_new_points_or_box(inference_state=self.inference_state, frame_idx=ann_frame_idx,
+                                                     obj_id=obj_class, box=box)
         return self.inference_state
 
     # ---- one chunk (det_sam2_RT.py:342-411) --------------------------------------------------------
@@ -289,8 +298,13 @@ class VideoProcessor:
             from .bank_format import save_bank
             save_bank(self.inference_state, save_path)
             return
+        # the pickle must stay loadable by Det-SAM2 itself: `cached_features` holds engine handles (FrameFeats: a class
+        # the reference cannot import, ~18 MB of transient backbone features per cached frame) where the reference
+        # expects (image, backbone_out) tuples — both sides recompute features on demand, so write it empty
+        st = dict(self.inference_state)
+        st["cached_features"] = {}
         with open(save_path, "wb") as f:
-            pickle.dump(self.inference_state, f)
+            pickle.dump(st, f)
 
     def load_inference_state(self, load_path):
         if str(load_path).endswith(".ds2bank"):

@@ -31,6 +31,8 @@ from detsam2_b200.weights import synthetic_state_dict  # noqa: E402
 from oracle import ref_shim, scenarios  # noqa: E402
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+# VideoProcessor.run scenarios: fixture name -> keyword arguments of scenarios.run_video_processor
+VP_SCENARIOS = scenarios.VP_SCENARIOS
 
 
 def fingerprint(sd):
@@ -45,11 +47,11 @@ def generate(name):
     torch.set_num_threads(os.cpu_count() or 1)
     ref = ref_shim.build_reference_predictor(cfg, sd, device="cpu")
     t0 = time.time()
-    if name == "video_processor":
+    if name in VP_SCENARIOS:
         def make_vp(detector, **kw):
             cls = ref_shim.reference_video_processor_class(ref, detector)
             return cls(sam2_checkpoint=None, model_cfg=None, detect_model_weights=None, **kw)
-        rec = scenarios.run_video_processor(make_vp)
+        rec = scenarios.run_video_processor(make_vp, **VP_SCENARIOS[name])
     else:
         rec = scenarios.SCENARIOS[name](ref)
     dt = time.time() - t0
@@ -67,6 +69,6 @@ def generate(name):
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(scenarios.SCENARIOS) + ["video_processor"]
+    names = sys.argv[1:] or list(scenarios.SCENARIOS) + list(VP_SCENARIOS)
     for n in names:
         generate(n)

@@ -234,18 +234,21 @@ def run_refine_click(predictor, num_frames=3, height=192, width=256, seed=29):
     return rec
 
 
-def run_video_processor(make_vp, num_frames=11, height=160, width=224, seed=11):
+def run_video_processor(make_vp, num_frames=11, height=160, width=224, seed=11, repeat_class=None):
     """Det-SAM2's own driver (det_sam2_RT.py VideoProcessor.run) over a frame folder: K = 4 frames per
     chunk, detection every 4 frames, reverse window M = 6, state window S = 6 with image release, a
     third object that the detector only reports from frame 4 on (online new id), and a 3-frame tail.
-    `make_vp(detector, **ctor_kwargs)` builds the reference's or this repo's VideoProcessor."""
+    `make_vp(detector, **ctor_kwargs)` builds the reference's or this repo's VideoProcessor.
+    `repeat_class` ({obj_id: (dx, dy)}) makes the detector report a second, shifted box of that class on every
+    detection frame: the reference then prompts that obj_id twice on one frame and the second call receives the first
+    call's mask logits as a dense prompt (det_sam2_RT.py:288-302 -> svp:470-482)."""
     import os
     import tempfile
 
     import cv2
     from detsam2_b200.synthetic import GroundTruthDetector
     vid = BilliardVideo(num_objects=3, height=height, width=width, num_frames=num_frames, seed=seed)
-    det = GroundTruthDetector(vid, detect_interval=4, appear_at={2: 4})
+    det = GroundTruthDetector(vid, detect_interval=4, appear_at={2: 4}, repeat_class=repeat_class)
     rec = {}
     with tempfile.TemporaryDirectory() as tmp:
         fdir = os.path.join(tmp, "frames")
@@ -289,6 +292,10 @@ def load_golden(name):
     return d, d.pop("__weights_fingerprint")
 
 
+# VideoProcessor.run scenarios: fixture name -> keyword arguments of run_video_processor.  `video_processor_dup`: the
+# detector reports object 1 twice per detection frame (second box shifted by 6 px)
+VP_SCENARIOS = {"video_processor": {}, "video_processor_dup": {"repeat_class": {1: (6.0, -4.0)}}}
+
 SCENARIOS = {"offline": run_offline, "stream": run_stream, "preload": run_preload, "mask_prompt": run_mask_prompt,
              "points_api": run_points_api, "refine_click": run_refine_click}
 
@@ -308,8 +315,12 @@ def compare(got, ref, rtol_rms, iou_min=None, int_exact=True):
             continue
         if k.endswith("masks_packed"):
             iou = packed_mask_iou(g, r)
-            if iou < (iou_min if iou_min is not None else 1.0):
-                bad.append(f"{k}: packed-mask IoU {iou:.5f}")
+            # boolean masks are all the reference's driver hands out: a logit that is 0 to fp32 rounding may land on
+            # either side of the `> 0` threshold, so ONE differing pixel per frame is not a mismatch (on the small
+            # VideoProcessor frames one pixel of a ~600-pixel union already reads as IoU 0.9984)
+            flips = int((np.unpackbits(g) != np.unpackbits(r)).sum())
+            if iou < (iou_min if iou_min is not None else 1.0) and flips > 1:
+                bad.append(f"{k}: packed-mask IoU {iou:.5f} ({flips} differing pixels)")
             continue
         if np.issubdtype(r.dtype, np.integer):
             if int_exact and not np.array_equal(g, r):
