@@ -3,7 +3,9 @@
 sam2.1_hiera_large, 1024x1024 frames, 16 box-prompted objects, synthetic billiard video, one
 independent stream per GPU (no collective on the data path).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]          this repo's sm_100a engine
+  python bench.py [--gpus N] [--steps K] [--warmup W]          this repo's sm_100a engine (offline mode A)
+  python bench.py --mode stream [--frames F]                  Det-SAM2's own drive mode B (VideoProcessor), same engine
+  python bench.py --model base_plus / --objects 64            other BASELINE configs through the same code
   python bench.py --impl reference ...                        the reference's algorithm on host cores
 
 One "step" = one tracked frame through the public predictor API (propagate_in_video): image encoder
@@ -14,7 +16,10 @@ video resolution.
           timed with CUDA events over exactly K steps, max over ranks, whole-job aggregate.
   e2e   : same metric with frames in pinned host memory (the reference default), H2D of every frame
           and D2H of the bit-packed thresholded masks inside the timed region.
-Prints ONE JSON line on rank 0.
+Extra keys on the N = 1 line: `roofline` (dominant kernel, live CUDA-event timing), `cpu_baseline` (the fp32 torch
+restatement of the reference on the host cores, REAL 16-object steps against a full memory bank), `gpu_library_baseline`
+(the same restatement on this GPU under bf16 autocast + fused SDPA = torch's library kernels, the bar SURVEY.md §2.2
+names) and `stream_mode` (mode B, short run).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -227,13 +232,17 @@ def run_ours(args):
         avg_ms = sum(durs) / len(durs)
         achieved = fm["cross_exec_per_launch"] / (avg_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "flash_d256_tcgen05_kernel<DV=64,BN=128,QT=1> (memory cross-attention, Q in TMEM)",
-                "achieved": round(achieved, 1), "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": round(achieved / peaks["tflops_sustained"], 4),
+                # the timed region is a fraction of a second and the SM clock sampler reads ~max clocks throughout, i.e.
+                # burst conditions: the denominator is the BURST cuBLAS figure; the sustained one is given beside it
+                "achieved": round(achieved, 1), "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
+                "frac": round(achieved / peaks["tflops_burst"], 4),
+                "peak_sustained": peaks["tflops_sustained"],
+                "frac_of_sustained_peak": round(achieved / peaks["tflops_sustained"], 4),
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture of the
                 # same shape (B=16, N=28736): profiles/r1_s8_attn_gemm_ncu_full_summary.txt; algorithmic 336 MB
                 "traffic": 379.9e6 if (B == 16 and N == 28736) else None, "traffic_unit": "bytes/launch",
                 "algorithmic_bytes_per_launch": int(2 * B * (T * 256 + N * 256 + N * 64 + T * 64)),
-                "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step)",
+                "peak_source": peaks["source"] + ", burst bf16 GEMM figure (clocks stay at max over the short timed region)",
                 "avg_launch_ms": round(avg_ms, 4), "launches_timed": len(durs), "keys_N": N,
                 "flops_per_launch_executed": fm["cross_exec_per_launch"],
                 "achieved_reference_formulation": round(fm["cross_alg_per_launch"] / (avg_ms * 1e-3) / 1e12, 1),
@@ -245,8 +254,7 @@ def run_ours(args):
         "metric": METRIC, "value": round(fps, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(results["device"] / K, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"configs[1]: sam2.1_hiera_{args.model}, {S}x{S}, {B} box-prompted objects, "
-                               f"synthetic billiard video, offline forward propagate_in_video, 1 stream per GPU",
+        "config": {"workload": _workload(args, S, world),
                    "objects": B, "image_size": S, "memory_tokens_N": (kern["flash_cross"][-1][1]["N"] if "flash_cross" in kern else None),
                    "prefill_frames": prefill, "encoder_batch_frames": predictor.encoder_batch_frames,
                    "encoder_batching": "the image encoder runs once per frame, several upcoming frames per launch sequence "
@@ -265,6 +273,16 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roof,
     }
+    if world == 1 and not args.no_extra_legs:
+        del predictor, eng
+        torch.cuda.empty_cache()
+        for key, fn in (("stream_mode", lambda: stream_mode(args, frames=args.stream_frames, quiet=True)),
+                        ("gpu_library_baseline", lambda: gpu_library_baseline(args))):
+            try:
+                line[key] = fn()
+            except Exception as e:   # a baseline leg must never take the bench line down with it
+                line[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.empty_cache()
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, budget_s=args.cpu_budget)
     print(json.dumps(line), flush=True)
@@ -276,87 +294,225 @@ def run_ours(args):
 # CPU arm: the reference's algorithm (oracle port; the reference itself is PyTorch-on-/root/reference,
 # which does not exist on the GPU box) on the host cores.
 # --------------------------------------------------------------------------------------------------
-def _cpu_frame_time(args, sample_objects, steps, warmup, budget_s):
-    """Times tracked frames of the CPU port.  A step = image encoder (shared by all objects) + the
-    per-object seams for `sample_objects` objects; the per-object part is scaled to args.objects."""
+def _steady_state_session(pred, args, steps, warmup):
+    """A session whose memory bank is ALREADY at its steady state when the first timed frame is tracked, at the real
+    object count: box prompts for all objects on frame 0 (one conditioning frame, memory-encoded by the preflight), then
+    frames 1..16 are marked as tracked by giving them stored outputs of the right shapes (copies of the conditioning
+    frame's: values do not change the cost).  Tracking frame 17 onwards then reads 1 conditioning + 6 recent frames +
+    16 object pointers = 28 736 memory tokens per object — the arithmetic of a steady-state step — without spending
+    16 x ~7 s of host time on filling the bank first."""
+    from detsam2_b200.synthetic import BilliardVideo
+    cfg = pred.cfg
+    S, B = cfg.image_size, args.objects
+    pre = 16
+    vid = BilliardVideo(num_objects=B, height=S, width=S, num_frames=1 + pre + warmup + steps, seed=0)
+    st = pred.init_state(list(vid.frames()))
+    import numpy as np
+    pred.add_new_boxes(st, 0, {oid: np.asarray(b, np.float32) for oid, b in vid.boxes(0).items()})
+    pred.propagate_in_video_preflight(st)
+    cond = st["output_dict"]["cond_frame_outputs"][0]
+    for t in range(1, pre + 1):
+        out = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in cond.items()}
+        st["output_dict"]["non_cond_frame_outputs"][t] = out
+        pred._add_output_per_object(st, t, out, "non_cond_frame_outputs")
+        st["frames_already_tracked"][t] = {"reverse": False}
+    return st, pre + 1
+
+
+def _cpu_frame_time(args, steps, warmup, budget_s):
+    """Times REAL steady-state tracked frames of the fp32 CPU restatement (oracle/sam2_oracle.py) at the real object
+    count: image encoder + memory attention over the full bank + mask decoder + memory encoder + hole filling + resize,
+    through the same predictor API as the CUDA arm.  Nothing is scaled or extrapolated."""
     from detsam2_b200.config import get_config
     from detsam2_b200.predictor import SAM2VideoPredictor
-    from detsam2_b200.synthetic import BilliardVideo
     from detsam2_b200.weights import synthetic_state_dict
     from oracle import sam2_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     cfg = get_config(args.model)
-    sd = synthetic_state_dict(cfg, 0)
-    eng = O.OracleEngine(cfg, sd, fill_holes=True)
-    S = cfg.image_size
-    Bs = sample_objects
-    nfr = 2 + warmup + steps
-    vid = BilliardVideo(num_objects=Bs, height=S, width=S, num_frames=nfr, seed=0)
-    # frame-at-a-time encoder, as the reference runs it (the encode-ahead of the CUDA arm would put several frames'
-    # encoder time into one step of this per-step accounting)
+    # attention: F.scaled_dot_product_attention (the call the reference makes) or the written-out form, whichever this
+    # host runs faster at the cross-attention shape — the baseline should be the CPU's best, not a strawman
+    fused = _cpu_faster_sdpa()
+    eng = O.OracleEngine(cfg, synthetic_state_dict(cfg, 0), fill_holes=True, fused_sdpa=fused)
+    # frame-at-a-time encoder, as the reference runs it
     pred = SAM2VideoPredictor(eng, fill_hole_area=8, encoder_batch_frames=1)
-    enc_times, rest_times = [], []
-    orig_encode = eng.encode_image
-
-    def timed_encode(img):
-        t = time.perf_counter()
-        r = orig_encode(img)
-        enc_times.append(time.perf_counter() - t)
-        return r
-
-    eng.encode_image = timed_encode
+    times = []
     with torch.inference_mode():
-        st = pred.init_state(list(vid.frames()))
-        for oid, box in vid.boxes(0).items():
-            pred.add_new_points_or_box(st, 0, oid, box=box)
-        gen = pred.propagate_in_video(st)
-        next(gen)  # frame 0 (prompted) — preflight + memory encoder of the cond frame
+        t_setup = time.perf_counter()
+        st, first = _steady_state_session(pred, args, steps, warmup)
+        setup_s = time.perf_counter() - t_setup
+        gen = pred.propagate_in_video(st, start_frame_idx=first)
         t_start = time.perf_counter()
-        done = 0
         for i in range(warmup + steps):
-            n_enc = len(enc_times)
             t = time.perf_counter()
             next(gen)
             dt = time.perf_counter() - t
-            enc = sum(enc_times[n_enc:])
             if i >= warmup:
-                rest_times.append((enc, dt - enc))
-                done += 1
-            if time.perf_counter() - t_start > budget_s and done >= 1:
+                times.append(dt)
+            if time.perf_counter() - t_start > budget_s and times:
                 break
-    enc = statistics.mean(e for e, _ in rest_times)
-    rest = statistics.mean(r for _, r in rest_times)
-    per_frame = enc + rest * (args.objects / Bs)
-    return {"s_per_frame": per_frame, "encoder_s": enc, "per_object_s": rest / Bs, "steps_measured": done, "cores": cores}
+    return {"s_per_frame": statistics.mean(times), "steps_measured": len(times), "cores": cores, "setup_s": setup_s,
+            "frame_times_s": [round(x, 2) for x in times],
+            "attention": "F.scaled_dot_product_attention" if fused else "written-out softmax(QK^T)V (faster on this host)"}
+
+
+def _cpu_faster_sdpa():
+    import torch.nn.functional as F
+    q, k, v = torch.randn(1, 4096, 256), torch.randn(1, 28736, 256), torch.randn(1, 28736, 256)
+    best = {}
+    with torch.inference_mode():
+        for name, fn in (("fused", lambda: F.scaled_dot_product_attention(q, k, v)),
+                         ("explicit", lambda: torch.softmax((q @ k.transpose(-1, -2)) * (1.0 / 16), dim=-1) @ v)):
+            fn()
+            t = time.perf_counter()
+            fn()
+            best[name] = time.perf_counter() - t
+    return best["fused"] <= best["explicit"]
+
+
+def _cpu_sample_text(args, r):
+    return (f"{r['steps_measured']} steady-state tracked frame(s) of sam2.1_hiera_{args.model} 1024^2 with all {args.objects} "
+            f"objects against a full memory bank (28 736 tokens per object), every seam executed, nothing scaled: "
+            f"{r['frame_times_s']} s; fp32 torch restatement of the reference (oracle/sam2_oracle.py, torch "
+            f"{torch.__version__}, {r['cores']} threads, attention = {r['attention']}); bank pre-filled with stored outputs of the right shapes "
+            f"(setup {r['setup_s']:.0f} s, untimed)")
 
 
 def cpu_baseline(args, budget_s=25.0):
-    r = _cpu_frame_time(args, sample_objects=1, steps=2, warmup=0, budget_s=budget_s)
+    r = _cpu_frame_time(args, steps=2, warmup=0, budget_s=budget_s)
     return {"value": round(1.0 / r["s_per_frame"], 5), "unit": UNIT, "cores": r["cores"], "kind": "port",
-            "sample": f"{r['steps_measured']} tracked frame(s) of sam2.1_hiera_{args.model} 1024^2 with 1 object on the fp32 "
-                      f"CPU port (oracle/sam2_oracle.py, torch {torch.__version__}, {r['cores']} threads); encoder "
-                      f"{r['encoder_s']:.2f} s/frame + {r['per_object_s']:.2f} s/object/frame scaled to {args.objects} objects"}
+            "extrapolated": False, "sample": _cpu_sample_text(args, r)}
 
 
 def run_reference(args):
     rank, _, world = _dist_env()
     if rank != 0:
         return
-    r = _cpu_frame_time(args, sample_objects=1, steps=args.steps, warmup=args.warmup, budget_s=args.cpu_budget_ref)
+    r = _cpu_frame_time(args, steps=args.steps, warmup=min(args.warmup, 1), budget_s=args.cpu_budget_ref)
     fps = 1.0 / r["s_per_frame"]
-    sample = (f"{r['steps_measured']} of {args.steps} requested tracked frames measured within the "
-              f"{args.cpu_budget_ref:.0f} s budget; each = Hiera-L encoder ({r['encoder_s']:.2f} s) + per-object seams "
-              f"for 1 object ({r['per_object_s']:.2f} s) scaled x{args.objects}; fp32 CPU port of the reference "
-              f"(oracle/sam2_oracle.py), {r['cores']} threads")
+    sample = (f"{r['steps_measured']} of {args.steps} requested steps measured within the {args.cpu_budget_ref:.0f} s budget "
+              f"(1 warm-up step); " + _cpu_sample_text(args, r))
+    S = 1024
     line = {"impl": "reference", "metric": METRIC, "value": round(fps, 5), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * r["s_per_frame"], 1),
+            "steps": args.steps, "steps_measured": r["steps_measured"], "warmup": args.warmup,
+            "ms_per_step": round(1e3 * r["s_per_frame"], 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"configs[1]: sam2.1_hiera_{args.model}, 1024x1024, {args.objects} box-prompted objects, "
-                                   f"synthetic billiard video, offline forward propagate_in_video (CPU, bounded sample)"},
-            "cpu_baseline": {"value": round(fps, 5), "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+            "config": {"workload": _workload(args, S, world), "objects": args.objects, "image_size": S,
+                       "memory_tokens_N": 28736},
+            "cpu_baseline": {"value": round(fps, 5), "unit": UNIT, "cores": r["cores"], "kind": "port",
+                             "extrapolated": False, "sample": sample},
             "e2e": {"value": round(fps, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU library baseline: the same torch restatement on THIS GPU the way the reference is run in production — bf16
+# autocast, F.scaled_dot_product_attention (flash backend), cuBLAS / cuDNN kernels (det_sam2_RT.py:101-107,
+# sam/transformer.py:28-41).  SURVEY.md §2.2 names it "the kernel to beat".  It is a baseline, never a checker, and
+# none of this repo's kernels run in it.  (The unmodified reference itself cannot travel to the GPU box; its module
+# and dict overhead would only make this number lower.)
+# --------------------------------------------------------------------------------------------------
+def gpu_library_baseline(args, steps=8, warmup=2):
+    from detsam2_b200.config import get_config
+    from detsam2_b200.predictor import SAM2VideoPredictor
+    from detsam2_b200.weights import synthetic_state_dict
+    from oracle import sam2_oracle as O
+    cfg = get_config(args.model)
+    eng = O.OracleEngine(cfg, synthetic_state_dict(cfg, 0), fill_holes=False, device="cuda", autocast=True)
+    pred = SAM2VideoPredictor(eng, fill_hole_area=0, encoder_batch_frames=1)
+    with torch.inference_mode():
+        st, first = _steady_state_session(pred, args, steps, warmup)
+        gen = pred.propagate_in_video(st, start_frame_idx=first)
+        for _ in range(warmup):
+            next(gen)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            next(gen)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": round(1e3 / ms, 3), "unit": UNIT, "ms_per_step": round(ms, 3), "steps": steps,
+            "what": f"torch {torch.__version__} eager, bf16 autocast, fused SDPA, cuBLAS/cuDNN: the fp32 restatement of the "
+                    f"reference (oracle/sam2_oracle.py) moved to cuda — same workload ({args.objects} objects, full bank), "
+                    f"frames resident in HBM, hole filling off (the reference's extension is absent); library kernels only"}
+
+
+# --------------------------------------------------------------------------------------------------
+# mode B: Det-SAM2's own drive (det_sam2_RT.py:342-411) — VideoProcessor with K = 30 frames per chunk, detection every
+# 30 frames (ground-truth boxes stand in for YOLO, detector time excluded), reverse window M = 60, state window S = 60.
+# video fps = video frames / WALL time: prompting, preflight, reverse re-tracking (every frame is tracked ~1.7x), release,
+# frame ingest and the D2H hand-off of the boolean masks included; frame synthesis excluded.
+# --------------------------------------------------------------------------------------------------
+def stream_mode(args, frames=150, quiet=False):
+    from detsam2_b200.build_sam import build_sam2_video_predictor
+    from detsam2_b200.synthetic import BilliardVideo, GroundTruthDetector
+    from detsam2_b200.video_processor import VideoProcessor
+    dev = torch.device("cuda", torch.cuda.current_device())
+    predictor = build_sam2_video_predictor(f"configs/sam2.1/sam2.1_hiera_{_YAML[args.model]}.yaml", device=dev, seed=0,
+                                           feature_cache_frames=64)
+    S = predictor.cfg.image_size
+    H, W = (S, S) if args.frame_hw is None else args.frame_hw
+    vid = BilliardVideo(num_objects=args.objects, height=H, width=W, num_frames=frames, seed=0)
+    imgs = [vid.frame(t) for t in range(frames)]
+    steps = [0]
+    orig = predictor._run_single_frame_inference
+
+    def counted(*a, **kw):
+        if not kw.get("is_init_cond_frame", False):
+            steps[0] += 1
+        return orig(*a, **kw)
+
+    predictor._run_single_frame_inference = counted
+    l0 = 0
+    for rep in range(2):   # first pass warms up graphs / allocator; the second is timed
+        steps[0] = 0
+        vp = VideoProcessor(predictor=predictor, detector=GroundTruthDetector(vid, detect_interval=30),
+                            frame_buffer_size=30, detect_interval=30, max_frame_num_to_track=60,
+                            max_inference_state_frames=60, skip_classes=set())
+        torch.cuda.synchronize()
+        l0 = predictor.engine.launches_executed()
+        t0 = time.perf_counter()
+        with torch.inference_mode():
+            segs = vp.run(frames=iter(imgs))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    launches = predictor.engine.launches_executed() - l0
+    ok = all(t in segs and len(segs[t]) == args.objects for t in range(frames))
+    out = {"video_fps": round(frames / dt, 2), "track_steps_per_s": round(steps[0] / dt, 2), "track_steps": steps[0],
+           "video_frames": frames, "wall_s": round(dt, 3), "every_frame_segmented": ok, "gpu_launches": int(launches),
+           "frame_hw": [H, W],
+           "drive": "VideoProcessor (det_sam2_RT.py semantics): K=30 frames per chunk, detection every 30 frames "
+                    "(ground-truth boxes, detector time excluded), reverse window M=60, state window S=60; wall time "
+                    "includes prompting, preflight, re-tracking, release, frame ingest and the D2H hand-off of the masks",
+           "chunk_phase_s": {k: round(v, 3) for k, v in vp.timings.items()}}
+    del predictor, vp
+    return out
+
+
+def run_stream(args):
+    """`--mode stream`: one JSON line for drive mode B (one GPU)."""
+    torch.cuda.set_device(0)
+    r = stream_mode(args, frames=args.frames)
+    line = {"metric": "video frames/sec, Det-SAM2 stream mode @ sam2.1_hiera_%s, %d objs" % (args.model, args.objects),
+            "value": r["video_fps"], "unit": "frames/s", "n_gpus": 1, "steps": r["track_steps"], "warmup": 0,
+            "ms_per_step": round(1e3 * r["wall_s"] / max(r["track_steps"], 1), 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"SURVEY.md 8d config 2 mode B: sam2.1_hiera_{args.model}, {r['frame_hw'][1]}x{r['frame_hw'][0]} "
+                                   f"frames, {args.objects} objects, {args.frames}-frame stream", "drive": r["drive"]},
+            "e2e": {"value": r["video_fps"], "unit": "frames/s",
+                    "h2d_bytes_per_step": 3 * r["frame_hw"][0] * r["frame_hw"][1],
+                    "d2h_bytes_per_step": args.objects * r["frame_hw"][0] * r["frame_hw"][1],
+                    "note": "wall-clock through VideoProcessor.run with host uint8 frames in and host boolean masks out; "
+                            "bytes are per VIDEO frame (uint8 RGB up, boolean masks down)"},
+            "gpu_launches": r["gpu_launches"], "stream_mode": r}
+    print(json.dumps(line), flush=True)
+
+
+def _workload(args, S, world):
+    return (f"configs[1]: sam2.1_hiera_{args.model}, {S}x{S}, {args.objects} box-prompted objects, synthetic billiard video, "
+            f"offline forward propagate_in_video, 1 stream per GPU")
 
 
 _YAML = {"tiny": "t", "small": "s", "base_plus": "b+", "large": "l"}
@@ -371,7 +527,13 @@ def main():
     ap.add_argument("--model", default="large", choices=list(_YAML))
     ap.add_argument("--objects", type=int, default=16)
     ap.add_argument("--prefill", type=int, default=16, help="tracked frames before warm-up so the bank is at steady state")
+    ap.add_argument("--mode", default="offline", choices=["offline", "stream"],
+                    help="offline = BASELINE configs[1] mode A (the bench line); stream = Det-SAM2's VideoProcessor drive (mode B)")
+    ap.add_argument("--frames", type=int, default=300, help="--mode stream: length of the stream")
+    ap.add_argument("--stream-frames", type=int, default=150, help="length of the short stream-mode leg on the default line")
+    ap.add_argument("--frame-hw", type=int, nargs=2, default=None, help="--mode stream: video frame height width (default S S)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the stream_mode and gpu_library_baseline legs")
     ap.add_argument("--only-device", action="store_true", help="A/B helper: time the device-resident leg only")
     ap.add_argument("--cuda-profiler", action="store_true", help="bracket the timed device steps with cudaProfilerStart/Stop")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
@@ -379,6 +541,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "stream":
+        run_stream(args)
     else:
         args.warmup = max(args.warmup, 3)
         run_ours(args)

@@ -48,8 +48,15 @@ def mlp(sd, p, x, n, act=F.relu, sigmoid_out=False):
     return torch.sigmoid(x) if sigmoid_out else x
 
 
+# False: attention written out (scores materialised, fp32) — the checker.  True: F.scaled_dot_product_attention, what the
+# reference calls (sam/transformer.py:268,347; flash backend under CUDA bf16 autocast) — used by the GPU library baseline.
+FUSED_SDPA = False
+
+
 def sdpa(q, k, v):
-    """F.scaled_dot_product_attention with no mask / dropout, written out (fp32)."""
+    """F.scaled_dot_product_attention with no mask / dropout, written out (fp32) unless FUSED_SDPA."""
+    if FUSED_SDPA:
+        return F.scaled_dot_product_attention(q, k, v)
     s = (q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(q.shape[-1]))
     return torch.softmax(s, dim=-1) @ v
 
@@ -505,7 +512,7 @@ def forward_sam_heads(sd, cfg, backbone_features, point_coords=None, point_label
         best = torch.argmax(ious, dim=-1)
         if DECISION_LOG is not None:
             top2 = torch.topk(ious, 2, dim=-1).values
-            DECISION_LOG.append({"multimask_top2_margin": (top2[:, 0] - top2[:, 1]).tolist()})
+            DECISION_LOG.append({"multimask_top2_margin": (top2[:, 0] - top2[:, 1]).tolist(), "best": best.tolist()})
         bi = torch.arange(B)
         low, high = low_multi[bi, best].unsqueeze(1), high_multi[bi, best].unsqueeze(1)
         if tokens.shape[1] > 1:
@@ -568,8 +575,8 @@ def encode_new_memory(sd, cfg, pix_feat, pred_masks_high_res, object_score_logit
 # ------------------------------------------------------------------------------------------------
 def fill_holes_in_mask_scores(mask, max_area):
     from . import cc_oracle
-    out = cc_oracle.fill_holes(mask.detach().cpu().numpy(), max_area)
-    return torch.from_numpy(out).reshape(mask.shape)
+    out = cc_oracle.fill_holes(mask.detach().float().cpu().numpy(), max_area)
+    return torch.from_numpy(out).reshape(mask.shape).to(mask.device)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -577,20 +584,52 @@ def fill_holes_in_mask_scores(mask, max_area):
 # engine in detsam2_b200/engine.py), so tests can drive the SAME host state machine with either.
 # ------------------------------------------------------------------------------------------------
 class OracleEngine:
-    """fp32 CPU implementation of the engine seams, used ONLY by tests / smoke / cpu_baseline."""
+    """Plain-PyTorch implementation of the engine seams, used ONLY by tests / smoke / bench.py's baseline legs.
 
-    name = "oracle-cpu-fp32"
+    device="cpu" (default): the fp32 CPU checker that is pinned against the reference fixtures.
+    device="cuda": the SAME code on torch's own CUDA kernels in fp32 with TF32 off (cuBLAS / cuDNN fp32) — an
+        independent fp32 reference that finishes the full-size cases (large, 16 objects, steady-state bank) in seconds;
+        tests/test_oracle_devices.py checks it against the CPU path.
+    autocast=True (CUDA only): bf16 autocast + fused SDPA, i.e. the arithmetic the reference runs in production
+        (det_sam2_RT.py:101-107, sam/transformer.py:28-41) — bench.py's `gpu_library_baseline`, never a checker."""
 
-    def __init__(self, cfg, state_dict, fill_holes=True):
+    name = "oracle-torch-fp32"
+
+    def __init__(self, cfg, state_dict, fill_holes=True, device="cpu", autocast=False, fused_sdpa=None):
         self.cfg = cfg
-        self.sd = {k: v.detach().float().cpu() for k, v in state_dict.items()}
-        self.device = torch.device("cpu")
+        self.device = torch.device(device)
+        if self.device.type == "cuda":
+            if self.device.index is None:
+                self.device = torch.device("cuda", torch.cuda.current_device())
+            # a checker must not silently run TF32 convolutions / matmuls
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+        if autocast and self.device.type != "cuda":
+            raise ValueError("autocast=True is the CUDA bf16 library baseline")
+        self.autocast = bool(autocast)
+        # fused_sdpa=True: attention through F.scaled_dot_product_attention, the call the reference makes
+        # (sam/transformer.py:268,347) — same mathematics, torch's blocked kernel instead of a materialised score matrix;
+        # the timing legs of bench.py use it (the checker keeps the written-out form)
+        self.fused_sdpa = self.autocast if fused_sdpa is None else bool(fused_sdpa)
+        self.sd = {k: v.detach().float().to(self.device) for k, v in state_dict.items()}
         self.fill_holes_enabled = fill_holes
         self._pos = {}
 
+    def _ctx(self):
+        """Factory calls inside the restated functions (torch.arange, torch.zeros ...) land on this engine's device."""
+        import contextlib
+        stack = contextlib.ExitStack()
+        stack.enter_context(torch.device(self.device))
+        if self.autocast:
+            stack.enter_context(torch.autocast("cuda", dtype=torch.bfloat16))
+        if self.fused_sdpa:
+            stack.enter_context(_fused_sdpa())
+        return stack
+
     # seam 1: sam2_video_predictor.py:1174-1212 + sam2_base.py:450-477
     def encode_image(self, image_f16):
-        bo = forward_image(self.sd, self.cfg, image_f16.float()[None])
+        with self._ctx():
+            bo = forward_image(self.sd, self.cfg, image_f16.to(self.device).float()[None])
         return {"fpn": bo["backbone_fpn"], "pos": bo["vision_pos_enc"]}
 
     def encode_images(self, images_f16):
@@ -603,33 +642,40 @@ class OracleEngine:
     # seam 2: sam2_base.py:479-690
     def condition_on_memory(self, feats, B, frame_idx, is_init_cond_frame, output_dict, num_frames, reverse,
                             preload_idx):
-        f = feats["fpn"][-1].expand(B, -1, -1, -1).flatten(2).permute(2, 0, 1)
-        p = feats["pos"][-1].expand(B, -1, -1, -1).flatten(2).permute(2, 0, 1)
-        return prepare_memory_conditioned_features(self.sd, self.cfg, frame_idx, is_init_cond_frame, f, p,
-                                                   output_dict, num_frames, reverse, preload_idx)
+        with self._ctx():
+            f = feats["fpn"][-1].expand(B, -1, -1, -1).flatten(2).permute(2, 0, 1)
+            p = feats["pos"][-1].expand(B, -1, -1, -1).flatten(2).permute(2, 0, 1)
+            return prepare_memory_conditioned_features(self.sd, self.cfg, frame_idx, is_init_cond_frame, f, p,
+                                                       output_dict, num_frames, reverse, preload_idx)
 
     # seam 3: sam2_base.py:254-397
     def sam_heads(self, pix_feat, feats, B, point_coords, point_labels, mask_inputs, multimask_output):
-        hr = [x.expand(B, -1, -1, -1) for x in feats["fpn"][:-1]]
-        o = forward_sam_heads(self.sd, self.cfg, pix_feat, point_coords, point_labels, mask_inputs, hr,
-                              multimask_output)
-        return {"pred_masks": o["low_res_masks"], "ious": o["ious"], "obj_ptr": o["obj_ptr"],
-                "object_score_logits": o["object_score_logits"], "_multimasks": o["low_res_multimasks"]}
+        with self._ctx():
+            hr = [x.expand(B, -1, -1, -1) for x in feats["fpn"][:-1]]
+            dev = lambda t: None if t is None else t.to(self.device)  # noqa: E731
+            o = forward_sam_heads(self.sd, self.cfg, pix_feat, dev(point_coords), dev(point_labels), dev(mask_inputs),
+                                  hr, multimask_output)
+        return {"pred_masks": o["low_res_masks"].float(), "ious": o["ious"].float(), "obj_ptr": o["obj_ptr"].float(),
+                "object_score_logits": o["object_score_logits"].float(), "_multimasks": o["low_res_multimasks"]}
 
     def mask_as_output(self, feats, mask_inputs):
-        B = mask_inputs.shape[0]
-        pix = feats["fpn"][-1].expand(B, -1, -1, -1)
-        hr = [x.expand(B, -1, -1, -1) for x in feats["fpn"][:-1]]
-        o = use_mask_as_output(self.sd, self.cfg, pix, hr, mask_inputs)
-        return {"pred_masks": o["low_res_masks"], "ious": o["ious"], "obj_ptr": o["obj_ptr"],
-                "object_score_logits": o["object_score_logits"]}
+        with self._ctx():
+            B = mask_inputs.shape[0]
+            pix = feats["fpn"][-1].expand(B, -1, -1, -1)
+            hr = [x.expand(B, -1, -1, -1) for x in feats["fpn"][:-1]]
+            o = use_mask_as_output(self.sd, self.cfg, pix, hr, mask_inputs.to(self.device))
+        return {"pred_masks": o["low_res_masks"].float(), "ious": o["ious"].float(), "obj_ptr": o["obj_ptr"].float(),
+                "object_score_logits": o["object_score_logits"].float()}
 
     # seam 4: sam2_base.py:692-743 (+ the x4 bilinear of sam2_base.py:355-360 / svp:736-741)
     def encode_memory(self, feats, B, pred_masks_low_res, object_score_logits, is_mask_from_pts):
-        S = self.cfg.image_size
-        high = F.interpolate(pred_masks_low_res.float(), size=(S, S), mode="bilinear", align_corners=False)
-        pix = feats["fpn"][-1].expand(B, -1, -1, -1)
-        mf, pos = encode_new_memory(self.sd, self.cfg, pix, high, object_score_logits, is_mask_from_pts)
+        with self._ctx():
+            S = self.cfg.image_size
+            high = F.interpolate(pred_masks_low_res.to(self.device).float(), size=(S, S), mode="bilinear",
+                                 align_corners=False)
+            pix = feats["fpn"][-1].expand(B, -1, -1, -1)
+            mf, pos = encode_new_memory(self.sd, self.cfg, pix, high, object_score_logits.to(self.device),
+                                        is_mask_from_pts)
         return mf.to(torch.bfloat16), [pos]
 
     # seam 5: svp:1341-1348 and svp:618-642
@@ -642,3 +688,15 @@ class OracleEngine:
         if masks.shape[-2:] == (H, W):
             return masks
         return F.interpolate(masks.float(), size=(H, W), mode="bilinear", align_corners=False)
+
+
+class _fused_sdpa:
+    """Context manager: route `sdpa` through F.scaled_dot_product_attention (library baseline only)."""
+
+    def __enter__(self):
+        global FUSED_SDPA
+        self.prev, FUSED_SDPA = FUSED_SDPA, True
+
+    def __exit__(self, *exc):
+        global FUSED_SDPA
+        FUSED_SDPA = self.prev

@@ -27,7 +27,9 @@ def oracle_predictor(name):
     return SAM2VideoPredictor(O.OracleEngine(cfg, sd, fill_holes=False), fill_hole_area=0), sd
 
 
-@pytest.mark.parametrize("name", ["stream", "preload", "offline", "mask_prompt", "points_api", "refine_click"])
+# large_1024 / bplus_720p: the full-size models (Hiera-L at 1024^2; base_plus with zero-padded 14/7 windows on 720p frames)
+@pytest.mark.parametrize("name", ["stream", "preload", "offline", "mask_prompt", "points_api", "refine_click",
+                                  "large_1024", "bplus_720p"])
 def test_oracle_matches_reference_golden(name):
     torch.set_num_threads(min(8, os.cpu_count() or 1))
     gold, fp = scenarios.load_golden(name)
