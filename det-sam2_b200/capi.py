@@ -29,6 +29,7 @@ class GemmArgs(C.Structure):
         ("rope_col0", C.c_int32), ("rope_col1", C.c_int32),
         ("rope_period", C.c_int32), ("rope_rows_per_batch", C.c_int32),
         ("rope_row_limit", C.c_int32), ("impl", C.c_int32),
+        ("rope_axial", C.c_void_p), ("rope_side", C.c_int32),
     ]
 
 

@@ -52,6 +52,14 @@ struct GemmParams {
   long long ldc, ldc_bf16;
   const float* rope_cs;
   int rope_col0, rope_col1, rope_period, rope_rows_per_batch, rope_row_limit;
+  // axial form of the rotary table: [64][side] (cos, sin) indexed by ONE grid coordinate — pairs 0..63 rotate by the x
+  // coordinate of the position, pairs 64..127 by its y coordinate, with the same 64 frequencies (position_encoding.py:
+  // 173-182), so the [128][side^2] table is this 32 KB table read two ways.  It is staged in shared memory (the
+  // pipeline runs with 3 stages then: rotary GEMMs have K <= 256) instead of 128 KB of table per 128-row tile coming
+  // out of L2 with one global load per pair.
+  const float* rope_axial;
+  int rope_side;
+  int stages;
 };
 
 // erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7) on the MUFU fast paths (rcp.approx, ex2.approx):
@@ -74,7 +82,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // bias / activation / gamma / rotary on NC consecutive columns of one row (registers).
 template <int NC>
 __device__ __forceinline__ void epilogue_math(const GemmParams& p, const uint32_t* acc, int row, int col0,
-                                              float (&v)[NC]) {
+                                              float (&v)[NC], uint32_t rope_smem = 0) {
 #pragma unroll
   for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(acc[i]);
   const bool full = (col0 + NC <= p.N);
@@ -106,7 +114,25 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, const uint32_
     for (int i = 0; i < NC; ++i)
       if (full || col0 + i < p.N) v[i] *= __ldg(p.gamma + col0 + i);
   }
-  if (p.rope_cs && col0 >= p.rope_col0 && col0 < p.rope_col1) {
+  if (p.rope_axial && col0 >= p.rope_col0 && col0 < p.rope_col1) {
+    const int rb = row % p.rope_rows_per_batch;
+    if (rb < p.rope_row_limit) {
+      const int pos = rb % p.rope_period;
+      const int pair0 = ((col0 - p.rope_col0) & 255) >> 1;        // 16 | 64: a chunk lies in ONE half of the pairs
+      const int coord = pair0 < 64 ? pos % p.rope_side : pos / p.rope_side;
+      // lanes = consecutive rows = consecutive x (conflict-free 8-byte reads) or one shared y (broadcast)
+      const uint32_t base = rope_smem + static_cast<uint32_t>(((pair0 & 63) * p.rope_side + coord) * 8);
+      const uint32_t pitch = static_cast<uint32_t>(p.rope_side) * 8u;
+#pragma unroll
+      for (int i = 0; i < NC / 2; ++i) {
+        float cx, cy;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cx), "=f"(cy) : "r"(base + static_cast<uint32_t>(i) * pitch));
+        const float a = v[2 * i], b = v[2 * i + 1];
+        v[2 * i] = a * cx - b * cy;
+        v[2 * i + 1] = a * cy + b * cx;
+      }
+    }
+  } else if (p.rope_cs && col0 >= p.rope_col0 && col0 < p.rope_col1) {
     const int rb = row % p.rope_rows_per_batch;
     if (rb < p.rope_row_limit) {
       // table is pair-major [128][period]: the 32 lanes of a warp (= 32 consecutive rows = consecutive
@@ -233,6 +259,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int num_tiles = p.tiles_m * p.tiles_n;
   const int k_blocks = (p.K + kBK - 1) / kBK;
   const uint32_t stage_tx = kABytes + static_cast<uint32_t>(p.BN) * kBK * 2;
+  const int nstages = p.stages;                                  // 4, or 3 when the rotary table takes the 4th slot
+  const uint32_t rope_smem = smem_base + 3u * kStageBytes;
 
   // Role gates use elect.sync, not `lane == 0`: tcgen05.mma / TMA take their operands from the uniform
   // datapath, and under a lane-id predicate the compiler wraps EVERY such instruction in an
@@ -250,7 +278,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const uint32_t sa = smem_base + stage * kStageBytes;
         tc::tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBK, m_blk * kBM);
         tc::tma_load_2d(sa + kABytes, &tmap_w, full_bar(stage), kb * kBK, n_blk * p.BN);
-        if (++stage == kStages) {
+        if (++stage == nstages) {
           stage = 0;
           phase ^= 1;
         }
@@ -279,7 +307,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           tc::umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
         }
         tc::umma_commit(empty_bar(stage));
-        if (++stage == kStages) {
+        if (++stage == nstages) {
           stage = 0;
           phase ^= 1;
         }
@@ -300,6 +328,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     int acc = 0;
     uint32_t acc_phase = 0;
     bool pending = false;  // lane 0: a bulk store may still be reading the staging buffer
+    if (p.rope_axial) {
+      // the table is a constant (not produced by the previous grid): nothing here waits for pdl — but every epilogue
+      // warp must see all of it, hence the named barrier over the 8 epilogue warps
+      const int n4 = 64 * p.rope_side * 2 / 4;
+      const float4* src = reinterpret_cast<const float4*>(p.rope_axial);
+      for (int i = threadIdx.x - 128; i < n4; i += 32 * kEpiWarps) {
+        const float4 t4 = __ldg(src + i);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rope_smem + 16u * i), "f"(t4.x), "f"(t4.y), "f"(t4.z),
+                     "f"(t4.w) : "memory");
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+    }
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = t / p.tiles_n, n_blk = t % p.tiles_n;
       tc::mbar_wait(tfull_bar(acc), acc_phase);
@@ -358,13 +398,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           uint32_t pk[32];
           {
             float v[32];
-            epilogue_math<32>(p, r0, mrow, n0 + c, v);
+            epilogue_math<32>(p, r0, mrow, n0 + c, v, rope_smem);
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[i] = tc::pack_bf16(v[2 * i], v[2 * i + 1]);
           }
           if (n0 + c + 32 < p.N && c + 32 < p.BN) {
             float v[32];
-            epilogue_math<32>(p, r1, mrow, n0 + c + 32, v);
+            epilogue_math<32>(p, r1, mrow, n0 + c + 32, v, rope_smem);
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[16 + i] = tc::pack_bf16(v[2 * i], v[2 * i + 1]);
           } else {
@@ -389,13 +429,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (mode == kStoreDirect) {
             if (row < p.M) {
               float v[32];
-              epilogue_math<32>(p, r, row, n0 + c, v);
+              epilogue_math<32>(p, r, row, n0 + c, v, rope_smem);
               epilogue_store_direct<32>(p, v, row, n0 + c);
             }
             continue;
           }
           float v[32];
-          epilogue_math<32>(p, r, mrow, n0 + c, v);
+          epilogue_math<32>(p, r, mrow, n0 + c, v, rope_smem);
           wait_staging();
           // 32 rows x 128 B, SWIZZLE_128B
           const uint32_t rowaddr = stg + static_cast<uint32_t>(lane) * 128u;
@@ -462,12 +502,15 @@ __global__ void gemm_bf16_simt_kernel(const __nv_bfloat16* __restrict__ A, long 
       if (p.act == 2) v[i] = gelu_erf(v[i]);
       if (p.gamma) v[i] *= p.gamma[c];
     }
-    if (p.rope_cs && col >= p.rope_col0 && col < p.rope_col1) {
+    if ((p.rope_cs || p.rope_axial) && col >= p.rope_col0 && col < p.rope_col1) {
       const int rb = row % p.rope_rows_per_batch;
       if (rb < p.rope_row_limit) {
         const int pos = rb % p.rope_period;
-        const float2 c = reinterpret_cast<const float2*>(p.rope_cs)[static_cast<size_t>(((col - p.rope_col0) & 255) >> 1) *
-                                                                       p.rope_period + pos];
+        const int pair = ((col - p.rope_col0) & 255) >> 1;
+        const float2 c = p.rope_axial
+            ? reinterpret_cast<const float2*>(p.rope_axial)[(pair & 63) * p.rope_side +
+                                                            (pair < 64 ? pos % p.rope_side : pos / p.rope_side)]
+            : reinterpret_cast<const float2*>(p.rope_cs)[static_cast<size_t>(pair) * p.rope_period + pos];
         const float a = v[0], b = v[1];
         v[0] = a * c.x - b * c.y;
         v[1] = a * c.y + b * c.x;
@@ -515,10 +558,15 @@ extern "C" int ds2_gemm(const ds2_gemm_args* a, void* stream) {
   DS2_REQUIRE(a->A && a->W, DS2_E_ARG, "ds2_gemm: null operand");
   DS2_REQUIRE(a->out_f32 || a->out_bf16, DS2_E_ARG, "ds2_gemm: no output");
   DS2_REQUIRE(a->lda >= a->K && a->ldw >= a->K, DS2_E_ARG, "ds2_gemm: leading dim < K");
-  if (a->rope_cs) {
+  if (a->rope_cs || a->rope_axial) {
     DS2_REQUIRE(a->rope_period > 0 && a->rope_rows_per_batch > 0 && (a->rope_col0 % 32) == 0 &&
                     (a->rope_col1 % 32) == 0,
                 DS2_E_ARG, "ds2_gemm: bad rotary spec");
+  }
+  if (a->rope_axial) {
+    DS2_REQUIRE(a->rope_side > 0 && a->rope_side * a->rope_side == a->rope_period && a->rope_side <= 96 &&
+                    (a->rope_side % 2) == 0 && (reinterpret_cast<uintptr_t>(a->rope_axial) & 15) == 0,
+                DS2_E_ARG, "ds2_gemm: axial rotary table needs period == side^2, even side <= 96, 16-byte alignment");
   }
   GemmParams p;
   p.M = a->M;
@@ -540,6 +588,9 @@ extern "C" int ds2_gemm(const ds2_gemm_args* a, void* stream) {
   p.rope_period = a->rope_period;
   p.rope_rows_per_batch = a->rope_rows_per_batch;
   p.rope_row_limit = a->rope_row_limit;
+  p.rope_axial = a->rope_axial;
+  p.rope_side = a->rope_side;
+  p.stages = a->rope_axial ? 3 : kStages;   // 64 * side * 8 B <= 48 KB = the fourth stage's slot
   cudaStream_t st = as_stream(stream);
 
   if (a->impl == 1) {

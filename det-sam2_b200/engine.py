@@ -60,6 +60,17 @@ def _rope_table(dim, side, theta):
     return torch.stack([ang.cos(), ang.sin()], dim=-1).permute(1, 0, 2).contiguous()
 
 
+def _rope_axial(dim, side, theta):
+    """The same table in its axial form [dim/4, side, 2]: entry [j, c] = (cos, sin)(c * freq_j).  Pair j < dim/4 of a head
+    rotates by the x coordinate of the position and pair j + dim/4 by its y coordinate with the SAME frequency
+    (position_encoding.py:173-182), so `_rope_table(dim, side, theta)[j, y * side + x] == _rope_axial(...)[j % (dim/4), x or y]`
+    bit for bit (tests/test_kernels_gpu.py::test_rope_axial_table_equals_full_table); 32 KB instead of 4 MB at side 64,
+    small enough for the GEMM epilogue to keep in shared memory."""
+    fr = 1.0 / (theta ** (torch.arange(0, dim, 4)[: dim // 4].float() / dim))
+    ang = torch.outer(torch.arange(side, dtype=F32), fr)           # [side, dim/4]
+    return torch.stack([ang.cos(), ang.sin()], dim=-1).permute(1, 0, 2).contiguous()
+
+
 def _dense_pe(gauss, side):
     """prompt_encoder.py:64-71 / position_encoding.py:131-149 -> token-major [side*side, 256]."""
     g = torch.ones(side, side, dtype=F32)
@@ -283,7 +294,7 @@ class CudaEngine:
         f32("ptr_tpos.w", sd["obj_ptr_tpos_proj.weight"])
         f32("ptr_tpos.b", sd["obj_ptr_tpos_proj.bias"])
         # ---- memory attention ----
-        f32("rope", _rope_table(256, fs, cfg.rope_theta))
+        f32("rope", _rope_axial(256, fs, cfg.rope_theta))
         for l in range(cfg.memattn_layers):
             q = f"memory_attention.layers.{l}."
             sa, ca = q + "self_attn.", q + "cross_attn_image."

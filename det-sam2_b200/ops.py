@@ -41,7 +41,8 @@ def _req(t, dtype, name):
 def gemm(a, w, *, bias=None, act=0, gamma=None, residual=None, res_row_mod=0, out_f32=None, out_bf16=None,
          rope=None, impl=0):
     """out = epilogue(a @ w.T).  a [M,K] bf16 (row-strided ok), w [N,K] bf16.
-    rope = (cs [128,P,2] f32 (pair-major), col0, col1, rows_per_batch, row_limit)."""
+    rope = (cs, col0, col1, rows_per_batch, row_limit) with cs f32, either the full pair-major table [128,P,2] or its
+    axial form [64,side,2] (P = side^2; staged in shared memory by the kernel — the product path)."""
     _req(a, BF16, "gemm.a"); _req(w, BF16, "gemm.w"); _req(bias, F32, "gemm.bias")
     _req(gamma, F32, "gemm.gamma"); _req(residual, F32, "gemm.residual")
     _req(out_f32, F32, "gemm.out_f32"); _req(out_bf16, BF16, "gemm.out_bf16")
@@ -64,9 +65,13 @@ def gemm(a, w, *, bias=None, act=0, gamma=None, residual=None, res_row_mod=0, ou
     if rope is not None:
         cs, c0, c1, rpb, lim = rope
         _req(cs, F32, "gemm.rope_cs")
-        g.rope_cs, g.rope_col0, g.rope_col1 = cs.data_ptr(), c0, c1
-        assert cs.shape[0] == 128 and cs.is_contiguous()
-        g.rope_period, g.rope_rows_per_batch, g.rope_row_limit = cs.shape[1], rpb, lim
+        g.rope_col0, g.rope_col1 = c0, c1
+        assert cs.shape[0] in (64, 128) and cs.is_contiguous()
+        if cs.shape[0] == 64:
+            g.rope_axial, g.rope_side, g.rope_period = cs.data_ptr(), cs.shape[1], cs.shape[1] * cs.shape[1]
+        else:
+            g.rope_cs, g.rope_period = cs.data_ptr(), cs.shape[1]
+        g.rope_rows_per_batch, g.rope_row_limit = rpb, lim
     g.impl = impl
     _chk(_lib().ds2_gemm(C.byref(g), _stream()), "ds2_gemm")
 

@@ -65,6 +65,11 @@ typedef struct ds2_gemm_args {
   int32_t rope_rows_per_batch;    /* rows per batch item */
   int32_t rope_row_limit;         /* rotate only rows with (row % rows_per_batch) < limit */
   int32_t impl;                   /* 0 = tcgen05 (product path), 1 = SIMT debug kernel */
+  /* axial form of the same table (takes precedence over rope_cs): [64][rope_side][2] (cos, sin) of ONE grid coordinate;
+   * pair j < 64 rotates by x = position % side, pair j >= 64 by y = position / side with the frequencies of pair j - 64
+   * (compute_axial_cis, position_encoding.py:173-182); requires rope_period == rope_side^2.  Staged in shared memory. */
+  const float* rope_axial;
+  int32_t rope_side;
 } ds2_gemm_args;
 int ds2_gemm(const ds2_gemm_args* args, void* stream);
 

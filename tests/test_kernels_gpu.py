@@ -115,6 +115,33 @@ def test_gemm_rope(ops):
     assert (of - ref).abs().max().item() < 1e-3
 
 
+@pytest.mark.parametrize("side,B,nptr,out", [(64, 2, 8, "bf16"), (32, 3, 4, "f32"), (64, 1, 0, "bf16")])
+def test_gemm_rope_axial_equals_full_table_path(ops, side, B, nptr, out):
+    """The rotary epilogue with the axial table staged in shared memory (product path) against the same GEMM with the
+    full pair-major table read from global memory: identical bits, on the memory-attention shapes (rows of several
+    stored frames per object, the pointer tokens at the end of every object's rows left unrotated)."""
+    from detsam2_b200.engine import _rope_axial, _rope_table
+    torch.manual_seed(33)
+    T = side * side
+    N_rows = 2 * T + nptr
+    a = bf(torch.randn(B * N_rows, 64, device=DEV))
+    w = bf(torch.randn(256, 64, device=DEV) / 8)
+    bias = torch.randn(256, device=DEV)
+    full, ax = _rope_table(256, side, 10000.0).to(DEV), _rope_axial(256, side, 10000.0).to(DEV)
+    kw = dict(out_bf16=None, out_f32=None)
+    outs = []
+    for tab in (full, ax):
+        o = torch.empty(B * N_rows, 256, device=DEV, dtype=torch.bfloat16 if out == "bf16" else torch.float32)
+        kw = {"out_bf16": o} if out == "bf16" else {"out_f32": o}
+        ops.gemm(a, w, bias=bias, rope=(tab, 0, 256, N_rows, N_rows - nptr), **kw)
+        outs.append(o)
+    assert torch.equal(outs[0], outs[1])
+    # and the SIMT debug kernel reads the axial table the same way
+    o1 = torch.empty(B * N_rows, 256, device=DEV)
+    ops.gemm(a, w, bias=bias, rope=(ax, 0, 256, N_rows, N_rows - nptr), out_f32=o1, impl=1)
+    assert (o1 - outs[1].float()).abs().max().item() < (4e-2 if out == "bf16" else 1e-3)
+
+
 def test_gemm_matches_simt_debug_kernel(ops):
     torch.manual_seed(4)
     a = bf(torch.randn(300, 96, device=DEV))

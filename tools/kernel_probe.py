@@ -37,21 +37,45 @@ def main():
         if res:
             kw["residual"] = o
         if rope:
-            ang = torch.rand(128, 4096, device=dev) * 6.28
-            cs = torch.stack([ang.cos(), ang.sin()], -1).contiguous()
+            from detsam2_b200.engine import _rope_axial, _rope_table
+            cs = (_rope_axial if rope == "axial" else _rope_table)(256, 64, 10000.0).to(dev)
             rpb = rows_per_batch or 4096
-            kw["rope"] = (cs, 0, min(N, 512), rpb, rpb)
+            kw["rope"] = (cs, 0, min(N, 512), rpb, rpb - (rpb % 4096))
         cases.append((name, lambda: ops.gemm(a, w, **kw), 2.0 * M * N * K, None))
+
+    def cublas_case(name, M, N, K):
+        a = torch.randn(M, K, device=dev).to(BF16)
+        w = (torch.randn(N, K, device=dev) / math.sqrt(K)).to(BF16)
+        o = torch.zeros(M, N, device=dev, dtype=BF16)
+        cases.append((name, lambda: torch.matmul(a, w.t(), out=o), 2.0 * M * N * K, None))
 
     gemm_case("s3.qkv   4096x1728x576", 4096, 1728, 576)
     gemm_case("s3.proj  4096x576x576 +res", 4096, 576, 576, out="f32", res=True)
     gemm_case("s3.fc1   4096x2304x576 gelu", 4096, 2304, 576, act=2)
     gemm_case("s3.fc2   4096x576x2304 +res", 4096, 576, 2304, out="f32", res=True)
+    # the same Hiera stage-3 block inside the 4-frame encoder pass (M = 4 x 4096 rows), with the epilogue varied, and
+    # cuBLAS (torch.matmul, plain bf16 store, no epilogue) on the same shapes as the library bar
+    gemm_case("e4.qkv   16384x1728x576", 16384, 1728, 576)
+    gemm_case("e4.proj  16384x576x576 +res", 16384, 576, 576, out="f32", res=True)
+    gemm_case("e4.fc1   16384x2304x576 gelu", 16384, 2304, 576, act=2)
+    gemm_case("e4.fc1   16384x2304x576 relu", 16384, 2304, 576, act=1)
+    gemm_case("e4.fc1   16384x2304x576 none", 16384, 2304, 576, act=0)
+    gemm_case("e4.fc2   16384x576x2304 +res", 16384, 576, 2304, out="f32", res=True)
+    gemm_case("e4.fc2   16384x576x2304 bf16", 16384, 576, 2304)
+    cublas_case("cublas   16384x1728x576", 16384, 1728, 576)
+    cublas_case("cublas   16384x576x576", 16384, 576, 576)
+    cublas_case("cublas   16384x2304x576", 16384, 2304, 576)
+    cublas_case("cublas   16384x576x2304", 16384, 576, 2304)
+    cublas_case("cublas   65536x2048x256", 65536, 2048, 256)
+    cublas_case("cublas   65536x256x2048", 65536, 256, 2048)
+    cublas_case("cublas   8192x8192x8192", 8192, 8192, 8192)
     gemm_case("s2.fc1   16384x1152x288 gelu", 16384, 1152, 288, act=2)
     gemm_case("s2.fc2   16384x288x1152 +res", 16384, 288, 1152, out="f32", res=True)
     gemm_case("s4.fc2   1024x1152x4608 +res", 1024, 1152, 4608, out="f32", res=True)
     gemm_case("ma.sa_qkv 65536x768x256 rope", 65536, 768, 256, rope=True)
     gemm_case("ma.ca_k  459776x256x64 rope", 459776, 256, 64, rope=True, rows_per_batch=28736)
+    gemm_case("ma.ca_k  459776x256x64 rope axial", 459776, 256, 64, rope="axial", rows_per_batch=28736)
+    gemm_case("ma.sa_qkv 65536x768x256 rope axial", 65536, 768, 256, rope="axial")
     gemm_case("ma.ca_k  459776x256x64 norope", 459776, 256, 64)
     gemm_case("ma.ff1   65536x2048x256 relu", 65536, 2048, 256, act=1)
     gemm_case("ma.ff2   65536x256x2048 +res", 65536, 256, 2048, out="f32", res=True)
