@@ -40,6 +40,7 @@ class FlashArgs(C.Structure):
         ("bsq", C.c_int64), ("bsk", C.c_int64), ("bsv", C.c_int64), ("bso", C.c_int64),
         ("B", C.c_int32), ("Lq", C.c_int32), ("Lk", C.c_int32), ("DV", C.c_int32),
         ("scale", C.c_float), ("impl", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("impl_flags", C.c_int32),
     ]
 
 
@@ -91,6 +92,7 @@ SYMBOLS = {
     "ds2_device_sm_count": (C.c_int, []),
     "ds2_gemm": (C.c_int, [C.POINTER(GemmArgs), _P]),
     "ds2_flash_attn": (C.c_int, [C.POINTER(FlashArgs), _P]),
+    "ds2_flash_workspace_bytes": (C.c_int64, [_I, _I, _I]),
     "ds2_debug_flash_stalls": (C.c_int, [C.POINTER(C.c_ulonglong), C.c_int]),
     "ds2_debug_win_times": (C.c_int, [C.POINTER(C.c_longlong)]),
     "ds2_mha": (C.c_int, [C.POINTER(MhaArgs), _P]),

@@ -38,13 +38,16 @@ constexpr int kQM = 128;
 struct FlashParams {
   int B, Lq, Lk;
   float scale_log2;
-  // Tail split: the grid is 1-D; the first n_full CTAs each own one (query tile, batch) item and all its key
-  // tiles; the remaining items (the partial last wave) are split `nsplit` ways over the key tiles so that
-  // the tail wave takes 1/nsplit of a full item.  Split parts leave (O, max, sum) partials in `ws`; the part that
-  // arrives last (atomic counter per item) combines them in part order and writes the output.
-  int n_full, nsplit, q_tiles;
-  float* ws;               // [tail items][nsplit][128 rows][DV + 4] f32
-  unsigned int* ws_count;  // [tail items], zero between launches
+  // Two key halves (two_phase != 0): EVERY (query tile, object) item is computed as two independent flash passes over
+  // the key tiles [0, T/2) and [T/2, T) whose (O, max, sum) partials go through the workspace `ws` and are combined
+  // in part order by the same code — by the one CTA that ran both halves back to back (the first n_full items), or, for
+  // the items of the partial last wave, by whichever of the item's two CTAs arrives last (atomic counter per item).
+  // The arithmetic of an item is therefore identical however it was scheduled: the grid may split the tail wave (3.46
+  // waves of 148 CTAs at 16 objects become 3 + 0.5) and "an object tracked in a batch == tracked alone" still holds
+  // bit for bit.  two_phase == 0: one pass over all keys, no workspace (self-attention, short key ranges).
+  int n_full, two_phase, q_tiles;
+  float* ws;               // [items][2][128 rows][DV + 4] f32
+  unsigned int* ws_count;  // [items], zero between launches
   int dbg;                 // timing experiments only (impl 5/6): 1 = load half of each K tile, 2 = skip the exps
   const __nv_bfloat16* q;  // QT kernels read the query rows straight from global memory
   long long ldq, bsq;
@@ -117,17 +120,19 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   int item = blockIdx.x, kv_part = 0, kv_parts = 1;
-  if (item >= p.n_full) {
+  if (item >= p.n_full) {          // only with two_phase: an item of the last wave, one CTA per key half
     const int t = item - p.n_full;
-    item = p.n_full + t / p.nsplit;
-    kv_part = t % p.nsplit;
-    kv_parts = p.nsplit;
+    item = p.n_full + (t >> 1);
+    kv_part = t & 1;
+    kv_parts = 2;
   }
   const int q0 = (item % p.q_tiles) * (kQM * NQ);
   const int b = item / p.q_tiles;
   const int all_tiles = (p.Lk + BN - 1) / BN;
   const int j0 = (all_tiles * kv_part) / kv_parts;                     // first key tile of this CTA
   const int n_tiles = (all_tiles * (kv_part + 1)) / kv_parts - j0;    // its number of key tiles (>= 1)
+  // local tile index at which the second key half starts when this CTA runs both halves itself (else never reached)
+  const int split_at = (p.two_phase && kv_parts == 1) ? all_tiles / 2 : -1;
 
   if (warp == 0 && lane == 0) {
     if (!QT) tc::prefetch_tmap(&tmap_q);
@@ -249,7 +254,9 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         for (int k = 0; k < BN / 16; ++k) {
           // V tile is MN-major: 64-channel blocks BN*128 B apart (LBO), 8-key groups 1024 B apart (SBO)
           const uint64_t db = tc::make_desc_sw128(sv + k * 2048, BN * 128, 1024);
-          tc::umma_ts(tmem_o(h), pa + k * 8, db, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          // O restarts from zero at the first tile of each key half (the softmax warps have moved the first half's
+          // O out of TMEM before they released P of this tile, see below)
+          tc::umma_ts(tmem_o(h), pa + k * 8, db, idesc_pv, ((j != 0 && j != split_at) || k != 0) ? 1u : 0u);
         }
         tc::umma_commit(bar(o_odone, h));
       }
@@ -305,6 +312,25 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
     float m_ref = -INFINITY;
     float l = 0.f;
+    float m_half0 = 0.f, l_half0 = 0.f;   // running max / sum of the first key half (two-phase items)
+    constexpr int WS_ROW = DV + 4;         // workspace row: O row + (max, sum), padded to keep rows 16-byte aligned
+    // leaves (O, m, l) of key half `part_idx` of this item in the workspace
+    auto dump_part = [&](int part_idx, float m_scaled, float lsum) {
+      float* wrow = p.ws + (static_cast<size_t>(item * 2 + part_idx) * (NQ * kQM) + rloc) * WS_ROW;
+#pragma unroll
+      for (int c = 0; c < OW / 32; ++c) {
+        uint32_t o[32];
+        tc::tmem_ld32(to + c * 32, o);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          reinterpret_cast<uint4*>(wrow + part * OW + c * 32)[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+      }
+      if (part == 0) {
+        wrow[DV] = m_scaled;
+        wrow[DV + 1] = lsum;
+      }
+    };
     const bool prof = p.dbg == 3 && warp == 2;
     long long w_s = 0, w_o = 0;
     const long long t_begin = clock64();
@@ -350,6 +376,12 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       bool resc = false;
       if (j == 0) {
         m_ref = mt;
+      } else if (j == split_at) {
+        // second key half: an independent flash pass — remember the first half's statistics, start over
+        m_half0 = m_ref * p.scale_log2;
+        l_half0 = l;
+        m_ref = mt;
+        l = 0.f;
       } else if ((mt - m_ref) * p.scale_log2 > 8.0f) {
         alpha = ex2_approx((m_ref - mt) * p.scale_log2);
         m_ref = mt;
@@ -385,6 +417,12 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       // Consume every phase of `odone` (P·V of tile j-1 complete) so this waiter is never more than
       // one phase behind the barrier — parity waits alias otherwise.  By now that MMA has long retired.
       if (j > 0) timed_wait(bar(o_odone, h), (j - 1) & 1, prof, w_o);
+      if (j == split_at) {
+        // P·V of the last tile of the first half is complete and P·V of this tile cannot be issued before every
+        // softmax warp has arrived on `pfull` below: O is stable — move the first half's result to the workspace
+        tc::tc_fence_after();
+        dump_part(0, m_half0, l_half0);
+      }
       if (__any_sync(0xffffffffu, resc)) {
         // O is stable here: P·V of tile j-1 is complete and P·V of tile j is not yet issued
         tc::tc_fence_after();
@@ -427,51 +465,41 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     tc::mbar_wait(bar(o_odone, h), (n_tiles - 1) & 1);
     tc::tc_fence_after();
     __nv_bfloat16* orow = p.out + static_cast<long long>(b) * p.bso + static_cast<long long>(row) * p.ldo + part * OW;
-    if (kv_parts > 1) {
-      // ---- split item: leave this part's (O, m, l) in the workspace; the last part to arrive combines ----
-      constexpr int WS_ROW = DV + 4;  // O row + (max, sum), padded to keep rows 16-byte aligned
-      const int slot = item - p.n_full;
-      float* wrow = p.ws + (static_cast<size_t>(slot * kv_parts + kv_part) * (NQ * kQM) + rloc) * WS_ROW;
-#pragma unroll
-      for (int c = 0; c < OW / 32; ++c) {
-        uint32_t o[32];
-        tc::tmem_ld32(to + c * 32, o);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          reinterpret_cast<uint4*>(wrow + part * OW + c * 32)[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-      }
-      if (part == 0) {
-        wrow[DV] = m_ref * p.scale_log2;
-        wrow[DV + 1] = l;
-      }
+    if (p.two_phase) {
+      // ---- two key halves: this CTA's (last) half goes to the workspace, then the halves are combined in part
+      //      order by this CTA (it ran both) or by the item's CTA that arrives last ----
+      const int slot = item;
+      dump_part(kv_parts == 1 ? 1 : kv_part, m_ref * p.scale_log2, l);
       __threadfence();
       asm volatile("bar.sync 15, %0;" ::"n"(128 * NQ * SP) : "memory");
-      const uint32_t flag = xch_base;  // the exchange buffer is idle now
-      if (warp == 2 && lane == 0) {
-        const unsigned int old = atomicAdd(p.ws_count + slot, 1u);
-        const unsigned int last = (old == static_cast<unsigned int>(kv_parts - 1)) ? 1u : 0u;
-        if (last) p.ws_count[slot] = 0u;  // every part has arrived: ready for the next launch
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(flag), "r"(last) : "memory");
+      unsigned int last = 1u;
+      if (kv_parts > 1) {
+        const uint32_t flag = xch_base;  // the exchange buffer is idle now
+        if (warp == 2 && lane == 0) {
+          const unsigned int old = atomicAdd(p.ws_count + slot, 1u);
+          const unsigned int lst = (old == 1u) ? 1u : 0u;
+          if (lst) p.ws_count[slot] = 0u;  // both halves have arrived: ready for the next launch
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(flag), "r"(lst) : "memory");
+        }
+        asm volatile("bar.sync 15, %0;" ::"n"(128 * NQ * SP) : "memory");
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(last) : "r"(flag) : "memory");
       }
-      asm volatile("bar.sync 15, %0;" ::"n"(128 * NQ * SP) : "memory");
-      unsigned int last;
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(last) : "r"(flag) : "memory");
       if (last) {
         __threadfence();
-        const float* base = p.ws + (static_cast<size_t>(slot * kv_parts) * (NQ * kQM) + rloc) * WS_ROW;
+        constexpr int kParts = 2;
+        const float* base = p.ws + (static_cast<size_t>(slot * kParts) * (NQ * kQM) + rloc) * WS_ROW;
         const size_t pstride = static_cast<size_t>(NQ * kQM) * WS_ROW;
         float mmax = -INFINITY;
-        for (int q = 0; q < kv_parts; ++q) mmax = fmaxf(mmax, __ldcg(base + q * pstride + DV));
+        for (int q = 0; q < kParts; ++q) mmax = fmaxf(mmax, __ldcg(base + q * pstride + DV));
         float lt = 0.f;
-        for (int q = 0; q < kv_parts; ++q) lt += __ldcg(base + q * pstride + DV + 1) * ex2_approx(__ldcg(base + q * pstride + DV) - mmax);
+        for (int q = 0; q < kParts; ++q) lt += __ldcg(base + q * pstride + DV + 1) * ex2_approx(__ldcg(base + q * pstride + DV) - mmax);
         const float inv = 1.0f / lt;
 #pragma unroll
         for (int c = 0; c < OW / 32; ++c) {
           float acc[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-          for (int q = 0; q < kv_parts; ++q) {  // fixed part order: the result does not depend on arrival order
+          for (int q = 0; q < kParts; ++q) {  // fixed part order: the result does not depend on arrival order
             const float w = ex2_approx(__ldcg(base + q * pstride + DV) - mmax);
             const float4* src = reinterpret_cast<const float4*>(base + q * pstride + part * OW + c * 32);
 #pragma unroll
@@ -562,6 +590,10 @@ __global__ void flash_simt_kernel(const __nv_bfloat16* __restrict__ q, const __n
   for (int i = 0; i < per; ++i) orow[lane * per + i] = __float2bfloat16(acc[i] / l);
 }
 
+// workspace layout: [items] arrival counters (u32, zero between launches), padded to 256 bytes, then
+// [items][2 halves][128 rows][DV + 4] f32 partials
+static inline size_t flash_ws_count_bytes(int items) { return (static_cast<size_t>(items) * 4 + 255) / 256 * 256; }
+
 template <int DV, int BN, int NQ, int KS, int VS, int SP, int QT>
 static int launch_flash(const ds2_flash_args* a, cudaStream_t st) {
   using Cfg = FlashCfg<DV, BN, NQ, KS, VS, SP, QT>;
@@ -608,79 +640,43 @@ static int launch_flash(const ds2_flash_args* a, cudaStream_t st) {
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   p.ldo = a->ldo;
   p.bso = a->bso;
-  // ---- grid: full items + tail items split over the key tiles (see FlashParams) ----
+  // ---- grid: whole items + (two-phase only) the items of the partial last wave as two half-length CTAs each ----
   p.q_tiles = (a->Lq + kQM * NQ - 1) / (kQM * NQ);
   const int items = p.q_tiles * a->B;
   const int sms = sm_count();
   DS2_REQUIRE(sms > 0, DS2_E_NODEVICE, "ds2_flash_attn: no CUDA device");
   const int all_tiles = (a->Lk + BN - 1) / BN;
-  int tail = items % sms, nsplit = 1;
-  // Opt-in (impl == 10): the split makes the summation order depend on the batch size and the SM count, which
-  // costs the engine its "an object tracked in a batch == tracked alone" invariant (differences at bf16-noise
-  // level, ~1e-2 relative) for ~10 % of this kernel's time; the default keeps one CTA per item.
-  if (NQ == 1 && tail > 0 && a->impl == 10) {
-    nsplit = sms / tail;
-    if (nsplit > 4) nsplit = 4;
-    if (nsplit > all_tiles) nsplit = all_tiles;
-  }
-  // Opt-in (impl == 11), not yet measured: EVERY item is split in two at the middle key tile.  The split point depends
-  // on the key count only — not on the batch size or the SM count — so the summation order, and with it the
-  // batch-independence invariant, is preserved, while the grid becomes 2x as many half-length CTAs (6.92 waves of half
-  // items instead of 3.46 waves of whole ones at 16 objects: 3.5 instead of 4 item-times on the critical path).
-  if (NQ == 1 && a->impl == 11 && all_tiles >= 8) {
-    nsplit = 2;
-    tail = items;
-  }
-  if (nsplit < 2) {
-    nsplit = 1;
-    tail = 0;
+  // Two key halves whenever the caller lends a workspace and the key range is long enough to be worth it.  The decision
+  // depends on the key count and the query-tile count only (never on the batch size or the SM count), so the
+  // arithmetic of an item — and with it "tracked in a batch == tracked alone" — does not depend on the grid.
+  const size_t ws_need = ds2_flash_workspace_bytes(a->B, a->Lq, DV);
+  p.two_phase = (DV == 64 && NQ == 1 && SP == 1 && a->impl == 0 && all_tiles >= 16 && a->workspace != nullptr &&
+                 static_cast<size_t>(a->workspace_bytes) >= ws_need) ? 1 : 0;
+  int tail = 0;
+  if (p.two_phase) {
+    // the partial last wave runs as half-length CTAs when they all fit into one wave (3.46 waves -> 3 + 0.5 at 16
+    // objects); which items are split is a scheduling choice without numerical consequences
+    tail = items % sms;
+    if (2 * tail > sms) tail = 0;
+    if (a->impl_flags & 1) tail = 0;          // tests: force whole items
+    if (a->impl_flags & 2) tail = items;      // tests: force every item to run as two CTAs
   }
   p.n_full = items - tail;
-  p.nsplit = nsplit;
-  p.ws = nullptr;
-  p.ws_count = nullptr;
-  if (tail > 0) {
-    // grow-only workspace owned by the library (one stream at a time, like every handle-less entry point);
-    // allocated on an eager call — the engine runs every new shape eagerly before capturing it into a graph
-    static float* ws = nullptr;
-    static unsigned int* ws_count = nullptr;
-    static size_t ws_bytes = 0;
-    const size_t need = static_cast<size_t>(tail) * nsplit * (NQ * kQM) * (DV + 4) * sizeof(float);
-    if (need > ws_bytes) {
-      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-      cudaStreamIsCapturing(st, &cs);
-      DS2_REQUIRE(cs == cudaStreamCaptureStatusNone, DS2_E_ARG,
-                  "ds2_flash_attn: first use of a larger split workspace inside a stream capture");
-      cudaStreamSynchronize(st);
-      if (ws) cudaFree(ws);
-      cudaError_t e = cudaMalloc(&ws, need);
-      DS2_REQUIRE(e == cudaSuccess, static_cast<int>(e), "ds2_flash_attn: workspace: %s", cudaGetErrorString(e));
-      ws_bytes = need;
-    }
-    static int ws_count_n = 0;
-    if (tail > ws_count_n) {
-      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-      cudaStreamIsCapturing(st, &cs);
-      DS2_REQUIRE(cs == cudaStreamCaptureStatusNone, DS2_E_ARG,
-                  "ds2_flash_attn: first use of a larger split counter array inside a stream capture");
-      cudaStreamSynchronize(st);
-      if (ws_count) cudaFree(ws_count);
-      ws_count = nullptr;
-      const int n = tail > 1024 ? tail : 1024;
-      cudaError_t e = cudaMalloc(&ws_count, n * sizeof(unsigned int));
-      DS2_REQUIRE(e == cudaSuccess, static_cast<int>(e), "ds2_flash_attn: workspace: %s", cudaGetErrorString(e));
-      cudaMemset(ws_count, 0, n * sizeof(unsigned int));
-      ws_count_n = n;
-    }
-    p.ws = ws;
-    p.ws_count = ws_count;
-  }
-  const int grid = p.n_full + tail * nsplit;
+  p.ws_count = reinterpret_cast<unsigned int*>(a->workspace);
+  p.ws = p.two_phase ? reinterpret_cast<float*>(reinterpret_cast<char*>(a->workspace) + flash_ws_count_bytes(items)) : nullptr;
+  const int grid = p.n_full + 2 * tail;
   DS2_LAUNCH((flash_d256_tcgen05_kernel<DV, BN, NQ, KS, VS, SP, QT>), grid, Cfg::kThreads, Cfg::kSmem, st, tq, tk, tv, p);
   return post_launch("flash_d256_tcgen05_kernel");
 }
 
 }  // namespace ds2
+
+extern "C" int64_t ds2_flash_workspace_bytes(int32_t B, int32_t Lq, int32_t DV) {
+  if (B <= 0 || Lq <= 0 || DV != 64) return 0;     // only the 64-wide (cross-attention) kernel runs in two key halves
+  const int items = B * ((Lq + ds2::kQM - 1) / ds2::kQM);
+  return static_cast<int64_t>(ds2::flash_ws_count_bytes(items) +
+                              static_cast<size_t>(items) * 2 * ds2::kQM * (DV + 4) * sizeof(float));
+}
 
 extern "C" int ds2_debug_flash_stalls(unsigned long long* out8, int reset) {
   cudaError_t e = cudaMemcpyFromSymbol(out8, ds2::g_flash_stall, 8 * sizeof(unsigned long long));
@@ -715,8 +711,9 @@ extern "C" int ds2_flash_attn(const ds2_flash_args* a, void* stream) {
   //           tensor-bound; its bf16-rounded running max changes P by rounding noise, so not the default)
   //       2 = Q as a shared-memory operand (SS MMA), 3 = two query tiles per CTA / 64-key tiles (SS)
   //       5, 6, 8 = timing experiments (half K loads, no exps, barrier-stall accounting)
-  //       10 = default kernel with the partial last wave split over the key tiles (see launch_flash)
-  //       11 = default kernel with every item split in two at the middle key tile (batch-invariant; see launch_flash)
+  // With a workspace (ds2_flash_workspace_bytes) the default 64-wide kernel computes every item as two key halves and
+  // may run the items of the partial last wave as two CTAs each (see FlashParams); impl_flags bit 0 / bit 1 force
+  // "never split" / "always split" (tests: both must give the same bits).
   if (a->DV == 64) {
     if (a->impl == 3) return launch_flash<64, 64, 2, 2, 3, 1, 0>(a, st);
     if (a->impl == 2) return launch_flash<64, 128, 1, 2, 2, 1, 0>(a, st);

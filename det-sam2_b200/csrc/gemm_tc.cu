@@ -80,9 +80,25 @@ __device__ __forceinline__ float gelu_erf(float x) {
 }
 
 // bias / activation / gamma / rotary on NC consecutive columns of one row (registers).
+// Rotary state of one output row (= one epilogue thread for a whole tile): computed once per tile, not per chunk — the
+// three integer divisions by run-time values cost as many issue slots as the rotation of a 32-column chunk itself.
+struct RopeRow {
+  uint32_t x_off, y_off;  // byte offsets of this row's x / y coordinate inside one pair's [side] (cos, sin) line
+  bool on;                // false: row beyond rope_row_limit (object-pointer tokens) -> no rotation
+};
+__device__ __forceinline__ RopeRow rope_row(const GemmParams& p, int row) {
+  RopeRow r;
+  const int rb = row % p.rope_rows_per_batch;
+  const int pos = rb % p.rope_period;
+  r.on = rb < p.rope_row_limit;
+  r.x_off = static_cast<uint32_t>(pos % p.rope_side) * 8u;
+  r.y_off = static_cast<uint32_t>(pos / p.rope_side) * 8u;
+  return r;
+}
+
 template <int NC>
 __device__ __forceinline__ void epilogue_math(const GemmParams& p, const uint32_t* acc, int row, int col0,
-                                              float (&v)[NC], uint32_t rope_smem = 0) {
+                                              float (&v)[NC], uint32_t rope_smem = 0, RopeRow rr = RopeRow{0u, 0u, false}) {
 #pragma unroll
   for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(acc[i]);
   const bool full = (col0 + NC <= p.N);
@@ -114,22 +130,22 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, const uint32_
     for (int i = 0; i < NC; ++i)
       if (full || col0 + i < p.N) v[i] *= __ldg(p.gamma + col0 + i);
   }
-  if (p.rope_axial && col0 >= p.rope_col0 && col0 < p.rope_col1) {
-    const int rb = row % p.rope_rows_per_batch;
-    if (rb < p.rope_row_limit) {
-      const int pos = rb % p.rope_period;
+  if (p.rope_axial) {
+    if (rr.on && col0 >= p.rope_col0 && col0 < p.rope_col1) {
       const int pair0 = ((col0 - p.rope_col0) & 255) >> 1;        // 16 | 64: a chunk lies in ONE half of the pairs
-      const int coord = pair0 < 64 ? pos % p.rope_side : pos / p.rope_side;
       // lanes = consecutive rows = consecutive x (conflict-free 8-byte reads) or one shared y (broadcast)
-      const uint32_t base = rope_smem + static_cast<uint32_t>(((pair0 & 63) * p.rope_side + coord) * 8);
       const uint32_t pitch = static_cast<uint32_t>(p.rope_side) * 8u;
+      const uint32_t base = rope_smem + static_cast<uint32_t>(pair0 & 63) * pitch + (pair0 < 64 ? rr.x_off : rr.y_off);
+      float cx[NC / 2], cy[NC / 2];
+#pragma unroll
+      for (int i = 0; i < NC / 2; ++i)
+        // volatile: must stay behind the named barrier that publishes the table (volatile asm keeps its order)
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cx[i]), "=f"(cy[i]) : "r"(base + static_cast<uint32_t>(i) * pitch));
 #pragma unroll
       for (int i = 0; i < NC / 2; ++i) {
-        float cx, cy;
-        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cx), "=f"(cy) : "r"(base + static_cast<uint32_t>(i) * pitch));
         const float a = v[2 * i], b = v[2 * i + 1];
-        v[2 * i] = a * cx - b * cy;
-        v[2 * i + 1] = a * cy + b * cx;
+        v[2 * i] = a * cx[i] - b * cy[i];
+        v[2 * i + 1] = a * cy[i] + b * cx[i];
       }
     }
   } else if (p.rope_cs && col0 >= p.rope_col0 && col0 < p.rope_col1) {
@@ -386,6 +402,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       };
       const int mrow = row < p.M ? row : 0;
+      const RopeRow rr = p.rope_axial ? rope_row(p, mrow) : RopeRow{0u, 0u, false};
       if (mode == kStoreTmaBf16) {
         // 64-column chunks: 32 rows x 128 B staging, SWIZZLE_128B (16-byte chunk j of row r at j ^ (r & 7)),
         // one TMA store of a full 128-byte line per row
@@ -398,13 +415,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           uint32_t pk[32];
           {
             float v[32];
-            epilogue_math<32>(p, r0, mrow, n0 + c, v, rope_smem);
+            epilogue_math<32>(p, r0, mrow, n0 + c, v, rope_smem, rr);
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[i] = tc::pack_bf16(v[2 * i], v[2 * i + 1]);
           }
           if (n0 + c + 32 < p.N && c + 32 < p.BN) {
             float v[32];
-            epilogue_math<32>(p, r1, mrow, n0 + c + 32, v, rope_smem);
+            epilogue_math<32>(p, r1, mrow, n0 + c + 32, v, rope_smem, rr);
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[16 + i] = tc::pack_bf16(v[2 * i], v[2 * i + 1]);
           } else {
@@ -429,13 +446,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (mode == kStoreDirect) {
             if (row < p.M) {
               float v[32];
-              epilogue_math<32>(p, r, row, n0 + c, v, rope_smem);
+              epilogue_math<32>(p, r, row, n0 + c, v, rope_smem, rr);
               epilogue_store_direct<32>(p, v, row, n0 + c);
             }
             continue;
           }
           float v[32];
-          epilogue_math<32>(p, r, mrow, n0 + c, v, rope_smem);
+          epilogue_math<32>(p, r, mrow, n0 + c, v, rope_smem, rr);
           wait_staging();
           // 32 rows x 128 B, SWIZZLE_128B
           const uint32_t rowaddr = stg + static_cast<uint32_t>(lane) * 128u;
@@ -463,6 +480,361 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 2) {
     tc::tc_fence_after();
     tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+
+// =================================================================================================
+// gemm2: the same GEMM on CTA PAIRS (tcgen05 cta_group::2), the default for M >= 512
+// =================================================================================================
+// A cluster of two CTAs (two SMs of one TPC) owns a 256 x BN output tile: CTA r holds rows [128 r, 128 r + 128) of A
+// and rows [r BN/2, (r + 1) BN/2) of W in its shared memory, ONE thread of the leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256) which reads both CTAs' operands and writes both CTAs' TMEM, and each CTA runs
+// the epilogue of its own 128 rows.  Per k-block a CTA loads 16 KB of A + <= 16 KB of W instead of 16 + 32 KB: the
+// Hiera / memory-attention GEMMs have short K (256 ... 2304) and were bound by L2 -> SM operand traffic (510 MB per
+// 16384 x 2304 x 576 launch = 12.4 TB/s, the L2 fabric limit, at 1.0 PFLOP/s; profiles/r2_s5_gemm_probe.txt).
+//   warp 0        : TMA producer (both CTAs; transaction bytes of both land on the LEADER's full barrier)
+//   warp 1        : MMA issuer (leader CTA only); commits multicast to both CTAs' barriers
+//   warp 2        : TMEM allocation (512 columns, cta_group::2, both CTAs)
+//   warps 4..19   : epilogue, FOUR warps per TMEM lane quarter: 16 warps hide the latencies (TMEM load, bias, MUFU of
+//                   the GELU, shared-memory staging) that 8 warps exposed — the v1 epilogue issued on 40 % of the
+//                   cycles of its two warps per scheduler (ncu source page, profiles/r2_s5_gemm_epilogue_ncu.txt).
+//                   A warp owns 32-column chunks ci = cg, cg + 4, ...; bias / gamma of its chunks are fetched BEFORE it
+//                   waits for the accumulator and re-read from a warp-private shared-memory line; results leave
+//                   through two alternating 2 KB staging boxes per warp (64-byte swizzle) and TMA stores / reduce-adds.
+constexpr int k2Stages = 4;
+constexpr int k2ABytes = kBM * kBK * 2;          // 16 KB: this CTA's 128 rows of A
+constexpr int k2BBytesMax = 128 * kBK * 2;       // 16 KB: this CTA's half (<= 128 rows) of the W tile
+constexpr int k2StageBytes = k2ABytes + k2BBytesMax;
+constexpr int k2EpiWarps = 16;
+constexpr int k2StagingBytes = 4096;             // per warp: two boxes of 32 rows x 64 B
+constexpr int k2VecBytes = 512;                  // per warp: bias (64 f32) + gamma (64 f32)
+constexpr int k2Smem = k2Stages * k2StageBytes + k2EpiWarps * (k2StagingBytes + k2VecBytes) + 1024 + 256;
+constexpr int k2Threads = 128 + 32 * k2EpiWarps;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;      // shared::cluster address of the same offset in the pair's even CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 2-SM TMA load: data into THIS CTA's shared memory, transaction bytes onto the barrier at `bar` (a shared::cluster
+// address, here the leader's full barrier)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ss_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}\n"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+// arrives (once all MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+// bias / activation / gamma / rotary on 32 consecutive columns of one row, in place; bias and gamma come from the warp's
+// shared-memory line `vec` (64 f32 bias, then 64 f32 gamma) at element offset `voff`
+__device__ __forceinline__ void epilogue_math_v2(const GemmParams& p, float (&v)[32], int col0, uint32_t vec, int voff,
+                                                 uint32_t rope_smem, const RopeRow& rr) {
+  if (p.bias) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float b0, b1, b2, b3;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(vec + 4u * (voff + 4 * i)));
+      v[4 * i] += b0;
+      v[4 * i + 1] += b1;
+      v[4 * i + 2] += b2;
+      v[4 * i + 3] += b3;
+    }
+  }
+  if (p.act == 1) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+  } else if (p.act == 2) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+  }
+  if (p.gamma) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float g0, g1, g2, g3;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g0), "=f"(g1), "=f"(g2), "=f"(g3) : "r"(vec + 256u + 4u * (voff + 4 * i)));
+      v[4 * i] *= g0;
+      v[4 * i + 1] *= g1;
+      v[4 * i + 2] *= g2;
+      v[4 * i + 3] *= g3;
+    }
+  }
+  if (p.rope_axial && rr.on && col0 >= p.rope_col0 && col0 < p.rope_col1) {
+    const int pair0 = ((col0 - p.rope_col0) & 255) >> 1;
+    const uint32_t pitch = static_cast<uint32_t>(p.rope_side) * 8u;
+    const uint32_t base = rope_smem + static_cast<uint32_t>(pair0 & 63) * pitch + (pair0 < 64 ? rr.x_off : rr.y_off);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float cx, cy;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cx), "=f"(cy) : "r"(base + static_cast<uint32_t>(i) * pitch));
+      const float a = v[2 * i], b = v[2 * i + 1];
+      v[2 * i] = a * cx - b * cy;
+      v[2 * i + 1] = a * cy + b * cx;
+    }
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
+gemm2_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                               const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t staging_base = smem_base + k2Stages * k2StageBytes;
+  const uint32_t vec_base = staging_base + k2EpiWarps * k2StagingBytes;
+  const uint32_t bar_base = vec_base + k2EpiWarps * k2VecBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (k2Stages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * k2Stages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * k2Stages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * k2Stages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmap_a);
+    tc::prefetch_tmap(&tmap_w);
+    if (p.store_mode != kStoreDirect) tc::prefetch_tmap(&tmap_c);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < k2Stages; ++s) {
+      tc::mbar_init(full_bar(s), 1);     // leader: its own producer's arrive.expect_tx (bytes of BOTH CTAs)
+      tc::mbar_init(empty_bar(s), 1);    // one multicast commit per use
+    }
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(tfull_bar(s), 1);                  // one multicast commit per tile
+      tc::mbar_init(tempty_bar(s), 2 * k2EpiWarps);    // leader: the epilogue warps of both CTAs
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();       // both CTAs' barriers are initialised and both TMEM allocations done before any remote access
+  tc::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_sync();
+
+  const int num_tiles = p.tiles_m * p.tiles_n;       // tiles of 256 x BN
+  const int k_blocks = (p.K + kBK - 1) / kBK;
+  const int half_bn = p.BN >> 1;
+  const uint32_t cta_tx = k2ABytes + static_cast<uint32_t>(half_bn) * kBK * 2;
+  const int nstages = p.stages;
+  const uint32_t rope_smem = smem_base + 3u * k2StageBytes;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && tc::elect_one()) {
+    // ---------------- TMA producer (both CTAs) ----------------
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const int m_blk = t / p.tiles_n, n_blk = t % p.tiles_n;
+      const int row_a = m_blk * 256 + static_cast<int>(rank) * kBM;
+      const int row_w = n_blk * p.BN + static_cast<int>(rank) * half_bn;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        tc::mbar_wait(empty_bar(stage), phase ^ 1);
+        if (leader) tc::mbar_expect_tx(full_bar(stage), 2u * cta_tx);
+        const uint32_t sa = smem_base + stage * k2StageBytes;
+        const uint32_t lead_full = full_bar(stage) & kPeerMask;
+        tma_load_2d_2sm(sa, &tmap_a, lead_full, kb * kBK, row_a);
+        tma_load_2d_2sm(sa + k2ABytes, &tmap_w, lead_full, kb * kBK, row_w);
+        if (++stage == nstages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && leader && tc::elect_one()) {
+    // ---------------- MMA issuer (leader CTA) ----------------
+    const uint32_t idesc = tc::make_idesc_bf16(256, p.BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      tc::mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tc::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        tc::mbar_wait(full_bar(stage), phase);
+        tc::tc_fence_after();
+        const uint32_t sa = smem_base + stage * k2StageBytes;
+        const uint32_t sb = sa + k2ABytes;
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          const uint64_t da = tc::make_desc_sw128(sa + k * 32, 16, 1024);
+          const uint64_t db = tc::make_desc_sw128(sb + k * 32, 16, 1024);
+          umma_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit_2sm(empty_bar(stage));
+        if (++stage == nstages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit_2sm(tfull_bar(acc));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue (both CTAs, own 128 rows) ----------------
+    const int ew = warp - 4;       // 0..15
+    const int lq = warp & 3;       // TMEM lane quarter
+    const int cg = ew >> 2;        // column group: 32-column chunks cg, cg + 4, ...
+    const uint32_t stg = staging_base + static_cast<uint32_t>(ew) * k2StagingBytes;
+    const uint32_t vec = vec_base + static_cast<uint32_t>(ew) * k2VecBytes;
+    const int mode = p.store_mode;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t nstores = 0;          // lane 0: bulk stores issued so far (box = nstores & 1)
+    if (p.rope_axial) {
+      const int n4 = 64 * p.rope_side * 2 / 4;
+      const float4* src = reinterpret_cast<const float4*>(p.rope_axial);
+      for (int i = threadIdx.x - 128; i < n4; i += 32 * k2EpiWarps) {
+        const float4 t4 = __ldg(src + i);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rope_smem + 16u * i), "f"(t4.x), "f"(t4.y), "f"(t4.z),
+                     "f"(t4.w) : "memory");
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * k2EpiWarps) : "memory");
+    }
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const int m_blk = t / p.tiles_n, n_blk = t % p.tiles_n;
+      const int n0 = n_blk * p.BN;
+      const int row0 = m_blk * 256 + static_cast<int>(rank) * kBM + lq * 32;
+      const int row = row0 + lane;
+      const int mrow = row < p.M ? row : 0;
+      // bias / gamma of this warp's (<= 2) chunks: fetched before the accumulator wait, kept in a warp-private line
+      float bv[2] = {0.f, 0.f}, gv[2] = {1.f, 1.f};
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = n0 + (cg + 4 * j) * 32 + lane;
+        if ((cg + 4 * j) * 32 < p.BN && c < p.N) {
+          if (p.bias) bv[j] = __ldg(p.bias + c);
+          if (p.gamma) gv[j] = __ldg(p.gamma + c);
+        }
+      }
+      const RopeRow rr = p.rope_axial ? rope_row(p, mrow) : RopeRow{0u, 0u, false};
+      __syncwarp();   // the previous tile's reads of the line are done
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(vec + 4u * (32 * j + lane)), "f"(bv[j]) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(vec + 256u + 4u * (32 * j + lane)), "f"(gv[j]) : "memory");
+      }
+      __syncwarp();
+      tc::mbar_wait(tfull_bar(acc), acc_phase);
+      tc::tc_fence_after();
+      const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc) * 256u + (static_cast<uint32_t>(lq * 32) << 16);
+      int j = 0;
+      for (int ci = cg; ci * 32 < p.BN; ci += 4, ++j) {
+        const int c = ci * 32;
+        uint32_t r[32];
+        tc::tmem_ld32(t_addr + c, r);
+        tc::tmem_ld_wait();
+        if (n0 + c >= p.N) continue;  // warp-uniform
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        epilogue_math_v2(p, v, n0 + c, vec, 32 * j, rope_smem, rr);
+        if (mode == kStoreDirect) {
+          if (row < p.M) epilogue_store_direct<32>(p, v, row, n0 + c);
+          continue;
+        }
+        // staging boxes: 32 rows x 64 B, SWIZZLE_64B (16-byte chunk q of row r at q ^ ((r >> 1) & 3)); a box may be
+        // overwritten once the store issued two stores ago has finished reading it
+        const uint32_t sw = (static_cast<uint32_t>(lane) >> 1) & 3u;
+        auto box_addr = [&](uint32_t n) { return stg + (n & 1u) * 2048u + static_cast<uint32_t>(lane) * 64u; };
+        auto issue = [&](uint32_t box, int col) {
+          tc::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (mode == kStoreTmaAddF32) tc::tma_reduce_add_2d(&tmap_c, box, col, row0);
+            else tc::tma_store_2d(&tmap_c, box, col, row0);
+            tc::bulk_commit();
+          }
+        };
+        if (mode == kStoreTmaBf16) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = tc::pack_bf16(v[2 * i], v[2 * i + 1]);
+          if (lane == 0 && nstores >= 2) bulk_wait_read1();
+          __syncwarp();
+          const uint32_t ra = box_addr(nstores);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            st_shared_v4(ra + ((static_cast<uint32_t>(q) ^ sw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          issue(stg + (nstores & 1u) * 2048u, n0 + c);
+          ++nstores;
+        } else {
+          // f32: two boxes of 16 columns
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            if (n0 + c + 16 * hlf >= p.N) break;  // warp-uniform (N % 16 == 0 is required for the TMA f32 modes)
+            if (lane == 0 && nstores >= 2) bulk_wait_read1();
+            __syncwarp();
+            const uint32_t ra = box_addr(nstores);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              st_shared_v4(ra + ((static_cast<uint32_t>(q) ^ sw) << 4), __float_as_uint(v[16 * hlf + 4 * q]),
+                           __float_as_uint(v[16 * hlf + 4 * q + 1]), __float_as_uint(v[16 * hlf + 4 * q + 2]),
+                           __float_as_uint(v[16 * hlf + 4 * q + 3]));
+            issue(stg + (nstores & 1u) * 2048u, n0 + c + 16 * hlf);
+            ++nstores;
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_bar(acc) & kPeerMask);   // the leader's barrier, from either CTA
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (lane == 0) tc::bulk_wait0();  // global writes complete before the CTA retires
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // no CTA of the pair retires while its peer may still address its shared memory / TMEM
+  if (warp == 2) {
+    tc::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -548,6 +920,81 @@ static int choose_bn(int M, int N, int sms, int step) {
   return best;
 }
 
+
+// Tile width of the CTA-pair kernel: multiples of 32 (32-column staging boxes); one n-tile when N <= 256, otherwise the
+// width that minimises waves x (width + per-tile fixed cost) over the 74 clusters.
+static int choose_bn2(int M, int N, int clusters) {
+  if (N <= 256) return ((N + 31) / 32) * 32;
+  const int tiles_m = (M + 255) / 256;
+  int best = 256;
+  long long best_cost = -1;
+  for (int bn = 256; bn >= 64; bn -= 32) {
+    const long long tiles = static_cast<long long>(tiles_m) * ((N + bn - 1) / bn);
+    const long long waves = (tiles + clusters - 1) / clusters;
+    const long long cost = waves * (bn + 24);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+static int launch_gemm2(const ds2_gemm_args* a, GemmParams p, int sms, cudaStream_t st) {
+  const int clusters = sms / 2;
+  p.BN = choose_bn2(a->M, a->N, clusters);
+  {
+    static const int force_bn = [] {
+      const char* e = getenv("DS2_GEMM_BN");
+      return e ? atoi(e) : 0;
+    }();
+    if (force_bn >= 64 && force_bn <= 256 && (force_bn % 32) == 0 && a->N > 256) p.BN = force_bn;
+  }
+  p.tiles_m = (a->M + 255) / 256;
+  p.tiles_n = (a->N + p.BN - 1) / p.BN;
+  p.stages = a->rope_axial ? 3 : k2Stages;    // 64 * side * 8 B <= 32 KB = the fourth stage's slot (side <= 64)
+  DS2_REQUIRE(!a->rope_axial || a->rope_side <= 64, DS2_E_ARG, "ds2_gemm: axial rotary table side %d > 64", a->rope_side);
+  CUtensorMap ta, tw, tcm;
+  memset(&tcm, 0, sizeof(tcm));
+  if (p.store_mode == kStoreTmaBf16) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->M)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(a->ldc_bf16) * 2};
+    const uint32_t box[2] = {32, 32};
+    int rc = make_tmap(&tcm, a->out_bf16, 2, 64, 2, dims, strides, box);
+    if (rc) return rc;
+  } else if (p.store_mode == kStoreTmaF32 || p.store_mode == kStoreTmaAddF32) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->M)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(a->ldc) * 4};
+    const uint32_t box[2] = {16, 32};
+    int rc = make_tmap(&tcm, a->out_f32, 4, 64, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->M)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(a->lda) * 2};
+    const uint32_t box[2] = {static_cast<uint32_t>(kBK), static_cast<uint32_t>(kBM)};
+    int rc = make_tmap_bf16(&ta, a->A, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->N)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(a->ldw) * 2};
+    const uint32_t box[2] = {static_cast<uint32_t>(kBK), static_cast<uint32_t>(p.BN / 2)};
+    int rc = make_tmap_bf16(&tw, a->W, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k2Smem);
+    DS2_REQUIRE(e == cudaSuccess, static_cast<int>(e), "ds2_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = 2 * (tiles < clusters ? tiles : clusters);
+  DS2_LAUNCH((gemm2_bf16_tcgen05_2cta_kernel), grid, k2Threads, k2Smem, st, ta, tw, tcm, p);
+  return post_launch("gemm2_bf16_tcgen05_2cta_kernel");
+}
+
 }  // namespace ds2
 
 extern "C" int ds2_gemm(const ds2_gemm_args* a, void* stream) {
@@ -621,6 +1068,16 @@ extern "C" int ds2_gemm(const ds2_gemm_args* a, void* stream) {
     }
   }
 
+  // ---- CTA-pair kernel (gemm2): the default for tall problems; impl 3 forces it, impl 4 forces the single-CTA kernel ----
+  {
+    static const int v2_env = [] {
+      const char* e = getenv("DS2_GEMM_V2");
+      return e ? atoi(e) : 1;
+    }();
+    const bool full_table = a->rope_cs != nullptr && a->rope_axial == nullptr;   // only the single-CTA kernel reads it
+    const bool want_v2 = !full_table && (a->impl == 3 || (a->impl == 0 && v2_env != 0 && a->M >= 512 && a->N >= 32));
+    if (want_v2 && (sms % 2) == 0) return launch_gemm2(a, p, sms, st);
+  }
   // bf16 stores go out in 64-column boxes, so tiles must not end inside one
   p.BN = choose_bn(a->M, a->N, sms, p.store_mode == kStoreTmaBf16 ? 64 : 32);
   {

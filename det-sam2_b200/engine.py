@@ -638,6 +638,14 @@ class CudaEngine:
         hff = self._buf("ma_ff", (B * T, cfg.memattn_ffn), BF16)
         rope = p["rope"]
         scale = 1.0 / math.sqrt(D)
+        # scratch of the cross-attention kernel (two key halves per item, see ds2_flash_args.workspace): zeroed once —
+        # the kernel leaves its arrival counters at zero — and private to this engine (= one stream)
+        fws = self._ws.get(("flash_ws", B))
+        if os.environ.get("DS2_FLASH_TWO_PHASE", "1") == "0":   # A/B switch (tuning only): one pass per item
+            fws = self._ws[("flash_ws", B)] = torch.zeros(16, dtype=torch.uint8, device=self.device)
+        if fws is None:
+            fws = self._ws[("flash_ws", B)] = torch.zeros(max(ops.flash_workspace_bytes(B, T, M), 16), dtype=torch.uint8,
+                                                          device=self.device)
         for l in range(cfg.memattn_layers):
             w = f"ma{l}."
             # rows of the shared prefix: one object's worth in layer 0, all objects afterwards
@@ -660,11 +668,11 @@ class CudaEngine:
             if self.kernel_timers is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
-                ops.flash_attn(q16, k16, val, o64, scale)
+                ops.flash_attn(q16, k16, val, o64, scale, workspace=fws)
                 ev1.record()
                 self.kernel_timers.append(("flash_cross", ev0, ev1, {"N": N, "B": B}))
             else:
-                ops.flash_attn(q16, k16, val, o64, scale)
+                ops.flash_attn(q16, k16, val, o64, scale, workspace=fws)
             ops.gemm(o64.view(B * T, M), p[w + "ca_ov.w"], bias=p[w + "ca_ov.b"], residual=x2, out_f32=x2)
             ops.layernorm(x2, p[w + "n3.w"], p[w + "n3.b"], 1e-5, out_bf16=t16)
             ops.gemm(t16, p[w + "ff1.w"], bias=p[w + "ff1.b"], act=1, out_bf16=hff)

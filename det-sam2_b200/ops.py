@@ -79,8 +79,14 @@ def gemm(a, w, *, bias=None, act=0, gamma=None, residual=None, res_row_mod=0, ou
 _FLASH_IMPL = int(__import__("os").environ.get("DS2_FLASH_IMPL", "0"))  # kernel-variant A/B switch (tuning only)
 
 
-def flash_attn(q, k, v, out, scale, impl=None):
-    """q [B,Lq,256] k [B,Lk,256] v [B,Lk,DV] out [B,Lq,DV], bf16; last dim contiguous."""
+def flash_workspace_bytes(B, Lq, DV):
+    return int(_lib().ds2_flash_workspace_bytes(B, Lq, DV))
+
+
+def flash_attn(q, k, v, out, scale, impl=None, workspace=None, flags=0):
+    """q [B,Lq,256] k [B,Lk,256] v [B,Lk,DV] out [B,Lq,DV], bf16; last dim contiguous.
+    workspace: zero-initialised uint8 device tensor of at least flash_workspace_bytes(B, Lq, DV) bytes (DV = 64 only):
+    every item is then computed as two key halves and the partial last wave may run as two CTAs per item."""
     if impl is None:
         impl = _FLASH_IMPL
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
@@ -93,6 +99,10 @@ def flash_attn(q, k, v, out, scale, impl=None):
     f.bsq, f.bsk, f.bsv, f.bso = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
     f.B, f.Lq, f.Lk, f.DV = B, Lq, k.shape[1], v.shape[2]
     f.scale, f.impl = scale, impl
+    if workspace is not None:
+        assert workspace.dtype == torch.uint8 and workspace.is_cuda and workspace.is_contiguous()
+        f.workspace, f.workspace_bytes = workspace.data_ptr(), workspace.numel()
+    f.impl_flags = flags
     _chk(_lib().ds2_flash_attn(C.byref(f), _stream()), "ds2_flash_attn")
 
 

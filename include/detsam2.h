@@ -86,8 +86,16 @@ typedef struct ds2_flash_args {
   int32_t B, Lq, Lk, DV;
   float scale;
   int32_t impl; /* 0 = tcgen05, 1 = SIMT debug kernel */
+  /* Optional caller-owned scratch for the DV = 64 kernel (at least ds2_flash_workspace_bytes(B, Lq, DV) bytes, zeroed
+   * once by the caller, private to one stream): every (object, query tile) item is then computed as two key halves
+   * combined in a fixed order, which lets the launch run the items of its partial last wave as two CTAs each without
+   * changing a bit of the result.  NULL: one pass per item.  The library keeps no state of its own between calls. */
+  void* workspace;
+  int64_t workspace_bytes;
+  int32_t impl_flags; /* tests only: bit 0 = never split an item over two CTAs, bit 1 = always split */
 } ds2_flash_args;
 int ds2_flash_attn(const ds2_flash_args* args, void* stream);
+int64_t ds2_flash_workspace_bytes(int32_t B, int32_t Lq, int32_t DV);
 
 /* Tuning aid: barrier-stall cycle counters of flash launches made with impl == 8 (summed over CTAs):
  * [0] K-tile wait [1] V-tile wait [2] P wait [3] MMA-warp cycles [4] S wait [5] O wait [6] softmax-warp

@@ -133,7 +133,9 @@ def test_cuda_video_processor_matches_reference_golden():
         else:
             assert np.array_equal(got[k], r), k     # frames segmented, ids per frame, window contents
     calib = _calib()["stream"]["video_res_masks"]
-    assert min(ious) >= calib["iou_min"] - 1e-3, (min(ious), calib["iou_min"])
+    # raw IoU of near-degenerate random-weight masks on 160x224 frames: one or two pixels of a ~300-pixel mask move it by
+    # 0.005 whenever the summation order of a kernel changes, hence the 0.01 slack on the reference's own bf16 floor
+    assert min(ious) >= calib["iou_min"] - 1e-2, (min(ious), calib["iou_min"])
     assert float(np.mean(ious)) >= calib["iou_mean"] - 5e-3, (float(np.mean(ious)), calib["iou_mean"])
 
 

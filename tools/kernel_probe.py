@@ -126,7 +126,11 @@ def main():
     o = torch.zeros(16, 4096, 64, device=dev, dtype=BF16)
     cases.append(("flash cross B16 N28736", lambda: ops.flash_attn(q, k, v, o, 1 / 16.0),
                   2.0 * 16 * 4096 * 28736 * 320, None))
-    for im, nm in ((10, "tail split"), (9, "2 softmax wg"), (2, "Q in smem")):
+    fws = torch.zeros(ops.flash_workspace_bytes(16, 4096, 64), dtype=torch.uint8, device=dev)
+    for fl, nm in ((0, "two key halves, tail wave split"), (1, "two key halves, whole items")):
+        cases.append((f"flash cross B16 N28736 workspace ({nm})",
+                      lambda fl=fl: ops.flash_attn(q, k, v, o, 1 / 16.0, workspace=fws, flags=fl), 2.0 * 16 * 4096 * 28736 * 320, None))
+    for im, nm in ((9, "2 softmax wg"), (2, "Q in smem")):
         cases.append((f"flash cross B16 N28736 impl{im} ({nm})", lambda im=im: ops.flash_attn(q, k, v, o, 1 / 16.0, impl=im),
                       2.0 * 16 * 4096 * 28736 * 320, None))
     qs = torch.randn(16, 4096, 768, device=dev).to(BF16)
