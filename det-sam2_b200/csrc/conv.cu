@@ -10,9 +10,7 @@
 
 namespace ds2 {
 
-__device__ __forceinline__ float gelu_erf_c(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
-}
+__device__ __forceinline__ float gelu_erf_c(float x) { return gelu_erf_fast(x); }
 
 // ---- patch embedding im2col: fp16 [3,S,S] -> bf16 [(S/4)^2, Kpad], k = c*49 + ky*7 + kx ----------
 __global__ void im2col_patch_kernel(const __half* __restrict__ img, __nv_bfloat16* __restrict__ out, int S,

@@ -7,9 +7,7 @@
 
 namespace ds2 {
 
-__device__ __forceinline__ float gelu_erf_d(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
-}
+__device__ __forceinline__ float gelu_erf_d(float x) { return gelu_erf_fast(x); }
 __device__ __forceinline__ float warp_sum_d(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -171,7 +169,9 @@ __global__ void __launch_bounds__(256) mlp3_kernel(const Mlp3Params p) {
   for (int o = threadIdx.x; o < p.dout; o += blockDim.x) p.y[static_cast<long long>(item) * p.ldy + o] = yout[o];
 }
 
-// mask / token selection: one CTA per object
+// mask / token selection: blockIdx.x = object; with multimask output the choice needs no reduction over the mask, so the
+// copy of the chosen 256^2 mask is sliced over gridDim.y CTAs (one CTA per object left 132 SMs idle for 64 us); the
+// stability test of the single-mask path counts over the whole mask and keeps one CTA per object (gridDim.y == 1)
 __global__ void __launch_bounds__(256) sam_select_kernel(const float* __restrict__ all_masks,
                                                          const float* __restrict__ ious,
                                                          const float* __restrict__ obj_score,
@@ -222,15 +222,22 @@ __global__ void __launch_bounds__(256) sam_select_kernel(const float* __restrict
       idx = (stab >= thresh) ? 0 : best_multi;
     }
     s_idx = idx;
-    best_idx[b] = idx;
-    iou_out[b] = io[idx];
+    if (blockIdx.y == 0) {
+      best_idx[b] = idx;
+      iou_out[b] = io[idx];
+    }
   }
   __syncthreads();
   const int idx = s_idx;
   const bool present = obj_score[b] > 0.f;
-  const float* src = all_masks + (static_cast<long long>(b) * 4 + idx) * n;
-  float* dst = low_res + static_cast<long long>(b) * n;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) dst[i] = present ? src[i] : -1024.0f;
+  const float4* src = reinterpret_cast<const float4*>(all_masks + (static_cast<long long>(b) * 4 + idx) * n);
+  float4* dst = reinterpret_cast<float4*>(low_res + static_cast<long long>(b) * n);
+  const float4 absent = make_float4(-1024.0f, -1024.0f, -1024.0f, -1024.0f);
+  const long long n4 = n / 4;      // S is a multiple of 4 (checked by the host side)
+  for (long long i = static_cast<long long>(blockIdx.y) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.y) * blockDim.x)
+    dst[i] = present ? src[i] : absent;
+  if (blockIdx.y != 0) return;
   // object-pointer token: the matching multimask token, or token 0 in single-mask mode
   const int tok = multimask ? idx : 0;
   for (int i = threadIdx.x; i < C; i += blockDim.x)
@@ -308,7 +315,9 @@ int ds2_sam_select(const float* all_masks, const float* ious, const float* obj_s
   using namespace ds2;
   DS2_REQUIRE(all_masks && ious && obj_score && mask_tokens && low_res && iou_out && best_idx && token_out && B > 0,
               DS2_E_ARG, "ds2_sam_select: bad args");
-  DS2_LAUNCH((sam_select_kernel), B, 256, 0, as_stream(stream), all_masks, ious, obj_score, mask_tokens, B, S, C, multimask,
+  DS2_REQUIRE((S % 2) == 0, DS2_E_ARG, "ds2_sam_select: mask side %d must be even", S);
+  const dim3 grid(B, multimask ? 16 : 1);
+  DS2_LAUNCH((sam_select_kernel), grid, 256, 0, as_stream(stream), all_masks, ious, obj_score, mask_tokens, B, S, C, multimask,
                                                      stab_delta, stab_thresh, low_res, iou_out, best_idx, token_out);
   return post_launch("sam_select_kernel");
 }

@@ -11,9 +11,7 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ float gelu_erf_e(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
-}
+__device__ __forceinline__ float gelu_erf_e(float x) { return gelu_erf_fast(x); }
 
 // ---------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, row held in registers (C <= 32*MAXV), two-pass mean / variance.

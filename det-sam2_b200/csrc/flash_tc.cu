@@ -48,7 +48,8 @@ struct FlashParams {
   int n_full, two_phase, q_tiles;
   float* ws;               // [items][2][128 rows][DV + 4] f32
   unsigned int* ws_count;  // [items], zero between launches
-  int dbg;                 // timing experiments only (impl 5/6): 1 = load half of each K tile, 2 = skip the exps
+  int dbg;                 // timing experiments only (impl 5/6/12/13): 1 = load half of each K tile, 2 = skip the exps,
+                           // 4 = skip the TMEM loads of S, 5 = softmax warps only run the barrier protocol
   const __nv_bfloat16* q;  // QT kernels read the query rows straight from global memory
   long long ldq, bsq;
   __nv_bfloat16* out;
@@ -74,7 +75,8 @@ struct FlashCfg {
 // Stall accounting for tuning (impl == 8 only): cycles the MMA issuer spent blocked on each barrier class
 // and the softmax warps on theirs, summed over CTAs.  [0] kfull [1] vfull [2] pfull [3] total MMA-warp
 // cycles, [4] sfull (softmax warp 2) [5] odone [6] total softmax-warp cycles [7] CTAs.
-__device__ unsigned long long g_flash_stall[8];
+// [8..13] softmax warp 2, stage cycles: S load, row max, exp + sum + pack, P store, store wait + fence + arrive, (spare)
+__device__ unsigned long long g_flash_stall[16];
 
 __device__ __forceinline__ void timed_wait(uint32_t bar, uint32_t parity, bool on, long long& acc) {
   if (!on) {
@@ -333,18 +335,40 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     };
     const bool prof = p.dbg == 3 && warp == 2;
     long long w_s = 0, w_o = 0;
+    long long st_load = 0, st_max = 0, st_exp = 0, st_pst = 0, st_arr = 0;
     const long long t_begin = clock64();
     for (int j = 0; j < n_tiles; ++j) {
       timed_wait(bar(o_sfull, 2 * h + (j & 1)), (j >> 1) & 1, prof, w_s);
       tc::tc_fence_after();
+      long long tstage = prof ? clock64() : 0;
+      auto lap = [&](long long& accu) {
+        if (prof) {
+          const long long now = clock64();
+          accu += now - tstage;
+          tstage = now;
+        }
+      };
       const uint32_t ts = tmem_s(h, j & 1) + lane_off;
-      uint32_t sraw[CW];
-#pragma unroll
-      for (int c = 0; c < CW / 32; ++c) {
-        uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sraw[c * 32]);
-        tc::tmem_ld32(ts + part * CW + c * 32, chunk);
+      if (p.dbg == 5) {   // timing experiment: the MMA pipeline alone (results are garbage)
+        if (j > 0) tc::mbar_wait(bar(o_odone, h), (j - 1) & 1);
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(bar(o_pfull, 2 * h + (j & 1)));
+        continue;
       }
-      tc::tmem_ld_wait();
+      uint32_t sraw[CW];
+      if (p.dbg == 4) {   // timing experiment: no TMEM -> register traffic for S
+#pragma unroll
+        for (int i = 0; i < CW; ++i) sraw[i] = __float_as_uint(static_cast<float>((i * 37 + lane) & 63) * 0.125f);
+      } else {
+#pragma unroll
+        for (int c = 0; c < CW / 32; ++c) {
+          uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sraw[c * 32]);
+          tc::tmem_ld32(ts + part * CW + c * 32, chunk);
+        }
+        tc::tmem_ld_wait();
+      }
+      lap(st_load);
       const int valid = p.Lk - (j0 + j) * BN - part * CW;  // columns >= valid are TMA zero fill -> mask
       if (valid < CW) {
 #pragma unroll
@@ -372,6 +396,7 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
           mt = fmaxf(mt, __bfloat162float(__ushort_as_bfloat16(u)));
         }
       }
+      lap(st_max);
       float alpha = 1.f;
       bool resc = false;
       if (j == 0) {
@@ -403,6 +428,7 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         pk[i] = tc::pack_bf16(e0, e1);
       }
       l = l * alpha + (sum0 + sum1);
+      lap(st_exp);
       // P (bf16 pairs) overwrites the first BN/2 columns of S: this thread's part at [part*CW/2, +CW/2)
       if (CW / 2 >= 32) {
 #pragma unroll
@@ -414,6 +440,7 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const uint32_t(&chunk)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&pk[0]);
         tc::tmem_st16(ts + part * (CW / 2), chunk);
       }
+      lap(st_pst);
       // Consume every phase of `odone` (P·V of tile j-1 complete) so this waiter is never more than
       // one phase behind the barrier — parity waits alias otherwise.  By now that MMA has long retired.
       if (j > 0) timed_wait(bar(o_odone, h), (j - 1) & 1, prof, w_o);
@@ -436,12 +463,19 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
           tc::tmem_st32(to + c * 32, o);
         }
       }
+      if (prof) tstage = clock64();
       tc::tmem_st_wait();
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(bar(o_pfull, 2 * h + (j & 1)));
+      lap(st_arr);
     }
     if (prof && lane == 0) {
+      atomicAdd(&g_flash_stall[8], static_cast<unsigned long long>(st_load));
+      atomicAdd(&g_flash_stall[9], static_cast<unsigned long long>(st_max));
+      atomicAdd(&g_flash_stall[10], static_cast<unsigned long long>(st_exp));
+      atomicAdd(&g_flash_stall[11], static_cast<unsigned long long>(st_pst));
+      atomicAdd(&g_flash_stall[12], static_cast<unsigned long long>(st_arr));
       atomicAdd(&g_flash_stall[4], static_cast<unsigned long long>(w_s));
       atomicAdd(&g_flash_stall[5], static_cast<unsigned long long>(w_o));
       atomicAdd(&g_flash_stall[6], static_cast<unsigned long long>(clock64() - t_begin));
@@ -633,7 +667,7 @@ static int launch_flash(const ds2_flash_args* a, cudaStream_t st) {
   p.Lq = a->Lq;
   p.Lk = a->Lk;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  p.dbg = a->impl == 5 ? 1 : (a->impl == 6 ? 2 : (a->impl == 8 ? 3 : 0));
+  p.dbg = a->impl == 5 ? 1 : (a->impl == 6 ? 2 : (a->impl == 8 ? 3 : (a->impl == 12 ? 4 : (a->impl == 13 ? 5 : 0))));
   p.q = reinterpret_cast<const __nv_bfloat16*>(a->q);
   p.ldq = a->ldq;
   p.bsq = a->bsq;
@@ -679,9 +713,9 @@ extern "C" int64_t ds2_flash_workspace_bytes(int32_t B, int32_t Lq, int32_t DV) 
 }
 
 extern "C" int ds2_debug_flash_stalls(unsigned long long* out8, int reset) {
-  cudaError_t e = cudaMemcpyFromSymbol(out8, ds2::g_flash_stall, 8 * sizeof(unsigned long long));
+  cudaError_t e = cudaMemcpyFromSymbol(out8, ds2::g_flash_stall, 16 * sizeof(unsigned long long));
   if (e == cudaSuccess && reset) {
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     e = cudaMemcpyToSymbol(ds2::g_flash_stall, z, sizeof(z));
   }
   return e == cudaSuccess ? DS2_OK : static_cast<int>(e);

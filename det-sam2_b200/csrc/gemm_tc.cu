@@ -62,22 +62,7 @@ struct GemmParams {
   int stages;
 };
 
-// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7) on the MUFU fast paths (rcp.approx, ex2.approx):
-// ~14 issue slots per element instead of ~50 for libdevice erff — the GELU epilogues of the Hiera MLPs
-// were epilogue-bound on it.  Total error ~1e-6 absolute, far below the bf16 store rounding.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = fmaf(-poly * t, e, 1.0f);
-  const float hx = 0.5f * x;
-  return fmaf(copysignf(erf_abs, x), hx, hx);
-}
+__device__ __forceinline__ float gelu_erf(float x) { return gelu_erf_fast(x); }
 
 // bias / activation / gamma / rotary on NC consecutive columns of one row (registers).
 // Rotary state of one output row (= one epilogue thread for a whole tile): computed once per tile, not per chunk — the
@@ -500,14 +485,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 //                   the GELU, shared-memory staging) that 8 warps exposed — the v1 epilogue issued on 40 % of the
 //                   cycles of its two warps per scheduler (ncu source page, profiles/r2_s5_gemm_epilogue_ncu.txt).
 //                   A warp owns 32-column chunks ci = cg, cg + 4, ...; bias / gamma of its chunks are fetched BEFORE it
-//                   waits for the accumulator and re-read from a warp-private shared-memory line; results leave
-//                   through two alternating 2 KB staging boxes per warp (64-byte swizzle) and TMA stores / reduce-adds.
+//                   waits for the accumulator and re-read from a warp-private shared-memory line; a warp owns 64
+//                   adjacent columns of the tile and sends them out through its 4 KB staging box (128-byte swizzle):
+//                   one TMA store of 64 bf16 columns, or two TMA stores / reduce-adds of 32 f32 columns.
 constexpr int k2Stages = 4;
 constexpr int k2ABytes = kBM * kBK * 2;          // 16 KB: this CTA's 128 rows of A
 constexpr int k2BBytesMax = 128 * kBK * 2;       // 16 KB: this CTA's half (<= 128 rows) of the W tile
 constexpr int k2StageBytes = k2ABytes + k2BBytesMax;
 constexpr int k2EpiWarps = 16;
-constexpr int k2StagingBytes = 4096;             // per warp: two boxes of 32 rows x 64 B
+constexpr int k2StagingBytes = 4096;             // per warp: one box of 32 rows x 128 B
 constexpr int k2VecBytes = 512;                  // per warp: bias (64 f32) + gamma (64 f32)
 constexpr int k2Smem = k2Stages * k2StageBytes + k2EpiWarps * (k2StagingBytes + k2VecBytes) + 1024 + 256;
 constexpr int k2Threads = 128 + 32 * k2EpiWarps;
@@ -552,7 +538,6 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // bias / activation / gamma / rotary on 32 consecutive columns of one row, in place; bias and gamma come from the warp's
 // shared-memory line `vec` (64 f32 bias, then 64 f32 gamma) at element offset `voff`
@@ -722,7 +707,7 @@ gemm2_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const
     const int mode = p.store_mode;
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t nstores = 0;          // lane 0: bulk stores issued so far (box = nstores & 1)
+    bool pending = false;          // lane 0: a bulk store may still be reading the staging box
     if (p.rope_axial) {
       const int n4 = 64 * p.rope_side * 2 / 4;
       const float4* src = reinterpret_cast<const float4*>(p.rope_axial);
@@ -743,8 +728,8 @@ gemm2_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const
       float bv[2] = {0.f, 0.f}, gv[2] = {1.f, 1.f};
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int c = n0 + (cg + 4 * j) * 32 + lane;
-        if ((cg + 4 * j) * 32 < p.BN && c < p.N) {
+        const int c = n0 + cg * 64 + 32 * j + lane;
+        if (cg * 64 + 32 * j < p.BN && c < p.N) {
           if (p.bias) bv[j] = __ldg(p.bias + c);
           if (p.gamma) gv[j] = __ldg(p.gamma + c);
         }
@@ -760,62 +745,67 @@ gemm2_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const
       tc::mbar_wait(tfull_bar(acc), acc_phase);
       tc::tc_fence_after();
       const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc) * 256u + (static_cast<uint32_t>(lq * 32) << 16);
-      int j = 0;
-      for (int ci = cg; ci * 32 < p.BN; ci += 4, ++j) {
-        const int c = ci * 32;
+      // one 4 KB staging box per warp: 32 rows x 128 B, SWIZZLE_128B (16-byte chunk q of row r at q ^ (r & 7)) —
+      // 64 bf16 columns (both halves, ONE store) or 32 f32 columns (one store per half)
+      const uint32_t rowaddr = stg + static_cast<uint32_t>(lane) * 128u;
+      const uint32_t sw = static_cast<uint32_t>(lane) & 7u;
+      auto wait_box = [&]() {   // the previous bulk store must have finished READING the box
+        if (pending) {
+          tc::bulk_wait_read0();
+          pending = false;
+        }
+        __syncwarp();
+      };
+      auto issue = [&](int col) {
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (mode == kStoreTmaAddF32) tc::tma_reduce_add_2d(&tmap_c, stg, col, row0);
+          else tc::tma_store_2d(&tmap_c, stg, col, row0);
+          tc::bulk_commit();
+          pending = true;
+        }
+      };
+      const int cbase = cg * 64;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = cbase + 32 * j;
+        if (c >= p.BN) break;  // warp-uniform
         uint32_t r[32];
         tc::tmem_ld32(t_addr + c, r);
         tc::tmem_ld_wait();
-        if (n0 + c >= p.N) continue;  // warp-uniform
+        const bool live = n0 + c < p.N;  // warp-uniform
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        epilogue_math_v2(p, v, n0 + c, vec, 32 * j, rope_smem, rr);
+        if (live) epilogue_math_v2(p, v, n0 + c, vec, 32 * j, rope_smem, rr);
         if (mode == kStoreDirect) {
-          if (row < p.M) epilogue_store_direct<32>(p, v, row, n0 + c);
+          if (live && row < p.M) epilogue_store_direct<32>(p, v, row, n0 + c);
           continue;
         }
-        // staging boxes: 32 rows x 64 B, SWIZZLE_64B (16-byte chunk q of row r at q ^ ((r >> 1) & 3)); a box may be
-        // overwritten once the store issued two stores ago has finished reading it
-        const uint32_t sw = (static_cast<uint32_t>(lane) >> 1) & 3u;
-        auto box_addr = [&](uint32_t n) { return stg + (n & 1u) * 2048u + static_cast<uint32_t>(lane) * 64u; };
-        auto issue = [&](uint32_t box, int col) {
-          tc::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            if (mode == kStoreTmaAddF32) tc::tma_reduce_add_2d(&tmap_c, box, col, row0);
-            else tc::tma_store_2d(&tmap_c, box, col, row0);
-            tc::bulk_commit();
-          }
-        };
         if (mode == kStoreTmaBf16) {
+          if (j == 0) {
+            if (!live) break;
+            wait_box();
+          }
           uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = tc::pack_bf16(v[2 * i], v[2 * i + 1]);
-          if (lane == 0 && nstores >= 2) bulk_wait_read1();
-          __syncwarp();
-          const uint32_t ra = box_addr(nstores);
+          for (int i = 0; i < 16; ++i) pk[i] = live ? tc::pack_bf16(v[2 * i], v[2 * i + 1]) : 0u;
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            st_shared_v4(ra + ((static_cast<uint32_t>(q) ^ sw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-          issue(stg + (nstores & 1u) * 2048u, n0 + c);
-          ++nstores;
+            st_shared_v4(rowaddr + ((static_cast<uint32_t>(4 * j + q) ^ sw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2],
+                         pk[4 * q + 3]);
+          // a 64-wide box never reaches into a neighbouring tile: with several n-tiles BN is a multiple of 64
+          // (choose_bn2), with one n-tile everything right of N is clipped by the tensor map
+          if (j == 1 || c + 32 >= p.BN) issue(n0 + cbase);
         } else {
-          // f32: two boxes of 16 columns
+          if (!live) break;
+          wait_box();
 #pragma unroll
-          for (int hlf = 0; hlf < 2; ++hlf) {
-            if (n0 + c + 16 * hlf >= p.N) break;  // warp-uniform (N % 16 == 0 is required for the TMA f32 modes)
-            if (lane == 0 && nstores >= 2) bulk_wait_read1();
-            __syncwarp();
-            const uint32_t ra = box_addr(nstores);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              st_shared_v4(ra + ((static_cast<uint32_t>(q) ^ sw) << 4), __float_as_uint(v[16 * hlf + 4 * q]),
-                           __float_as_uint(v[16 * hlf + 4 * q + 1]), __float_as_uint(v[16 * hlf + 4 * q + 2]),
-                           __float_as_uint(v[16 * hlf + 4 * q + 3]));
-            issue(stg + (nstores & 1u) * 2048u, n0 + c + 16 * hlf);
-            ++nstores;
-          }
+          for (int q = 0; q < 8; ++q)
+            st_shared_v4(rowaddr + ((static_cast<uint32_t>(q) ^ sw) << 4), __float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]),
+                         __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3]));
+          issue(n0 + c);
         }
       }
       tc::tc_fence_before();
@@ -826,7 +816,7 @@ gemm2_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const
         acc_phase ^= 1;
       }
     }
-    if (lane == 0) tc::bulk_wait0();  // global writes complete before the CTA retires
+    if (pending) tc::bulk_wait0();  // global writes complete before the CTA retires
   }
 
   tc::tc_fence_before();
@@ -923,12 +913,12 @@ static int choose_bn(int M, int N, int sms, int step) {
 
 // Tile width of the CTA-pair kernel: multiples of 32 (32-column staging boxes); one n-tile when N <= 256, otherwise the
 // width that minimises waves x (width + per-tile fixed cost) over the 74 clusters.
-static int choose_bn2(int M, int N, int clusters) {
+static int choose_bn2(int M, int N, int clusters, int step) {
   if (N <= 256) return ((N + 31) / 32) * 32;
   const int tiles_m = (M + 255) / 256;
   int best = 256;
   long long best_cost = -1;
-  for (int bn = 256; bn >= 64; bn -= 32) {
+  for (int bn = 256; bn >= 64; bn -= step) {
     const long long tiles = static_cast<long long>(tiles_m) * ((N + bn - 1) / bn);
     const long long waves = (tiles + clusters - 1) / clusters;
     const long long cost = waves * (bn + 24);
@@ -942,13 +932,14 @@ static int choose_bn2(int M, int N, int clusters) {
 
 static int launch_gemm2(const ds2_gemm_args* a, GemmParams p, int sms, cudaStream_t st) {
   const int clusters = sms / 2;
-  p.BN = choose_bn2(a->M, a->N, clusters);
+  const int step = p.store_mode == kStoreTmaBf16 ? 64 : 32;   // bf16 results leave in 64-column boxes
+  p.BN = choose_bn2(a->M, a->N, clusters, step);
   {
     static const int force_bn = [] {
       const char* e = getenv("DS2_GEMM_BN");
       return e ? atoi(e) : 0;
     }();
-    if (force_bn >= 64 && force_bn <= 256 && (force_bn % 32) == 0 && a->N > 256) p.BN = force_bn;
+    if (force_bn >= 64 && force_bn <= 256 && (force_bn % step) == 0 && a->N > 256) p.BN = force_bn;
   }
   p.tiles_m = (a->M + 255) / 256;
   p.tiles_n = (a->N + p.BN - 1) / p.BN;
@@ -959,14 +950,14 @@ static int launch_gemm2(const ds2_gemm_args* a, GemmParams p, int sms, cudaStrea
   if (p.store_mode == kStoreTmaBf16) {
     const uint64_t dims[2] = {static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->M)};
     const uint64_t strides[1] = {static_cast<uint64_t>(a->ldc_bf16) * 2};
-    const uint32_t box[2] = {32, 32};
-    int rc = make_tmap(&tcm, a->out_bf16, 2, 64, 2, dims, strides, box);
+    const uint32_t box[2] = {64, 32};
+    int rc = make_tmap(&tcm, a->out_bf16, 2, 128, 2, dims, strides, box);
     if (rc) return rc;
   } else if (p.store_mode == kStoreTmaF32 || p.store_mode == kStoreTmaAddF32) {
     const uint64_t dims[2] = {static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->M)};
     const uint64_t strides[1] = {static_cast<uint64_t>(a->ldc) * 4};
-    const uint32_t box[2] = {16, 32};
-    int rc = make_tmap(&tcm, a->out_f32, 4, 64, 2, dims, strides, box);
+    const uint32_t box[2] = {32, 32};
+    int rc = make_tmap(&tcm, a->out_f32, 4, 128, 2, dims, strides, box);
     if (rc) return rc;
   }
   {
@@ -1058,7 +1049,7 @@ extern "C" int ds2_gemm(const ds2_gemm_args* a, void* stream) {
   // epilogue store path
   p.store_mode = kStoreDirect;
   const bool one_out = (a->out_f32 != nullptr) != (a->out_bf16 != nullptr);
-  if (one_out && a->impl != 2) {
+  if (one_out && a->impl != 2) {   // impl 2: tests force the row-per-thread stores
     if (a->out_bf16 && !a->residual && (a->ldc_bf16 % 8) == 0 &&
         (reinterpret_cast<uintptr_t>(a->out_bf16) & 15) == 0) {
       p.store_mode = kStoreTmaBf16;

@@ -161,7 +161,7 @@ struct MaskEmbedParams {
   const float *w3, *b3, *g3, *be3;    // [16][16] ((cin, ky, kx) per output), [16], LN [16]
   __nv_bfloat16* out;                 // [B * (S/16)^2, 16]
 };
-__device__ __forceinline__ float gelu_erf_p(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_erf_p(float x) { return gelu_erf_fast(x); }
 
 __global__ void __launch_bounds__(128) mask_prompt_embed_kernel(const MaskEmbedParams p) {
   pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)

@@ -64,7 +64,9 @@ typedef struct ds2_gemm_args {
   int32_t rope_period;            /* table rows; position = (row % rope_rows_per_batch) % period */
   int32_t rope_rows_per_batch;    /* rows per batch item */
   int32_t rope_row_limit;         /* rotate only rows with (row % rows_per_batch) < limit */
-  int32_t impl;                   /* 0 = tcgen05 (product path), 1 = SIMT debug kernel */
+  int32_t impl;                   /* 0 = tcgen05 (product path: CTA-pair kernel for M >= 512, else single-CTA),
+                                     1 = SIMT debug kernel, 2 = single-CTA with row-per-thread stores,
+                                     3 = force the CTA-pair kernel, 4 = force the single-CTA kernel */
   /* axial form of the same table (takes precedence over rope_cs): [64][rope_side][2] (cos, sin) of ONE grid coordinate;
    * pair j < 64 rotates by x = position % side, pair j >= 64 by y = position / side with the frequencies of pair j - 64
    * (compute_axial_cis, position_encoding.py:173-182); requires rope_period == rope_side^2.  Staged in shared memory. */
@@ -100,7 +102,7 @@ int64_t ds2_flash_workspace_bytes(int32_t B, int32_t Lq, int32_t DV);
 /* Tuning aid: barrier-stall cycle counters of flash launches made with impl == 8 (summed over CTAs):
  * [0] K-tile wait [1] V-tile wait [2] P wait [3] MMA-warp cycles [4] S wait [5] O wait [6] softmax-warp
  * cycles [7] CTAs.  Synchronises the device.  No reference counterpart. */
-int ds2_debug_flash_stalls(unsigned long long* out8, int reset);
+int ds2_debug_flash_stalls(unsigned long long* out16, int reset);   /* 16 counters */
 /* Tuning aid: phase timestamps (cycles since kernel start) of CTA 0 of the last windowed-attention launch made
  * with DS2_WIN_DBG=1 in the environment.  Synchronises the device.  No reference counterpart. */
 int ds2_debug_win_times(long long* out16);

@@ -10,7 +10,8 @@ engine must deviate from the fp32 reference by NO MORE than the reference itself
 Det-SAM2 runs it — torch.autocast(bf16) — on the same scenario (tests/golden/ref_bf16_deviation.json,
 produced by oracle/calibrate_bf16.py).  With seeded random weights the masks are near-degenerate and
 the reference's own bf16 IoU against itself is 0.88-0.99, so the north-star IoU >= 0.999 is asserted on
-the *decided* pixels: those whose fp32 logit is farther from the 0 threshold than 4x the RMS error.
+the *confident* pixels: those whose fp32 logit is farther from the 0 threshold than 0.30 x the rms logit of the mask
+(a band fixed by the reference mask and the stated tolerance, not by the measured error).
 """
 import json
 import os
@@ -39,6 +40,9 @@ def _cuda_predictor(cfg, fill_hole_area=0, **kw):
     return SAM2VideoPredictor(eng, fill_hole_area=fill_hole_area, **kw)
 
 
+CONF_BAND = 0.30
+
+
 def _kind_errors(got, gold):
     per_kind = {}
     for k, r in gold.items():
@@ -54,7 +58,10 @@ def _kind_errors(got, gold):
             a, b = got[k] > 0, r > 0
             u = np.logical_or(a, b).sum()
             d["iou"].append((1.0 if u == 0 else np.logical_and(a, b).sum() / u, k))
-            dec = np.abs(r64) > 4.0 * rms_abs
+            # confident pixels: fp32 logit farther from the threshold than CONF_BAND x the rms logit of the array — a band
+            # fixed by the reference mask and the stated tolerance (5x the ~0.06 rel-rms band of the logits), not by the
+            # measured error (tests/test_fullsize_gpu.py::_confident_iou explains why raw IoU says little here)
+            dec = np.abs(r64) > CONF_BAND * np.sqrt(np.mean(r64 ** 2))
             u = (np.logical_or(a, b) & dec).sum()
             d["iou_decided"].append((1.0 if u == 0 else (np.logical_and(a, b) & dec).sum() / u, k))
     return per_kind
@@ -101,7 +108,7 @@ def test_cuda_engine_matches_reference_golden(name):
             iou_mean = float(np.mean([e for e, _ in d["iou"]]))
             lo_d, lkd = min(d["iou_decided"])
             report.append(f"{name}.{kind}: IoU mean {iou_mean:.4f} (ref-bf16 {calib[kind]['iou_mean']:.4f}), min {lo:.4f} at {lk} "
-                          f"(ref-bf16 {calib[kind]['iou_min']:.4f}); decided-pixel IoU min {lo_d:.5f}")
+                          f"(ref-bf16 {calib[kind]['iou_min']:.4f}); confident-pixel IoU min {lo_d:.5f}")
             if iou_mean < calib[kind]["iou_mean"] - 5e-3 or lo < min(c[kind]["iou_min"] for c in allcal.values()) - 0.02 \
                     or lo_d < 0.999:
                 bad.append(report[-1])

@@ -255,7 +255,9 @@ def test_cuda_engine_matches_reference_fixture_at_full_size(name):
     assert set(got) == set(gold)
     lines, bad = [], []
     # bf16 operands / fp32 accumulation against the fp32 reference; measured values in profiles/r2_parity_fullsize_fixtures.txt
+    # (the second tracked frame reads a bank that already carries bf16 noise: wider band, as in test_configs_gpu.py)
     bounds = {"pred_masks": 0.06, "obj_ptr": 0.08, "maskmem_features": 0.02, "object_score_logits": 0.02}
+    late = {"pred_masks": 0.10}
     for k in sorted(gold):
         r = gold[k]
         kind = k.rsplit(".", 1)[-1]
@@ -283,7 +285,7 @@ def test_cuda_engine_matches_reference_fixture_at_full_size(name):
             if worst < 0.999:
                 bad.append(msg)
         lines.append(msg)
-        if rel > bounds[kind]:
+        if rel > (late.get(kind, bounds[kind]) if ".f2." in k else bounds[kind]):
             bad.append(msg)
     print("\n".join(lines))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -70,6 +70,54 @@ def test_gemm_store_paths(ops, M, N, K, mode):
         assert (o - ref).abs().max().item() < 1e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(512, 32, 64), (1000, 64, 144), (4096 + 128, 192, 576), (16384, 288, 288),
+                                   (2048, 576, 2304), (4096, 2304, 576), (65536, 256, 64), (777, 96, 200)])
+@pytest.mark.parametrize("mode", ["bf16_gelu", "f32", "inplace", "gamma_res", "two_out", "relu_bf16"])
+def test_gemm_cta_pair_kernel_vs_single_cta_kernel(ops, M, N, K, mode):
+    """gemm2 (tcgen05 cta_group::2, 256-row tiles on CTA pairs, 16 epilogue warps; impl 3) against the single-CTA kernel
+    (impl 4) and torch, every epilogue / store path, ragged M / N / K."""
+    torch.manual_seed(21)
+    a = bf(torch.randn(M, K, device=DEV))
+    w = bf(torch.randn(N, K, device=DEV) / math.sqrt(K))
+    b = torch.randn(N, device=DEV)
+    ref = a.float() @ w.float().t() + b
+    g = torch.rand(N, device=DEV) + 0.5
+    r = torch.randn(256, N, device=DEV)
+    outs = []
+    for impl in (3, 4):
+        if mode == "bf16_gelu":
+            o = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+            ops.gemm(a, w, bias=b, act=2, out_bf16=o, impl=impl)
+            want, tol = F.gelu(ref), 4e-2
+        elif mode == "relu_bf16":
+            o = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+            ops.gemm(a, w, bias=b, act=1, out_bf16=o, impl=impl)
+            want, tol = F.relu(ref), 4e-2
+        elif mode == "f32":
+            o = torch.full((M, N), float("nan"), device=DEV)
+            ops.gemm(a, w, bias=b, out_f32=o, impl=impl)
+            want, tol = ref, 1e-3
+        elif mode == "inplace":
+            torch.manual_seed(5)
+            o = torch.randn(M, N, device=DEV)
+            want, tol = o.clone() + ref, 1e-3
+            ops.gemm(a, w, bias=b, residual=o, out_f32=o, impl=impl)
+        elif mode == "gamma_res":
+            o = torch.full((M, N), float("nan"), device=DEV)
+            ops.gemm(a, w, bias=b, act=2, gamma=g, residual=r, res_row_mod=256, out_f32=o, impl=impl)
+            want, tol = F.gelu(ref) * g + r.repeat((M + 255) // 256, 1)[:M], 1e-3
+        else:
+            o = torch.full((M, N), float("nan"), device=DEV)
+            o2 = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+            ops.gemm(a, w, bias=b, out_f32=o, out_bf16=o2, impl=impl)
+            assert (o2.float() - ref).abs().max().item() < 4e-2
+            want, tol = ref, 1e-3
+        assert (o.float() - want).abs().max().item() < tol, (impl, mode)
+        outs.append(o.float())
+    # same products accumulated in the same k order: the two kernels agree to fp32 rounding (usually bit for bit)
+    assert (outs[0] - outs[1]).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item()) + (8e-3 if "bf16" in mode else 0)
+
+
 def test_gemm_bf16_store_into_column_slice(ops):
     torch.manual_seed(12)
     a = bf(torch.randn(500, 256, device=DEV))
@@ -130,12 +178,14 @@ def test_gemm_rope_axial_equals_full_table_path(ops, side, B, nptr, out):
     full, ax = _rope_table(256, side, 10000.0).to(DEV), _rope_axial(256, side, 10000.0).to(DEV)
     kw = dict(out_bf16=None, out_f32=None)
     outs = []
-    for tab in (full, ax):
+    # full table (single-CTA kernel only), axial table on the single-CTA kernel (impl 4) and on the CTA-pair kernel (impl 3)
+    for tab, impl in ((full, 4), (ax, 4), (ax, 3)):
         o = torch.empty(B * N_rows, 256, device=DEV, dtype=torch.bfloat16 if out == "bf16" else torch.float32)
         kw = {"out_bf16": o} if out == "bf16" else {"out_f32": o}
-        ops.gemm(a, w, bias=bias, rope=(tab, 0, 256, N_rows, N_rows - nptr), **kw)
+        ops.gemm(a, w, bias=bias, rope=(tab, 0, 256, N_rows, N_rows - nptr), impl=impl, **kw)
         outs.append(o)
     assert torch.equal(outs[0], outs[1])
+    assert (outs[2].float() - outs[1].float()).abs().max().item() <= (8e-3 if out == "bf16" else 1e-5)
     # and the SIMT debug kernel reads the axial table the same way
     o1 = torch.empty(B * N_rows, 256, device=DEV)
     ops.gemm(a, w, bias=bias, rope=(ax, 0, 256, N_rows, N_rows - nptr), out_f32=o1, impl=1)
