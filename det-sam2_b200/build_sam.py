@@ -38,6 +38,45 @@ def load_state_dict(cfg, ckpt_path=None, seed=0):
     return sd
 
 
+# hydra override keys the reference's callers pass (build_sam.py:111-146 and its docs), mapped onto ModelConfig fields
+# ("cfg") or SAM2VideoPredictor keyword arguments ("pred").  hydra itself is not used.
+_OVERRIDE_KEYS = {
+    "model.fill_hole_area": ("cfg", "fill_hole_area", int),
+    "model.non_overlap_masks": ("cfg", "non_overlap_masks", bool),
+    "model.binarize_mask_from_pts_for_mem_enc": ("cfg", "binarize_mask_from_pts_for_mem_enc", bool),
+    "model.sam_mask_decoder_extra_args.dynamic_multimask_via_stability": ("cfg", "dynamic_multimask_via_stability", bool),
+    "model.sam_mask_decoder_extra_args.dynamic_multimask_stability_delta": ("cfg", "dynamic_multimask_stability_delta", float),
+    "model.sam_mask_decoder_extra_args.dynamic_multimask_stability_thresh": ("cfg", "dynamic_multimask_stability_thresh", float),
+    "model.image_size": ("cfg", "image_size", int),
+    "model.num_maskmem": ("cfg", "num_maskmem", int),
+    "model.max_cond_frames_in_attn": ("cfg", "max_cond_frames_in_attn", int),
+    "model.max_obj_ptrs_in_encoder": ("cfg", "max_obj_ptrs_in_encoder", int),
+    "model.multimask_min_pt_num": ("cfg", "multimask_min_pt_num", int),
+    "model.multimask_max_pt_num": ("cfg", "multimask_max_pt_num", int),
+    "model.clear_non_cond_mem_around_input": ("pred", "clear_non_cond_mem_around_input", bool),
+    "model.clear_non_cond_mem_for_multi_obj": ("pred", "clear_non_cond_mem_for_multi_obj", bool),
+    "model.add_all_frames_to_correct_as_cond": ("pred", "add_all_frames_to_correct_as_cond", bool),
+}
+
+
+def parse_hydra_overrides(overrides):
+    """``["++model.fill_hole_area=0", ...]`` -> (ModelConfig overrides, predictor kwargs).  The reference appends the
+    caller's ``hydra_overrides_extra`` to its own eval overrides (build_sam.py:123-137); the keys understood here are
+    the model / predictor settings that exist on this path, anything else is refused by name."""
+    cfg_over, pred_kw = {}, {}
+    for item in overrides or ():
+        if not isinstance(item, str) or "=" not in item:
+            raise ValueError(f"malformed override {item!r}: expected '++model.<key>=<value>'")
+        key, val = item.lstrip("+~").split("=", 1)
+        if key not in _OVERRIDE_KEYS:
+            raise ValueError(f"unsupported override {key!r}; supported: {sorted(_OVERRIDE_KEYS)}")
+        where, name, typ = _OVERRIDE_KEYS[key]
+        v = val.strip().strip("'\"")
+        parsed = (v.lower() in ("true", "1", "yes")) if typ is bool else typ(float(v)) if typ is int else typ(v)
+        (cfg_over if where == "cfg" else pred_kw)[name] = parsed
+    return cfg_over, pred_kw
+
+
 def build_sam2_video_predictor(config_file, ckpt_path=None, device="cuda", mode="eval", hydra_overrides_extra=(),
                                apply_postprocessing=True, state_dict=None, seed=0, engine=None, **kwargs):
     """Returns a detsam2_b200.predictor.SAM2VideoPredictor backed by the sm_100a CUDA engine.
@@ -46,9 +85,10 @@ def build_sam2_video_predictor(config_file, ckpt_path=None, device="cuda", mode=
     inject a checker implementation of the engine seams; production callers never pass it."""
     if mode != "eval":
         raise ValueError("only mode='eval' is supported (training is out of scope)")
-    if hydra_overrides_extra:
-        raise ValueError("hydra overrides are not supported; pass ModelConfig field overrides as keyword arguments")
-    cfg_over = {k: kwargs.pop(k) for k in list(kwargs) if k in get_config("tiny").__dataclass_fields__}
+    cfg_over, pred_kw = parse_hydra_overrides(hydra_overrides_extra)
+    cfg_over.update({k: kwargs.pop(k) for k in list(kwargs) if k in get_config("tiny").__dataclass_fields__})
+    for k, v in pred_kw.items():
+        kwargs.setdefault(k, v)
     cfg = get_config(config_file, **cfg_over)
     if engine is None:
         if torch.device(device).type != "cuda":
@@ -58,6 +98,29 @@ def build_sam2_video_predictor(config_file, ckpt_path=None, device="cuda", mode=
         engine = CudaEngine(cfg, sd, device=device)
     fill = cfg.fill_hole_area if apply_postprocessing else 0
     return SAM2VideoPredictor(engine, fill_hole_area=fill, non_overlap_masks=cfg.non_overlap_masks, **kwargs)
+
+
+class _ImageModel:
+    """What build_sam2 returns: the handle SAM2ImagePredictor wraps (the reference returns the SAM2Base module)."""
+
+    def __init__(self, engine):
+        self.engine, self.cfg = engine, engine.cfg
+        self.image_size, self.device = engine.cfg.image_size, engine.device
+
+
+def build_sam2(config_file, ckpt_path=None, device="cuda", mode="eval", hydra_overrides_extra=(), apply_postprocessing=True,
+               state_dict=None, seed=0, engine=None, **kwargs):
+    """build_sam.py:69-108: the image model.  ``SAM2ImagePredictor(build_sam2(...).engine)`` or
+    ``SAM2ImagePredictor.from_pretrained`` wrap it; same factory arguments as the video predictor."""
+    pred = build_sam2_video_predictor(config_file, ckpt_path, device, mode, hydra_overrides_extra, apply_postprocessing,
+                                      state_dict, seed, engine, **kwargs)
+    return _ImageModel(pred.engine)
+
+
+def build_sam2_hf(model_id, **kwargs):
+    """build_sam.py:155-157."""
+    config_name, ckpt_path = _hf_download(model_id)
+    return build_sam2(config_file=config_name, ckpt_path=ckpt_path, **kwargs)
 
 
 def _hf_download(model_id):

@@ -439,7 +439,9 @@ class CudaEngine:
         for cap, t in lst:
             if cap >= rows:
                 return t[: B * rows * cols].view(B, rows, cols)
-        cap = max(rows, min_rows)
+        # grow geometrically: a bank that keeps growing row by row (preload banks with many conditioning frames) must not
+        # leave one retired buffer per size behind
+        cap = max(rows, min_rows, int(1.5 * lst[-1][0]) if lst else 0)
         t = torch.empty(B * cap * cols, dtype=dtype, device=self.device)
         lst.append((cap, t))
         lst.sort(key=lambda e: e[0])
@@ -735,7 +737,10 @@ class CudaEngine:
             low, iou_out, obj_ptr, score = (t.clone() for t in self._sam_heads_body(
                 {"coords": coords.to(self.device), "labels": labels.to(self.device), "s0": feats.feat_s0, "s1": feats.feat_s1},
                 pix, B, P, mm, dense=dense))
-            return {"pred_masks": low, "ious": iou_out, "obj_ptr": obj_ptr, "object_score_logits": score}
+            S4 = 4 * cfg.feat_size
+            return {"pred_masks": low, "ious": iou_out, "obj_ptr": obj_ptr, "object_score_logits": score,
+                    "_all_masks": self._buf("dec_masks", (B, 4, S4, S4), F32), "_all_ious": self._buf("dec_ious", (B, 4), F32),
+                    "_best_idx": self._buf("dec_best", (B,), torch.int32)}
         body = lambda inp: self._sam_heads_body(inp, pix, B, P, mm)  # noqa: E731
         low, iou_out, obj_ptr, score = self.graphs.run(
             ("sam", B, P, mm, pix.data_ptr()),
@@ -747,6 +752,31 @@ class CudaEngine:
         return {"pred_masks": low, "ious": iou_out, "obj_ptr": obj_ptr, "object_score_logits": score,
                 "_all_masks": self._buf("dec_masks", (B, 4, S4, S4), F32), "_all_ious": self._buf("dec_ious", (B, 4), F32),
                 "_best_idx": self._buf("dec_best", (B,), torch.int32)}
+
+    def decode_masks(self, pix_feat, feats, B, point_coords, point_labels, mask_inputs, multimask_output):
+        """Prompt encoder + mask decoder WITHOUT the tracking epilogue — what SAM2ImagePredictor._predict calls
+        (sam2_image_predictor.py:395-420): the three multimask candidates with their predicted IoUs, or the single mask
+        after the stability fallback (mask_decoder.py:143-148, 261-296); never gated by the object score.
+        Returns (low_res_masks [B,C,4h,4w] f32, iou_predictions [B,C] f32), C = 3 or 1."""
+        if point_coords is None:
+            # PromptEncoder.forward with points=None emits NO sparse tokens (prompt_encoder.py:150-160), unlike the
+            # tracker's padded "no prompt" decode: a mask-only image prompt is not wired to the CUDA decoder
+            raise NotImplementedError("decode_masks without point / box prompts (mask-only prompt) is not implemented")
+        dev = lambda t: None if t is None else t.to(self.device)  # noqa: E731
+        out = self.sam_heads(pix_feat.to(self.device), feats, B, dev(point_coords), dev(point_labels), dev(mask_inputs),
+                             multimask_output)
+        if "_all_masks" not in out:
+            raise Ds2Error("decode_masks: the decoder did not expose its candidate masks")
+        allm, alli, best = out["_all_masks"], out["_all_ious"], out["_best_idx"]
+        if multimask_output:
+            return allm[:, 1:4].clone(), alli[:, 1:4].clone()
+        idx = best.long()
+        bi = torch.arange(B, device=self.device)
+        return allm[bi, idx].unsqueeze(1).clone(), alli[bi, idx].unsqueeze(1).clone()
+
+    def connected_components(self, mask_u8):
+        """uint8 [N,1,H,W] -> (labels, areas) int32: ds2_connected_components, the drop-in for the reference's only FFI."""
+        return ops.connected_components(mask_u8.to(self.device).contiguous())
 
     def _noprompt(self, B):
         key = ("noprompt", B)

@@ -51,7 +51,7 @@ class VideoProcessor:
                  vis_frame_stride=-1, visualize_prompt=False, frame_buffer_size=30, detect_interval=30,
                  max_frame_num_to_track=60, max_inference_state_frames=60, load_inference_state_path=None,
                  save_inference_state_path=None, *, predictor=None, detector=None, device="cuda", object_stats=False,
-                 frames_on_device=None):
+                 frames_on_device=None, offload_state_to_cpu=None):
         if vis_frame_stride != -1 or visualize_prompt:
             raise NotImplementedError("matplotlib rendering is outside the hot path; use vis_frame_stride=-1")
         if save_inference_state_path is not None:
@@ -101,6 +101,15 @@ class VideoProcessor:
         if frames_on_device is None:
             frames_on_device = getattr(getattr(predictor, "device", None), "type", "cpu") == "cuda"
         self.frames_on_device = bool(frames_on_device)
+        # Where a preloaded bank lives once it is loaded (init_preloading_state, svp:123-156).  The reference moves it to
+        # the host by default (offload_state_to_cpu=True: its constant-memory design targets 24 GB cards) and every memory
+        # read then drags the stored features back over PCIe — measured on configs[2] (base_plus, 720p, 16 objects, 10-frame
+        # bank, 2000-frame stream): 8.6 video frames/s host-bound (profiles/r2_config3_stream_2000_frames_state_on_host.json).
+        # A 10-frame bank is 0.12 GB of the 180 GB: None = keep it in HBM for a CUDA predictor (results are bit-identical,
+        # tests/test_fullsize_gpu.py::test_offload_state_to_cpu_on_cuda_engine); True = the reference's behaviour.
+        if offload_state_to_cpu is None:
+            offload_state_to_cpu = getattr(getattr(predictor, "device", None), "type", "cpu") != "cuda"
+        self.offload_state_to_cpu = bool(offload_state_to_cpu)
         self.video_stats = {}
         self.timings = {}
         self.inference_state = None
@@ -334,10 +343,8 @@ class VideoProcessor:
             st["preloading_memory_non_cond_frames_idx"] = list(st["output_dict"]["non_cond_frame_outputs"].keys())
             self.pre_frames = st["num_frames"]
             self.inference_state = st
-            if self.frames_on_device:
-                self.predictor.init_preloading_state(st, offload_video_to_cpu=False)
-            else:
-                self.predictor.init_preloading_state(st)
+            self.predictor.init_preloading_state(st, offload_video_to_cpu=not self.frames_on_device,
+                                                 offload_state_to_cpu=self.offload_state_to_cpu)
 
         def stream():
             if frames is not None:

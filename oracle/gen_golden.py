@@ -41,7 +41,25 @@ def fingerprint(sd):
     return np.asarray([[float(sd[k].double().sum()), float(sd[k].double().abs().sum())] for k in keys], dtype=np.float64)
 
 
+def generate_image_predictor():
+    """tests/golden/image_predictor.npz from the UNMODIFIED reference SAM2ImagePredictor (sam2_image_predictor.py)."""
+    ref_shim.install()
+    from sam2.sam2_image_predictor import SAM2ImagePredictor
+    cfg = scenarios.image_predictor_config()
+    sd = synthetic_state_dict(cfg, 0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = ref_shim.build_reference_predictor(cfg, sd, device="cpu")   # a SAM2Base subclass: what the predictor wraps
+    rec = scenarios.run_image_predictor(SAM2ImagePredictor(model))
+    rec["__weights_fingerprint"] = fingerprint(sd)
+    rec["__torch_version"] = np.asarray(torch.__version__)
+    path = os.path.join(GOLDEN_DIR, "image_predictor.npz")
+    np.savez_compressed(path, **rec)
+    print(f"image_predictor: {len(rec)} arrays, {os.path.getsize(path) / 1e6:.2f} MB -> {path}")
+
+
 def generate(name):
+    if name == "image_predictor":
+        return generate_image_predictor()
     cfg = scenarios.scenario_config(name)
     sd = synthetic_state_dict(cfg, 0)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -69,6 +87,6 @@ def generate(name):
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(scenarios.SCENARIOS) + list(VP_SCENARIOS)
+    names = sys.argv[1:] or list(scenarios.SCENARIOS) + list(VP_SCENARIOS) + ["image_predictor"]
     for n in names:
         generate(n)

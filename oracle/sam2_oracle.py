@@ -594,6 +594,7 @@ class OracleEngine:
         (det_sam2_RT.py:101-107, sam/transformer.py:28-41) — bench.py's `gpu_library_baseline`, never a checker."""
 
     name = "oracle-torch-fp32"
+    image_dtype = torch.float32     # SAM2ImagePredictor feeds the fp32 normalised image (sam2_image_predictor.py:108-115)
 
     def __init__(self, cfg, state_dict, fill_holes=True, device="cpu", autocast=False, fused_sdpa=None):
         self.cfg = cfg
@@ -657,6 +658,27 @@ class OracleEngine:
                                   hr, multimask_output)
         return {"pred_masks": o["low_res_masks"].float(), "ious": o["ious"].float(), "obj_ptr": o["obj_ptr"].float(),
                 "object_score_logits": o["object_score_logits"].float(), "_multimasks": o["low_res_multimasks"]}
+
+    def decode_masks(self, pix_feat, feats, B, point_coords, point_labels, mask_inputs, multimask_output):
+        """sam_prompt_encoder + sam_mask_decoder as SAM2ImagePredictor._predict calls them (sam2_image_predictor.py:395-420)."""
+        with self._ctx():
+            dev = lambda t: None if t is None else t.to(self.device)  # noqa: E731
+            hr = [x.expand(B, -1, -1, -1) for x in feats["fpn"][:-1]]
+            pc, pl = dev(point_coords), dev(point_labels)
+            if pc is None:   # PromptEncoder.forward with points=None: no sparse tokens at all (prompt_encoder.py:150-160)
+                sparse = torch.zeros(B, 0, self.cfg.hidden_dim)
+                _, dense = prompt_encoder(self.sd, self.cfg, torch.zeros(B, 1, 2), -torch.ones(B, 1, dtype=torch.int32),
+                                          dev(mask_inputs))
+            else:
+                sparse, dense = prompt_encoder(self.sd, self.cfg, pc, pl.to(torch.int32), dev(mask_inputs))
+            masks, ious, _, _ = mask_decoder(self.sd, self.cfg, pix_feat.to(self.device), dense_pe(self.sd, self.cfg.feat_size),
+                                             sparse, dense, multimask_output, hr)
+        return masks.float(), ious.float()
+
+    def connected_components(self, mask_u8):
+        from . import cc_oracle
+        lab, cnt = cc_oracle.connected_components(mask_u8.cpu().numpy())
+        return torch.from_numpy(lab).to(mask_u8.device), torch.from_numpy(cnt).to(mask_u8.device)
 
     def mask_as_output(self, feats, mask_inputs):
         with self._ctx():

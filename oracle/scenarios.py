@@ -305,6 +305,49 @@ def run_video_processor(make_vp, num_frames=11, height=160, width=224, seed=11, 
     return rec
 
 
+def run_image_predictor(ip, height=480, width=640, seed=41):
+    """SAM2ImagePredictor (sam2_image_predictor.py): set_image on a non-square image (antialiased resize), then
+    (1) one click, three candidate masks; (2) a box, single mask with the stability fallback; (3) box + click +
+    the previous low-resolution logits as a dense prompt; (4) two boxes in one batched call (repeat_image)."""
+    vid = BilliardVideo(num_objects=3, height=height, width=width, num_frames=1, seed=seed)
+    img = vid.frame(0)
+    c, boxes = vid.centers(0), vid.boxes(0)
+    rec = {}
+
+    def put(tag, out):
+        masks, ious, low = out
+        rec[f"{tag}.masks_packed"] = np.packbits((np.asarray(masks) > 0).astype(np.uint8))
+        rec[f"{tag}.mask_logits"] = np.asarray(masks, dtype=np.float32)[..., ::4, ::4].copy()
+        rec[f"{tag}.ious"] = np.asarray(ious, dtype=np.float32)
+        rec[f"{tag}.pred_masks"] = np.asarray(low, dtype=np.float32)
+
+    with torch.inference_mode():
+        ip.set_image(img)
+        rec["embedding_shape"] = np.asarray(tuple(ip.get_image_embedding().shape), dtype=np.int64)
+        out = ip.predict(point_coords=np.asarray([c[0]], np.float32), point_labels=np.array([1], np.int32),
+                         multimask_output=True, return_logits=True)
+        put("click", out)
+        best = int(np.argmax(out[1]))
+        out2 = ip.predict(box=np.asarray(boxes[1], np.float32), multimask_output=False, return_logits=True)
+        put("box", out2)
+        out3 = ip.predict(point_coords=np.asarray([c[0]], np.float32), point_labels=np.array([1], np.int32),
+                          box=np.asarray(boxes[0], np.float32), mask_input=out[2][best][None], multimask_output=False,
+                          return_logits=True)
+        put("refine", out3)
+        out4 = ip.predict(box=np.asarray([boxes[1], boxes[2]], np.float32), multimask_output=False, return_logits=True)
+        put("boxes2", out4)
+        m = ip.predict(box=np.asarray(boxes[2], np.float32), multimask_output=False)[0]
+        # thresholded output: the reference hands back float32 0.0 / 1.0, not booleans (sam2_image_predictor.py:299)
+        rec["plain.is_float32_01"] = np.asarray([int(m.dtype == np.float32 and set(np.unique(m)) <= {0.0, 1.0})], dtype=np.int64)
+        rec["plain.shape"] = np.asarray(m.shape, dtype=np.int64)
+    return rec
+
+
+def image_predictor_config():
+    # the reference hard-codes the backbone feature sizes of a 1024^2 input (sam2_image_predictor.py:60-64)
+    return get_config("tiny")
+
+
 def packed_mask_iou(a, b):
     """IoU of two np.packbits arrays."""
     a, b = np.unpackbits(a), np.unpackbits(b)

@@ -90,3 +90,28 @@ def test_from_pretrained_maps_hub_ids_like_the_reference(monkeypatch):
     assert seen["kw"] == {"device": "cuda"}
     with pytest.raises(KeyError):
         SAM2VideoPredictor.from_pretrained("facebook/sam2-hiera-large")
+
+
+def test_factory_accepts_the_reference_style_hydra_overrides():
+    """build_sam.py:111-146: callers pass hydra_overrides_extra such as "++model.fill_hole_area=0"; the factory maps the
+    keys that exist on this path and refuses unknown ones by name (no hydra involved)."""
+    from detsam2_b200.build_sam import build_sam2_video_predictor, parse_hydra_overrides
+    from detsam2_b200.config import get_config
+    from detsam2_b200.weights import synthetic_state_dict
+    from oracle import sam2_oracle as O
+    cfg_over, pred_kw = parse_hydra_overrides(["++model.fill_hole_area=0", "++model.non_overlap_masks=true",
+                                               "++model.sam_mask_decoder_extra_args.dynamic_multimask_stability_thresh=0.95",
+                                               "++model.clear_non_cond_mem_around_input=true"])
+    assert cfg_over == {"fill_hole_area": 0, "non_overlap_masks": True, "dynamic_multimask_stability_thresh": 0.95}
+    assert pred_kw == {"clear_non_cond_mem_around_input": True}
+    cfg = get_config("tiny", image_size=256)
+    eng = O.OracleEngine(cfg, synthetic_state_dict(cfg, 0), fill_holes=False)
+    pred = build_sam2_video_predictor("configs/sam2.1/sam2.1_hiera_t.yaml", device="cpu", engine=eng,
+                                      hydra_overrides_extra=["++model.fill_hole_area=0", "++model.non_overlap_masks=true",
+                                                             "++model.clear_non_cond_mem_around_input=true"])
+    assert pred.fill_hole_area == 0 and pred.non_overlap_masks is True and pred.clear_non_cond_mem_around_input is True
+    import pytest
+    with pytest.raises(ValueError):
+        parse_hydra_overrides(["++model.compile_image_encoder=true"])
+    with pytest.raises(ValueError):
+        parse_hydra_overrides(["nonsense"])
