@@ -327,11 +327,13 @@ def run_image_predictor(ip, height=480, width=640, seed=41):
         out = ip.predict(point_coords=np.asarray([c[0]], np.float32), point_labels=np.array([1], np.int32),
                          multimask_output=True, return_logits=True)
         put("click", out)
-        best = int(np.argmax(out[1]))
         out2 = ip.predict(box=np.asarray(boxes[1], np.float32), multimask_output=False, return_logits=True)
         put("box", out2)
-        out3 = ip.predict(point_coords=np.asarray([c[0]], np.float32), point_labels=np.array([1], np.int32),
-                          box=np.asarray(boxes[0], np.float32), mask_input=out[2][best][None], multimask_output=False,
+        # refinement: the same box plus a click, with the box step's low-resolution logits as the dense prompt (the click
+        # step's candidates are not used here: with random weights they are chaotic — the reference's own bf16 run
+        # deviates by 0.3 on them — and would hand different dense prompts to the implementations under comparison)
+        out3 = ip.predict(point_coords=np.asarray([c[1]], np.float32), point_labels=np.array([1], np.int32),
+                          box=np.asarray(boxes[1], np.float32), mask_input=out2[2][0][None], multimask_output=False,
                           return_logits=True)
         put("refine", out3)
         out4 = ip.predict(box=np.asarray([boxes[1], boxes[2]], np.float32), multimask_output=False, return_logits=True)
