@@ -126,6 +126,7 @@ SYMBOLS = {
     "ds2_downsample4_aa": (C.c_int, [_P, _P, _I, _I, _F, _F, _P]),
     "ds2_mask_prompt_embed": (C.c_int, [_P, _I, _I] + [_P] * 10 + [_P, _P]),
     "ds2_ingest_frames": (C.c_int, [_P, _I, _I, _I, _L, _L, _P, _P, _I, _P]),
+    "ds2_letterbox_frames": (C.c_int, [_P, _I, _I, _I, _L, _L, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
 }
 
 

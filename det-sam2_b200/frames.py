@@ -52,6 +52,27 @@ def load_video_frames(video_path, image_size, offload_video_to_cpu=True, compute
     """
     arrays = None
     paths = None
+    if isinstance(video_path, torch.Tensor):
+        # addition: uint8 RGB frames [N, H, W, 3] ALREADY in HBM (VideoProcessor uploads a chunk once and shares it
+        # between the detector pre-processing and this ingest): straight into ds2_ingest_frames, no host staging
+        t = video_path
+        if not (t.is_cuda and t.dtype == torch.uint8 and t.dim() == 4 and t.shape[3] == 3):
+            raise NotImplementedError("tensor frame sources must be CUDA uint8 [N, H, W, 3] RGB")
+        from . import ops
+        device = t.device
+        lut = _normalize_lut(tuple(img_mean), tuple(img_std))
+        key = (str(device), lut.tobytes())
+        dev_lut = _DEV_LUTS.get(key)
+        if dev_lut is None:
+            dev_lut = _DEV_LUTS[key] = torch.from_numpy(lut.view(np.int16).copy()).to(device)
+        dst = torch.empty(t.shape[0], 3, image_size, image_size, dtype=torch.float16, device=device)
+        ops.ingest_frames(t.contiguous(), dev_lut, dst)
+        if offload_video_to_cpu:
+            images = torch.empty(dst.shape, dtype=torch.float16, pin_memory=True)
+            images.copy_(dst, non_blocking=True)
+            torch.cuda.current_stream(device).synchronize()
+            return images, int(t.shape[1]), int(t.shape[2])
+        return dst, int(t.shape[1]), int(t.shape[2])
     if _is_path(video_path) and os.path.isdir(video_path):
         names = [p for p in os.listdir(video_path) if os.path.splitext(p)[-1] in (".jpg", ".jpeg", ".JPG", ".JPEG")]
         names.sort(key=lambda p: int(os.path.splitext(p)[0]))

@@ -314,6 +314,25 @@ def mask_pack_stats(masks, bits=None, stats=None):
     return bits, stats
 
 
+def letterbox_frames(src_u8, lut, out, new_h, new_w, top, left, pad_value=114):
+    """Detector pre-processing on the device: src_u8 uint8 [N, Hv, Wv, 3] RGB, lut [256] (out's dtype: v / 255),
+    out fp32 / fp16 [N, 3, Hd, Wd] contiguous; the resized frame lands at rows [top, top+new_h), cols [left, left+new_w)."""
+    _req(src_u8, torch.uint8, "letterbox_frames.src_u8")
+    if src_u8.dim() != 4 or src_u8.shape[3] != 3 or src_u8.stride(3) != 1 or src_u8.stride(2) != 3:
+        raise capi.Ds2Error(f"letterbox_frames: src must be [N, Hv, Wv, 3] with packed RGB pixels, got {tuple(src_u8.shape)}")
+    if out.dtype not in (torch.float32, torch.float16) or lut.dtype != out.dtype or not out.is_cuda or not lut.is_cuda:
+        raise capi.Ds2Error("letterbox_frames: out / lut must be CUDA fp32 or fp16 tensors of one dtype")
+    N, Hv, Wv, _ = src_u8.shape
+    if out.dim() != 4 or out.shape[0] != N or out.shape[1] != 3 or not out.is_contiguous() or lut.numel() != 256:
+        raise capi.Ds2Error("letterbox_frames: out must be contiguous [N, 3, Hd, Wd] and lut must hold 256 entries")
+    _chk(_lib().ds2_letterbox_frames(_p(src_u8), N, Hv, Wv, src_u8.stride(1),
+                                     src_u8.stride(0) if N > 1 else max(src_u8.stride(0), src_u8.stride(1) * Hv),
+                                     _p(lut), _p(out), 1 if out.dtype == torch.float32 else 0, out.shape[2], out.shape[3],
+                                     int(new_h), int(new_w), int(top), int(left), int(pad_value), _stream()),
+         "ds2_letterbox_frames")
+    return out
+
+
 def ingest_frames(src_u8, lut, out):
     """Frame ingest (misc.py:336-359 on the device): src_u8 uint8 [N, Hv, Wv, 3] RGB (rows / frames may be strided),
     lut int16 [3, 256] = fp16 bit patterns of the normalised byte values, out fp16 [N, 3, S, S] contiguous."""

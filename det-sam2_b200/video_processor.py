@@ -51,7 +51,7 @@ class VideoProcessor:
                  vis_frame_stride=-1, visualize_prompt=False, frame_buffer_size=30, detect_interval=30,
                  max_frame_num_to_track=60, max_inference_state_frames=60, load_inference_state_path=None,
                  save_inference_state_path=None, *, predictor=None, detector=None, device="cuda", object_stats=False,
-                 frames_on_device=None, offload_state_to_cpu=None):
+                 frames_on_device=None, offload_state_to_cpu=None, detector_preproc=None):
         if vis_frame_stride != -1 or visualize_prompt:
             raise NotImplementedError("matplotlib rendering is outside the hot path; use vis_frame_stride=-1")
         if save_inference_state_path is not None:
@@ -110,6 +110,13 @@ class VideoProcessor:
         if offload_state_to_cpu is None:
             offload_state_to_cpu = getattr(getattr(predictor, "device", None), "type", "cpu") != "cuda"
         self.offload_state_to_cpu = bool(offload_state_to_cpu)
+        # addition: `detector_preproc` = a detsam2_b200.detector_preproc.DeviceLetterbox.  The chunk's
+        # uint8 frames are then uploaded ONCE; the detector is called with the letterboxed [n, 3, H, W] tensor built on
+        # the device from that copy (ultralytics skips its host pre-processing for tensor input) and must return its
+        # boxes in the pixels of that tensor — they are mapped back to frame pixels here; the SAM 2 ingest reads the same
+        # device copy.  None = the reference's flow (BGR ndarrays to the detector).
+        self.detector_preproc = detector_preproc
+        self._chunk_dev_u8 = None
         self.video_stats = {}
         self.timings = {}
         self.inference_state = None
@@ -125,13 +132,22 @@ class VideoProcessor:
         for i, image in enumerate(images):
             frame_idx = past_num_frames + i
             if frame_idx % self.detect_interval == 0:
-                selected.append(np.ascontiguousarray(image[..., ::-1]))  # RGB -> BGR, what YOLO was trained on
+                selected.append(i if self.detector_preproc is not None else
+                                np.ascontiguousarray(image[..., ::-1]))  # RGB -> BGR, what YOLO was trained on
                 absolute.append(frame_idx)
         if not selected:
             return detection_results
         if self.detect_model is None:
             raise RuntimeError("detect_interval != -1 but no detector was provided")
-        for i, dets in enumerate(self.detect_model(selected)):
+        if self.detector_preproc is not None:
+            dev = self._upload_chunk(images)
+            hw = tuple(images[0].shape[:2])
+            results = self.detect_model(self.detector_preproc(dev[selected]))
+            results = [[dict(d, coordinates=self.detector_preproc.unletterbox(d["coordinates"], hw)[0]) for d in dets]
+                       for dets in results]
+        else:
+            results = self.detect_model(selected)
+        for i, dets in enumerate(results):
             dets = list(dets)
             if not self.special_classes_detection:
                 self.special_classes_count = 0
@@ -142,6 +158,22 @@ class VideoProcessor:
                 self.special_classes_count = n_special
             detection_results[f"frame_{absolute[i]}"] = dets
         return detection_results
+
+    def _upload_chunk(self, images):
+        """The chunk's uint8 RGB frames as ONE device tensor [n, H, W, 3] (pinned staging, one asynchronous copy), shared by
+        the detector pre-processing and the SAM 2 ingest of the same chunk."""
+        if self._chunk_dev_u8 is None:
+            dev = self.predictor.device
+            n, (H, W) = len(images), images[0].shape[:2]
+            stage = self.__dict__.get("_u8_stage")
+            if stage is None or stage.numel() < n * H * W * 3:
+                stage = self._u8_stage = torch.empty(n * H * W * 3, dtype=torch.uint8).pin_memory()
+            view = stage[: n * H * W * 3].view(n, H, W, 3)
+            host = view.numpy()
+            for k, im in enumerate(images):
+                np.copyto(host[k], im)
+            self._chunk_dev_u8 = view.to(dev, non_blocking=True)
+        return self._chunk_dev_u8
 
     # ---- prompts (det_sam2_RT.py:271-316) ----------------------------------------------------------
     def Detect_2_SAM2_Prompt(self, detection_results_json):
@@ -184,11 +216,14 @@ class VideoProcessor:
         past_num_frames = self.inference_state["num_frames"] if self.inference_state else 0
         detection_results_json = self.detect_predict(self.frame_buffer, past_num_frames)
         t1 = time.perf_counter()
+        # frames for the predictor: the device copy the detector pre-processing already uploaded, if there is one
+        source = self._chunk_dev_u8 if self._chunk_dev_u8 is not None else self.frame_buffer
+        self._chunk_dev_u8 = None
         if self.inference_state is None:
-            self.inference_state = self.predictor.init_state(video_path=self.frame_buffer,
+            self.inference_state = self.predictor.init_state(video_path=source,
                                                              offload_video_to_cpu=not self.frames_on_device)
         else:
-            self.inference_state = self.predictor.update_state(video_path=self.frame_buffer,
+            self.inference_state = self.predictor.update_state(video_path=source,
                                                                inference_state=self.inference_state)
         t2 = time.perf_counter()
         try:

@@ -302,6 +302,17 @@ int ds2_mask_pack_stats(const float* x, uint8_t* bits, uint64_t* stats, int32_t 
 int ds2_ingest_frames(const uint8_t* src_u8, int32_t N, int32_t Hv, int32_t Wv, int64_t pitch_bytes,
                       int64_t frame_stride_bytes, const uint16_t* lut_3x256, void* dst_f16, int32_t S, void* stream);
 
+/* ---- detector (YOLOv8) pre-processing on the device — SURVEY.md 8f rank 1 -----------------------------------------
+ * replaces, for the frames Det-SAM2 hands to its detector (det_sam2_inference/det_sam2_RT.py:201-245), the HOST work of
+ * ultralytics 8.2.82 (third party, requirements.txt:134): LetterBox (cv2.resize INTER_LINEAR to new_w x new_h, grey
+ * border 114 to Wd x Hd), BGR->RGB, upload, cast, / 255.  src as for ds2_ingest_frames (uint8 RGB already in HBM);
+ * dst planar RGB [N][3][Hd][Wd], fp32 (dst_is_f32) or fp16; lut_256 = the 256 values v / 255 in that dtype.  The
+ * resized frame occupies rows [top, top + new_h), columns [left, left + new_w); byte-exact with cv2.              */
+int ds2_letterbox_frames(const uint8_t* src_u8, int32_t N, int32_t Hv, int32_t Wv, int64_t pitch_bytes,
+                         int64_t frame_stride_bytes, const void* lut_256, void* dst, int32_t dst_is_f32, int32_t Hd,
+                         int32_t Wd, int32_t new_h, int32_t new_w, int32_t top, int32_t left, int32_t pad_value,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif
