@@ -5,6 +5,7 @@
 #include <math.h>
 
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.h"
 
@@ -137,43 +138,63 @@ __device__ __forceinline__ float hires_mask_value(const float* __restrict__ lr, 
   return hy * (hx * lr[y0 * Sl + x0] + lx * lr[y0 * Sl + x1]) + ly * (hx * lr[y1 * Sl + x0] + lx * lr[y1 * Sl + x1]);
 }
 
-__global__ void maskds_stage1_kernel(const float* __restrict__ lowres, int B, int Sl, int binarize, float scale,
-                                     float bias, const float* __restrict__ w, const float* __restrict__ cb,
-                                     const float* __restrict__ lnw, const float* __restrict__ lnb,
-                                     __nv_bfloat16* __restrict__ out) {
+// One CTA = 32 x 8 outputs.  The (2*32+1) x (2*8+1) patch of the never-materialised 1024^2 mask that these outputs read
+// is evaluated ONCE per CTA into shared memory (4.3 bilinear + sigmoid evaluations per output instead of 9; positions
+// outside the mask hold the conv's zero padding), then every thread convolves its 3x3 window from there.
+constexpr int kS1TX = 32, kS1TY = 8;
+constexpr int kS1PW = 2 * kS1TX + 1, kS1PH = 2 * kS1TY + 1;
+
+__global__ void __launch_bounds__(kS1TX * kS1TY)
+maskds_stage1_kernel(const float* __restrict__ lowres, int B, int Sl, int binarize, float scale, float bias,
+                     const float* __restrict__ w, const float* __restrict__ cb, const float* __restrict__ lnw,
+                     const float* __restrict__ lnb, __nv_bfloat16* __restrict__ out) {
+  __shared__ float sh[kS1PH][kS1PW + 1];
   pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   const int So = Sl * 2, Sh = Sl * 4;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= static_cast<long long>(B) * So * So) return;
-  const int ox = static_cast<int>(i % So);
-  const int oy = static_cast<int>((i / So) % So);
-  const int b = static_cast<int>(i / (static_cast<long long>(So) * So));
+  const int tiles_x = (So + kS1TX - 1) / kS1TX, tiles_y = (So + kS1TY - 1) / kS1TY;
+  int t = blockIdx.x;
+  const int tx0 = (t % tiles_x) * kS1TX;
+  t /= tiles_x;
+  const int ty0 = (t % tiles_y) * kS1TY;
+  const int b = t / tiles_y;
   const float* lr = lowres + static_cast<long long>(b) * Sl * Sl;
+  const int X0 = 2 * tx0 - 1, Y0 = 2 * ty0 - 1;
+  for (int i = threadIdx.x; i < kS1PH * kS1PW; i += blockDim.x) {
+    const int py = i / kS1PW, px = i - py * kS1PW;
+    const int Y = Y0 + py, X = X0 + px;
+    float m = 0.f;
+    if (Y >= 0 && Y < Sh && X >= 0 && X < Sh) {
+      const float hv = hires_mask_value(lr, Sl, Y, X);
+      m = (binarize ? (hv > 0.f ? 1.f : 0.f) : 1.f / (1.f + expf(-hv))) * scale + bias;
+    }
+    sh[py][px] = m;
+  }
+  float wr[36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) wr[i] = __ldg(w + i);
+  __syncthreads();
+  const int lx = threadIdx.x % kS1TX, ly = threadIdx.x / kS1TX;
+  const int ox = tx0 + lx, oy = ty0 + ly;
+  if (ox >= So || oy >= So) return;
   float acc[4] = {cb[0], cb[1], cb[2], cb[3]};
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-    const int Y = oy * 2 - 1 + ky;
-    if (Y < 0 || Y >= Sh) continue;
+  for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
-      const int X = ox * 2 - 1 + kx;
-      if (X < 0 || X >= Sh) continue;
-      const float hv = hires_mask_value(lr, Sl, Y, X);
-      const float m = (binarize ? (hv > 0.f ? 1.f : 0.f) : 1.f / (1.f + expf(-hv))) * scale + bias;
+      const float m = sh[2 * ly + ky][2 * lx + kx];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[c] = fmaf(m, w[c * 9 + ky * 3 + kx], acc[c]);
+      for (int c = 0; c < 4; ++c) acc[c] = fmaf(m, wr[c * 9 + ky * 3 + kx], acc[c]);
     }
-  }
   const float u = 0.25f * (acc[0] + acc[1] + acc[2] + acc[3]);
-  float s = 0.f;
+  float sq = 0.f;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) s += (acc[c] - u) * (acc[c] - u);
-  const float rstd = rsqrtf(0.25f * s + 1e-6f);
+  for (int c = 0; c < 4; ++c) sq += (acc[c] - u) * (acc[c] - u);
+  const float rstd = rsqrtf(0.25f * sq + 1e-6f);
   uint2 o;
   __nv_bfloat16* oe = reinterpret_cast<__nv_bfloat16*>(&o);
 #pragma unroll
   for (int c = 0; c < 4; ++c) oe[c] = __float2bfloat16(gelu_erf_c((acc[c] - u) * rstd * lnw[c] + lnb[c]));
-  *reinterpret_cast<uint2*>(out + i * 4) = o;
+  *reinterpret_cast<uint2*>(out + ((static_cast<long long>(b) * So + oy) * So + ox) * 4) = o;
 }
 
 // ---- direct conv3x3 s2 p1 (small Cin, Cout <= 16) + LN2d + GELU, channels-last bf16 ----------------
@@ -183,8 +204,13 @@ __global__ void maskds_conv_kernel(const __nv_bfloat16* __restrict__ x, int B, i
                                    const float* __restrict__ lnw, const float* __restrict__ lnb,
                                    __nv_bfloat16* __restrict__ out) {
   pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
-  __shared__ float sw[COUT * CIN * 9];
-  for (int i = threadIdx.x; i < COUT * CIN * 9; i += blockDim.x) sw[i] = w[i];
+  // weights re-laid out [tap][cin][cout]: the inner loop reads four output channels per 16-byte broadcast load (one
+  // shared-memory load per FMA made this kernel LSU-bound: 576 loads per output pixel)
+  __shared__ __align__(16) float sw[9 * CIN * COUT];
+  for (int i = threadIdx.x; i < COUT * CIN * 9; i += blockDim.x) {
+    const int o = i / (CIN * 9), c = (i / 9) % CIN, tap = i % 9;
+    sw[(tap * CIN + c) * COUT + o] = w[i];
+  }
   __syncthreads();
   const int Ho = Hi / 2, Wo = Wi / 2;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -205,12 +231,29 @@ __global__ void maskds_conv_kernel(const __nv_bfloat16* __restrict__ x, int B, i
       if (ix < 0 || ix >= Wi) continue;
       const __nv_bfloat16* px = x + ((static_cast<long long>(b) * Hi + iy) * Wi + ix) * CIN;
       float xv[CIN];
+      if (CIN == 4) {
+        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(px));
+        const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+        const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+        xv[0] = __low2float(p0);
+        xv[1] = __high2float(p0);
+        xv[2] = __low2float(p1);
+        xv[3] = __high2float(p1);
+      } else {
 #pragma unroll
-      for (int c = 0; c < CIN; ++c) xv[c] = __bfloat162float(px[c]);
+        for (int c = 0; c < CIN; ++c) xv[c] = __bfloat162float(px[c]);
+      }
+      const float4* wt = reinterpret_cast<const float4*>(sw + (ky * 3 + kx) * CIN * COUT);
 #pragma unroll
-      for (int o = 0; o < COUT; ++o)
+      for (int c = 0; c < CIN; ++c)
 #pragma unroll
-        for (int c = 0; c < CIN; ++c) acc[o] = fmaf(xv[c], sw[(o * CIN + c) * 9 + ky * 3 + kx], acc[o]);
+        for (int o4 = 0; o4 < COUT / 4; ++o4) {
+          const float4 w4 = wt[c * (COUT / 4) + o4];
+          acc[4 * o4] = fmaf(xv[c], w4.x, acc[4 * o4]);
+          acc[4 * o4 + 1] = fmaf(xv[c], w4.y, acc[4 * o4 + 1]);
+          acc[4 * o4 + 2] = fmaf(xv[c], w4.z, acc[4 * o4 + 2]);
+          acc[4 * o4 + 3] = fmaf(xv[c], w4.w, acc[4 * o4 + 3]);
+        }
     }
   }
   float u = 0.f;
@@ -222,8 +265,24 @@ __global__ void maskds_conv_kernel(const __nv_bfloat16* __restrict__ x, int B, i
   for (int o = 0; o < COUT; ++o) s += (acc[o] - u) * (acc[o] - u);
   const float rstd = rsqrtf(s / COUT + 1e-6f);
   __nv_bfloat16* po = out + i * COUT;
+  if (COUT % 8 == 0) {
 #pragma unroll
-  for (int o = 0; o < COUT; ++o) po[o] = __float2bfloat16(gelu_erf_c((acc[o] - u) * rstd * lnw[o] + lnb[o]));
+    for (int o8 = 0; o8 < COUT / 8; ++o8) {
+      uint4 pk;
+      uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int o = 8 * o8 + 2 * q;
+        const __nv_bfloat162 v2 = __floats2bfloat162_rn(gelu_erf_c((acc[o] - u) * rstd * lnw[o] + lnb[o]),
+                                                        gelu_erf_c((acc[o + 1] - u) * rstd * lnw[o + 1] + lnb[o + 1]));
+        pw[q] = *reinterpret_cast<const uint32_t*>(&v2);
+      }
+      reinterpret_cast<uint4*>(po)[o8] = pk;
+    }
+  } else {
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) po[o] = __float2bfloat16(gelu_erf_c((acc[o] - u) * rstd * lnw[o] + lnb[o]));
+  }
 }
 
 }  // namespace ds2
@@ -254,15 +313,23 @@ int ds2_dwconv7(const float* x, const float* w, const float* bias, float* y, int
                 int32_t C, void* stream) {
   using namespace ds2;
   DS2_REQUIRE(x && w && y && B > 0 && Hm > 0 && Wm > 0 && C > 0, DS2_E_ARG, "ds2_dwconv7: bad args");
-  constexpr int kDwx = 16;
-  static const int dwy = [] {
-    const char* e = getenv("DS2_DWCONV_DWY");  // tuning switch: output rows per thread (2 or 4)
-    return (e && e[0] == '2') ? 2 : 4;
+  // tile per thread (columns x rows): DS2_DWCONV_TILE = 16x4 (default) | 16x2 | 8x4 | 8x8 — tuning switch
+  static const int cfg = [] {
+    const char* e = getenv("DS2_DWCONV_TILE");
+    if (!e) return 0;
+    if (!strcmp(e, "16x2")) return 1;
+    if (!strcmp(e, "8x4")) return 2;
+    if (!strcmp(e, "8x8")) return 3;
+    return 0;
   }();
+  const int dwx = (cfg >= 2) ? 8 : 16;
+  const int dwy = cfg == 1 ? 2 : (cfg == 3 ? 8 : 4);
   const int threads = C >= 256 ? 256 : ((C + 31) / 32) * 32;
-  dim3 grid(static_cast<unsigned>(B) * ((Hm + dwy - 1) / dwy) * ((Wm + kDwx - 1) / kDwx), (C + threads - 1) / threads);
-  if (dwy == 2) DS2_LAUNCH((dwconv7_kernel<kDwx, 2>), grid, threads, 0, as_stream(stream), x, w, bias, y, B, Hm, Wm, C);
-  else DS2_LAUNCH((dwconv7_kernel<kDwx, 4>), grid, threads, 0, as_stream(stream), x, w, bias, y, B, Hm, Wm, C);
+  dim3 grid(static_cast<unsigned>(B) * ((Hm + dwy - 1) / dwy) * ((Wm + dwx - 1) / dwx), (C + threads - 1) / threads);
+  if (cfg == 1) DS2_LAUNCH((dwconv7_kernel<16, 2>), grid, threads, 0, as_stream(stream), x, w, bias, y, B, Hm, Wm, C);
+  else if (cfg == 2) DS2_LAUNCH((dwconv7_kernel<8, 4>), grid, threads, 0, as_stream(stream), x, w, bias, y, B, Hm, Wm, C);
+  else if (cfg == 3) DS2_LAUNCH((dwconv7_kernel<8, 8>), grid, threads, 0, as_stream(stream), x, w, bias, y, B, Hm, Wm, C);
+  else DS2_LAUNCH((dwconv7_kernel<16, 4>), grid, threads, 0, as_stream(stream), x, w, bias, y, B, Hm, Wm, C);
   return post_launch("dwconv7_kernel");
 }
 
@@ -272,8 +339,9 @@ int ds2_maskds_stage1(const float* lowres, int32_t B, int32_t Sl, int32_t binari
   using namespace ds2;
   DS2_REQUIRE(lowres && w && b && ln_w && ln_b && out_bf16 && B > 0 && Sl > 0, DS2_E_ARG,
               "ds2_maskds_stage1: bad args");
-  const long long n = static_cast<long long>(B) * Sl * 2 * Sl * 2;
-  DS2_LAUNCH((maskds_stage1_kernel), static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream), 
+  const int So = Sl * 2;
+  const long long ctas = static_cast<long long>(B) * ((So + kS1TX - 1) / kS1TX) * ((So + kS1TY - 1) / kS1TY);
+  DS2_LAUNCH((maskds_stage1_kernel), static_cast<unsigned>(ctas), kS1TX * kS1TY, 0, as_stream(stream),
       lowres, B, Sl, binarize, scale, bias, w, b, ln_w, ln_b, reinterpret_cast<__nv_bfloat16*>(out_bf16));
   return post_launch("maskds_stage1_kernel");
 }
