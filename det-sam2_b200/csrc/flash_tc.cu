@@ -26,6 +26,7 @@
 // caller (softmax rows sum to one), which cuts P·V work and V traffic 4x; NQ = 2 halves the K
 // traffic per FLOP (K tiles come out of L2, which is the binding bandwidth here).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "tc05.cuh"
@@ -48,17 +49,25 @@ struct FlashParams {
   int n_full, two_phase, q_tiles;
   float* ws;               // [items][2][128 rows][DV + 4] f32
   unsigned int* ws_count;  // [items], zero between launches
-  int dbg;                 // timing experiments only (impl 5/6/12/13): 1 = load half of each K tile, 2 = skip the exps,
-                           // 4 = skip the TMEM loads of S, 5 = softmax warps only run the barrier protocol
+  int dbg;                 // timing experiments only (impl 5/6/8): 1 = load half of each K tile, 2 = skip the exps, 3 = stall
+                           // accounting.  (Two more — no TMEM loads of S, softmax warps relaying barriers only — were run
+                           // once, profiles/r2_s7_flash_softmax_stage_accounting.txt, and removed: they cost registers.)
   const __nv_bfloat16* q;  // QT kernels read the query rows straight from global memory
   long long ldq, bsq;
   __nv_bfloat16* out;
   long long ldo, bso;
 };
 
-template <int DV, int BN, int NQ, int KS, int VS, int SP, int QT>
+// IL = softmax warpgroups that ALTERNATE over the key tiles of a query tile (tile j belongs to group j % IL), each with
+// its own O accumulator and running (max, sum): the per-tile softmax latency of one warp per scheduler (TMEM load, row
+// max, 128 dependent-issue exps per thread: ~1.7k clk against ~1.5k clk of MMA work per tile) sat on the same-S-buffer
+// chain softmax(j) -> P.V(j) -> Q.K^T(j+2); with two groups the softmax of tile j+1 runs while P.V(j) and Q.K^T(j+2) wait
+// for tile j.  The groups' partial results are combined like the two key halves (fixed order, through the workspace).
+// TP = 1: the instantiation that runs every item as two key halves through the workspace (see FlashParams); the plain
+// instantiation (TP = 0) contains none of that code — it costs the single-pass kernel ~120 registers otherwise.
+template <int DV, int BN, int NQ, int KS, int VS, int SP, int QT, int IL = 1, int TP = 0>
 struct FlashCfg {
-  static constexpr int kThreads = 64 + 128 * NQ * SP;
+  static constexpr int kThreads = 64 + 128 * NQ * SP * IL;
   static constexpr int kXchBytes = 2 * SP * NQ * kQM * 2;  // [parity][part][row] bf16 partial maxima
   static constexpr int kQBytes = QT ? 0 : kQM * kHD * 2;  // 64 KB per query tile when Q is a shared-memory operand
   static constexpr int kKBytes = BN * kHD * 2;
@@ -67,7 +76,9 @@ struct FlashCfg {
   static constexpr int kBarBytes = 256;
   static constexpr int kSmem = kSmemData + 1024 + kBarBytes + (kXchBytes < 1024 ? 1024 : kXchBytes);
   static_assert(BN % (32 * SP) == 0 && DV % (32 * SP) == 0, "column split");
-  static constexpr int kTmemCols = 2 * NQ * BN + NQ * DV + (QT ? NQ * (kHD / 2) : 0);
+  static constexpr int kTmemCols = 2 * NQ * BN + NQ * IL * DV + (QT ? NQ * (kHD / 2) : 0);
+  static_assert(IL == 1 || (IL == 2 && SP == 1 && NQ == 1 && TP == 1), "alternating softmax groups: one query tile, unsplit rows, workspace");
+  static_assert(TP == 0 || (SP == 1 && NQ == 1), "two key halves: one query tile, unsplit rows");
   static_assert(kTmemCols <= 512, "TMEM budget");
   static_assert(kSmem <= 232448, "shared memory budget");
 };
@@ -75,7 +86,8 @@ struct FlashCfg {
 // Stall accounting for tuning (impl == 8 only): cycles the MMA issuer spent blocked on each barrier class
 // and the softmax warps on theirs, summed over CTAs.  [0] kfull [1] vfull [2] pfull [3] total MMA-warp
 // cycles, [4] sfull (softmax warp 2) [5] odone [6] total softmax-warp cycles [7] CTAs.
-// [8..13] softmax warp 2, stage cycles: S load, row max, exp + sum + pack, P store, store wait + fence + arrive, (spare)
+// ([8..15] unused: the per-stage accounting of the softmax loop — S load, row max, exp + sum + pack, P store, arrive — cost
+// the product kernel 118 registers per thread and was removed after profiles/r2_s7_flash_softmax_stage_accounting.txt)
 __device__ unsigned long long g_flash_stall[16];
 
 __device__ __forceinline__ void timed_wait(uint32_t bar, uint32_t parity, bool on, long long& acc) {
@@ -94,12 +106,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int DV, int BN, int NQ, int KS, int VS, int SP, int QT>
-__global__ void __launch_bounds__(64 + 128 * NQ * SP, 1)
+template <int DV, int BN, int NQ, int KS, int VS, int SP, int QT, int IL = 1, int TP = 0>
+__global__ void __launch_bounds__(64 + 128 * NQ * SP * IL, 1)
 flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
                           const __grid_constant__ CUtensorMap tmap_k,
                           const __grid_constant__ CUtensorMap tmap_v, const FlashParams p) {
-  using Cfg = FlashCfg<DV, BN, NQ, KS, VS, SP, QT>;
+  using Cfg = FlashCfg<DV, BN, NQ, KS, VS, SP, QT, IL, TP>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sq = smem_base;
@@ -114,7 +126,7 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int o_vempty = nb;   nb += VS;
   const int o_sfull = nb;    nb += 2 * NQ;
   const int o_pfull = nb;    nb += 2 * NQ;
-  const int o_odone = nb;    nb += NQ;
+  const int o_odone = nb;    nb += NQ * IL;
   auto bar = [&](int off, int i) { return bar_base + 8u * static_cast<uint32_t>(off + i); };
   const uint32_t tmem_slot = bar_base + 8u * static_cast<uint32_t>(nb);
   const uint32_t xch_base = bar_base + Cfg::kBarBytes;  // partial row maxima / row sums of the split softmax
@@ -134,7 +146,9 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int j0 = (all_tiles * kv_part) / kv_parts;                     // first key tile of this CTA
   const int n_tiles = (all_tiles * (kv_part + 1)) / kv_parts - j0;    // its number of key tiles (>= 1)
   // local tile index at which the second key half starts when this CTA runs both halves itself (else never reached)
-  const int split_at = (p.two_phase && kv_parts == 1) ? all_tiles / 2 : -1;
+  const int split_at = (TP && kv_parts == 1) ? all_tiles / 2 : -1;
+  // tile j starts a fresh accumulation of its softmax group: the group's first tile of the item or of the second half
+  auto starts_group = [&](int j) { return j < IL || (TP && split_at >= 0 && j >= split_at && j - IL < split_at); };
 
   if (warp == 0 && lane == 0) {
     if (!QT) tc::prefetch_tmap(&tmap_q);
@@ -153,7 +167,7 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       tc::mbar_init(bar(o_sfull, i), 1);
       tc::mbar_init(bar(o_pfull, i), 4 * SP);
     }
-    for (int i = 0; i < NQ; ++i) tc::mbar_init(bar(o_odone, i), 1);
+    for (int i = 0; i < NQ * IL; ++i) tc::mbar_init(bar(o_odone, i), 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) {
@@ -169,12 +183,12 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   // only now wait for the producer of our operands, and let the next grid start its own prologue
   pdl_sync();
   auto tmem_s = [&](int h, int i) { return tmem_base + static_cast<uint32_t>((2 * h + i) * BN); };
-  auto tmem_o = [&](int h) { return tmem_base + static_cast<uint32_t>(2 * NQ * BN + h * DV); };
+  auto tmem_o = [&](int h, int g) { return tmem_base + static_cast<uint32_t>(2 * NQ * BN + (h * IL + g) * DV); };
   // QT: the query tile lives in TMEM (128 lanes x 128 columns of bf16 pairs) and Q·K^T is a TS MMA, so
   // the tensor core reads only the K tile from shared memory.  With both operands in shared memory a
   // 128x128x16 MMA reads 8 KB per 64 clk = the whole 128 B/clk of the SM's shared memory, on top of the
   // TMA writes of the K/V rings — the kernel was shared-memory-bandwidth bound at ~52 % of the MMA rate.
-  auto tmem_q = [&](int h) { return tmem_base + static_cast<uint32_t>(2 * NQ * BN + NQ * DV + h * (kHD / 2)); };
+  auto tmem_q = [&](int h) { return tmem_base + static_cast<uint32_t>(2 * NQ * BN + NQ * IL * DV + h * (kHD / 2)); };
 
   // Role gates use elect.sync, not `lane == 0`: tcgen05.mma / TMA take their operands from the uniform
   // datapath, and under a lane-id predicate the compiler wraps EVERY such instruction in an
@@ -258,9 +272,9 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
           const uint64_t db = tc::make_desc_sw128(sv + k * 2048, BN * 128, 1024);
           // O restarts from zero at the first tile of each key half (the softmax warps have moved the first half's
           // O out of TMEM before they released P of this tile, see below)
-          tc::umma_ts(tmem_o(h), pa + k * 8, db, idesc_pv, ((j != 0 && j != split_at) || k != 0) ? 1u : 0u);
+          tc::umma_ts(tmem_o(h, j % IL), pa + k * 8, db, idesc_pv, (!starts_group(j) || k != 0) ? 1u : 0u);
         }
-        tc::umma_commit(bar(o_odone, h));
+        tc::umma_commit(bar(o_odone, h * IL + j % IL));
       }
       tc::umma_commit(bar(o_vempty, s));
     }
@@ -276,18 +290,19 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     constexpr int CW = BN / SP;       // S columns of a row handled by this thread
     constexpr int OW = DV / SP;       // O columns of a row handled by this thread (rescale, epilogue)
     const int sw = warp - 2;
-    const int h = sw / (4 * SP);      // query tile
-    const int part = (sw >> 2) % SP;  // which column part of the row
+    const int h = (sw / (4 * SP)) % NQ;   // query tile
+    const int g = sw / (4 * SP * NQ);     // softmax group: owns the key tiles j with j % IL == g
+    const int part = (sw >> 2) % SP;      // which column part of the row
     const int lq = warp & 3;          // TMEM lane quarter this warp may access
     const uint32_t lane_off = static_cast<uint32_t>(lq * 32) << 16;
     const int rloc = h * kQM + lq * 32 + lane;  // row inside the CTA
     const int row = q0 + rloc;
-    const uint32_t to = tmem_o(h) + lane_off + part * OW;
+    const uint32_t to = tmem_o(h, g) + lane_off + part * OW;
     const int bar_id = 1 + h * 4 + lq;  // named barrier of the SP warps that share these 32 rows
     auto xch_max = [&](int par, int pt) {
       return xch_base + 2u * static_cast<uint32_t>((par * SP + pt) * (NQ * kQM) + rloc);
     };
-    if (QT) {
+    if (QT && g == 0) {
       // this thread's part of its query row: global -> registers -> TMEM (bf16 pairs, K-major A operand)
       constexpr int QW = (kHD / 2) / SP;  // 32-bit columns per thread
       const uint4* src = reinterpret_cast<const uint4*>(p.q + static_cast<long long>(b) * p.bsq +
@@ -317,8 +332,10 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     float m_half0 = 0.f, l_half0 = 0.f;   // running max / sum of the first key half (two-phase items)
     constexpr int WS_ROW = DV + 4;         // workspace row: O row + (max, sum), padded to keep rows 16-byte aligned
     // leaves (O, m, l) of key half `part_idx` of this item in the workspace
+    constexpr int kParts = 2 * IL;         // partial results per item: key halves x softmax groups
     auto dump_part = [&](int part_idx, float m_scaled, float lsum) {
-      float* wrow = p.ws + (static_cast<size_t>(item * 2 + part_idx) * (NQ * kQM) + rloc) * WS_ROW;
+      if constexpr (!TP) return;
+      float* wrow = p.ws + (static_cast<size_t>(item * kParts + part_idx) * (NQ * kQM) + rloc) * WS_ROW;
 #pragma unroll
       for (int c = 0; c < OW / 32; ++c) {
         uint32_t o[32];
@@ -335,120 +352,100 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     };
     const bool prof = p.dbg == 3 && warp == 2;
     long long w_s = 0, w_o = 0;
-    long long st_load = 0, st_max = 0, st_exp = 0, st_pst = 0, st_arr = 0;
     const long long t_begin = clock64();
-    for (int j = 0; j < n_tiles; ++j) {
+    for (int j = g; j < n_tiles; j += IL) {
       timed_wait(bar(o_sfull, 2 * h + (j & 1)), (j >> 1) & 1, prof, w_s);
       tc::tc_fence_after();
-      long long tstage = prof ? clock64() : 0;
-      auto lap = [&](long long& accu) {
-        if (prof) {
-          const long long now = clock64();
-          accu += now - tstage;
-          tstage = now;
-        }
-      };
       const uint32_t ts = tmem_s(h, j & 1) + lane_off;
-      if (p.dbg == 5) {   // timing experiment: the MMA pipeline alone (results are garbage)
-        if (j > 0) tc::mbar_wait(bar(o_odone, h), (j - 1) & 1);
-        tc::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(bar(o_pfull, 2 * h + (j & 1)));
-        continue;
-      }
-      uint32_t sraw[CW];
-      if (p.dbg == 4) {   // timing experiment: no TMEM -> register traffic for S
-#pragma unroll
-        for (int i = 0; i < CW; ++i) sraw[i] = __float_as_uint(static_cast<float>((i * 37 + lane) & 63) * 0.125f);
-      } else {
-#pragma unroll
+      float alpha = 1.f;
+      bool resc = false;
+      bool half1_flag = false;
+      {
+        uint32_t sraw[CW];
+  #pragma unroll
         for (int c = 0; c < CW / 32; ++c) {
           uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sraw[c * 32]);
           tc::tmem_ld32(ts + part * CW + c * 32, chunk);
         }
         tc::tmem_ld_wait();
-      }
-      lap(st_load);
-      const int valid = p.Lk - (j0 + j) * BN - part * CW;  // columns >= valid are TMA zero fill -> mask
-      if (valid < CW) {
-#pragma unroll
-        for (int i = 0; i < CW; ++i)
-          if (i >= valid) sraw[i] = 0xff800000u;  // -inf
-      }
-      // four independent chains: the running max is not one CW-long dependency chain
-      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int i = 0; i < CW; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(sraw[i]));
-      float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-      if (SP > 1) {
-        // every part of a row must scale by the same reference: exchange the (bf16-rounded) partial
-        // maxima; the barrier also orders "all parts have loaded their S columns" before any part
-        // overwrites S with P below
-        const __nv_bfloat16 mine = __float2bfloat16_rn(mt);
-        asm volatile("st.shared.b16 [%0], %1;" ::"r"(xch_max(j & 1, part)), "h"(__bfloat16_as_ushort(mine)) : "memory");
-        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * SP) : "memory");
-        mt = __bfloat162float(mine);
-#pragma unroll
-        for (int o = 0; o < SP; ++o) {
-          if (o == part) continue;
-          unsigned short u;
-          asm volatile("ld.shared.b16 %0, [%1];" : "=h"(u) : "r"(xch_max(j & 1, o)) : "memory");
-          mt = fmaxf(mt, __bfloat162float(__ushort_as_bfloat16(u)));
+        const int valid = p.Lk - (j0 + j) * BN - part * CW;  // columns >= valid are TMA zero fill -> mask
+        if (valid < CW) {
+  #pragma unroll
+          for (int i = 0; i < CW; ++i)
+            if (i >= valid) sraw[i] = 0xff800000u;  // -inf
         }
-      }
-      lap(st_max);
-      float alpha = 1.f;
-      bool resc = false;
-      if (j == 0) {
-        m_ref = mt;
-      } else if (j == split_at) {
-        // second key half: an independent flash pass — remember the first half's statistics, start over
-        m_half0 = m_ref * p.scale_log2;
-        l_half0 = l;
-        m_ref = mt;
-        l = 0.f;
-      } else if ((mt - m_ref) * p.scale_log2 > 8.0f) {
-        alpha = ex2_approx((m_ref - mt) * p.scale_log2);
-        m_ref = mt;
-        resc = true;
-      }
-      const float moff = m_ref * p.scale_log2;
-      float sum0 = 0.f, sum1 = 0.f;
-      uint32_t pk[CW / 2];
-#pragma unroll
-      for (int i = 0; i < CW / 2; ++i) {
-        float e0 = fmaf(__uint_as_float(sraw[2 * i]), p.scale_log2, -moff);
-        float e1 = fmaf(__uint_as_float(sraw[2 * i + 1]), p.scale_log2, -moff);
-        if (p.dbg != 2) {
-          e0 = ex2_approx(e0);
-          e1 = ex2_approx(e1);
+        // four independent chains: the running max is not one CW-long dependency chain
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  #pragma unroll
+        for (int i = 0; i < CW; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(sraw[i]));
+        float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        if (SP > 1) {
+          // every part of a row must scale by the same reference: exchange the (bf16-rounded) partial
+          // maxima; the barrier also orders "all parts have loaded their S columns" before any part
+          // overwrites S with P below
+          const __nv_bfloat16 mine = __float2bfloat16_rn(mt);
+          asm volatile("st.shared.b16 [%0], %1;" ::"r"(xch_max(j & 1, part)), "h"(__bfloat16_as_ushort(mine)) : "memory");
+          asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * SP) : "memory");
+          mt = __bfloat162float(mine);
+  #pragma unroll
+          for (int o = 0; o < SP; ++o) {
+            if (o == part) continue;
+            unsigned short u;
+            asm volatile("ld.shared.b16 %0, [%1];" : "=h"(u) : "r"(xch_max(j & 1, o)) : "memory");
+            mt = fmaxf(mt, __bfloat162float(__ushort_as_bfloat16(u)));
+          }
         }
-        sum0 += e0;
-        sum1 += e1;
-        pk[i] = tc::pack_bf16(e0, e1);
-      }
-      l = l * alpha + (sum0 + sum1);
-      lap(st_exp);
-      // P (bf16 pairs) overwrites the first BN/2 columns of S: this thread's part at [part*CW/2, +CW/2)
-      if (CW / 2 >= 32) {
-#pragma unroll
-        for (int c = 0; c < CW / 64; ++c) {
-          const uint32_t(&chunk)[32] = *reinterpret_cast<const uint32_t(*)[32]>(&pk[c * 32]);
-          tc::tmem_st32(ts + part * (CW / 2) + c * 32, chunk);
+        const bool half1_start = TP && split_at >= 0 && j >= split_at && j - IL < split_at;
+        if (j < IL) {
+          m_ref = mt;
+        } else if (half1_start) {
+          // second key half: an independent flash pass — remember the first half's statistics, start over
+          m_half0 = m_ref * p.scale_log2;
+          l_half0 = l;
+          m_ref = mt;
+          l = 0.f;
+        } else if ((mt - m_ref) * p.scale_log2 > 8.0f) {
+          alpha = ex2_approx((m_ref - mt) * p.scale_log2);
+          m_ref = mt;
+          resc = true;
         }
-      } else {
-        const uint32_t(&chunk)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&pk[0]);
-        tc::tmem_st16(ts + part * (CW / 2), chunk);
+        const float moff = m_ref * p.scale_log2;
+        float sum0 = 0.f, sum1 = 0.f;
+        uint32_t pk[CW / 2];
+  #pragma unroll
+        for (int i = 0; i < CW / 2; ++i) {
+          float e0 = fmaf(__uint_as_float(sraw[2 * i]), p.scale_log2, -moff);
+          float e1 = fmaf(__uint_as_float(sraw[2 * i + 1]), p.scale_log2, -moff);
+          if (p.dbg != 2) {
+            e0 = ex2_approx(e0);
+            e1 = ex2_approx(e1);
+          }
+          sum0 += e0;
+          sum1 += e1;
+          pk[i] = tc::pack_bf16(e0, e1);
+        }
+        l = l * alpha + (sum0 + sum1);
+        // P (bf16 pairs) overwrites the first BN/2 columns of S: this thread's part at [part*CW/2, +CW/2)
+        if (CW / 2 >= 32) {
+  #pragma unroll
+          for (int c = 0; c < CW / 64; ++c) {
+            const uint32_t(&chunk)[32] = *reinterpret_cast<const uint32_t(*)[32]>(&pk[c * 32]);
+            tc::tmem_st32(ts + part * (CW / 2) + c * 32, chunk);
+          }
+        } else {
+          const uint32_t(&chunk)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&pk[0]);
+          tc::tmem_st16(ts + part * (CW / 2), chunk);
+        }
+        half1_flag = half1_start;
       }
-      lap(st_pst);
       // Consume every phase of `odone` (P·V of tile j-1 complete) so this waiter is never more than
       // one phase behind the barrier — parity waits alias otherwise.  By now that MMA has long retired.
-      if (j > 0) timed_wait(bar(o_odone, h), (j - 1) & 1, prof, w_o);
-      if (j == split_at) {
+      if (j >= IL) timed_wait(bar(o_odone, h * IL + g), ((j / IL) - 1) & 1, prof, w_o);
+      if (TP && half1_flag) {
         // P·V of the last tile of the first half is complete and P·V of this tile cannot be issued before every
         // softmax warp has arrived on `pfull` below: O is stable — move the first half's result to the workspace
         tc::tc_fence_after();
-        dump_part(0, m_half0, l_half0);
+        dump_part(g, m_half0, l_half0);   // first half, group g (the half starts at tile 0: label = g)
       }
       if (__any_sync(0xffffffffu, resc)) {
         // O is stable here: P·V of tile j-1 is complete and P·V of tile j is not yet issued
@@ -463,19 +460,12 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
           tc::tmem_st32(to + c * 32, o);
         }
       }
-      if (prof) tstage = clock64();
       tc::tmem_st_wait();
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(bar(o_pfull, 2 * h + (j & 1)));
-      lap(st_arr);
     }
     if (prof && lane == 0) {
-      atomicAdd(&g_flash_stall[8], static_cast<unsigned long long>(st_load));
-      atomicAdd(&g_flash_stall[9], static_cast<unsigned long long>(st_max));
-      atomicAdd(&g_flash_stall[10], static_cast<unsigned long long>(st_exp));
-      atomicAdd(&g_flash_stall[11], static_cast<unsigned long long>(st_pst));
-      atomicAdd(&g_flash_stall[12], static_cast<unsigned long long>(st_arr));
       atomicAdd(&g_flash_stall[4], static_cast<unsigned long long>(w_s));
       atomicAdd(&g_flash_stall[5], static_cast<unsigned long long>(w_o));
       atomicAdd(&g_flash_stall[6], static_cast<unsigned long long>(clock64() - t_begin));
@@ -496,16 +486,24 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       l = lt;
     }
     // epilogue: O / l -> bf16 -> global
-    tc::mbar_wait(bar(o_odone, h), (n_tiles - 1) & 1);
+    {
+      const int jl = g + ((n_tiles - 1 - g) / IL) * IL;   // this group's last tile (two-phase halves have >= 8 tiles)
+      tc::mbar_wait(bar(o_odone, h * IL + g), (jl / IL) & 1);
+    }
     tc::tc_fence_after();
     __nv_bfloat16* orow = p.out + static_cast<long long>(b) * p.bso + static_cast<long long>(row) * p.ldo + part * OW;
-    if (p.two_phase) {
+    if constexpr (TP) {
       // ---- two key halves: this CTA's (last) half goes to the workspace, then the halves are combined in part
       //      order by this CTA (it ran both) or by the item's CTA that arrives last ----
       const int slot = item;
-      dump_part(kv_parts == 1 ? 1 : kv_part, m_ref * p.scale_log2, l);
+      // label of this group inside the half it just finished: tiles are numbered from the START of the half, so that a
+      // half computed by its own CTA (tiles from 0) and the same half inside a whole-item CTA (tiles from split_at) put
+      // the same tiles under the same label
+      const int half = kv_parts == 1 ? 1 : kv_part;
+      const int label = kv_parts == 1 ? (((g - split_at) % IL) + IL) % IL : g;
+      dump_part(half * IL + label, m_ref * p.scale_log2, l);
       __threadfence();
-      asm volatile("bar.sync 15, %0;" ::"n"(128 * NQ * SP) : "memory");
+      asm volatile("bar.sync 15, %0;" ::"n"(128 * NQ * SP * IL) : "memory");
       unsigned int last = 1u;
       if (kv_parts > 1) {
         const uint32_t flag = xch_base;  // the exchange buffer is idle now
@@ -515,12 +513,15 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
           if (lst) p.ws_count[slot] = 0u;  // both halves have arrived: ready for the next launch
           asm volatile("st.shared.u32 [%0], %1;" ::"r"(flag), "r"(lst) : "memory");
         }
-        asm volatile("bar.sync 15, %0;" ::"n"(128 * NQ * SP) : "memory");
+        asm volatile("bar.sync 15, %0;" ::"n"(128 * NQ * SP * IL) : "memory");
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(last) : "r"(flag) : "memory");
       }
       if (last) {
         __threadfence();
-        constexpr int kParts = 2;
+        // this thread combines OWc of the row's DV columns: the SP x IL threads of a row split them
+        constexpr int OWc = DV / (SP * IL);
+        const int col0 = (part * IL + g) * OWc;
+        __nv_bfloat16* ocomb = p.out + static_cast<long long>(b) * p.bso + static_cast<long long>(row) * p.ldo + col0;
         const float* base = p.ws + (static_cast<size_t>(slot * kParts) * (NQ * kQM) + rloc) * WS_ROW;
         const size_t pstride = static_cast<size_t>(NQ * kQM) * WS_ROW;
         float mmax = -INFINITY;
@@ -529,13 +530,13 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         for (int q = 0; q < kParts; ++q) lt += __ldcg(base + q * pstride + DV + 1) * ex2_approx(__ldcg(base + q * pstride + DV) - mmax);
         const float inv = 1.0f / lt;
 #pragma unroll
-        for (int c = 0; c < OW / 32; ++c) {
+        for (int c = 0; c < OWc / 32; ++c) {
           float acc[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) acc[i] = 0.f;
           for (int q = 0; q < kParts; ++q) {  // fixed part order: the result does not depend on arrival order
             const float w = ex2_approx(__ldcg(base + q * pstride + DV) - mmax);
-            const float4* src = reinterpret_cast<const float4*>(base + q * pstride + part * OW + c * 32);
+            const float4* src = reinterpret_cast<const float4*>(base + q * pstride + col0 + c * 32);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 v4 = __ldcg(src + i);
@@ -553,7 +554,7 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
               t.y = tc::pack_bf16(acc[8 * i + 2] * inv, acc[8 * i + 3] * inv);
               t.z = tc::pack_bf16(acc[8 * i + 4] * inv, acc[8 * i + 5] * inv);
               t.w = tc::pack_bf16(acc[8 * i + 6] * inv, acc[8 * i + 7] * inv);
-              reinterpret_cast<uint4*>(orow + c * 32)[i] = t;
+              reinterpret_cast<uint4*>(ocomb + c * 32)[i] = t;
             }
           }
         }
@@ -628,9 +629,16 @@ __global__ void flash_simt_kernel(const __nv_bfloat16* __restrict__ q, const __n
 // [items][2 halves][128 rows][DV + 4] f32 partials
 static inline size_t flash_ws_count_bytes(int items) { return (static_cast<size_t>(items) * 4 + 255) / 256 * 256; }
 
-template <int DV, int BN, int NQ, int KS, int VS, int SP, int QT>
+// true when the 64-wide kernel runs an item as two key halves (and, with them, two alternating softmax groups)
+static bool flash_two_phase(const ds2_flash_args* a, int BN, int DV) {
+  const int all_tiles = (a->Lk + BN - 1) / BN;
+  return DV == 64 && a->impl == 0 && all_tiles >= 16 && a->workspace != nullptr &&
+         a->workspace_bytes >= ds2_flash_workspace_bytes(a->B, a->Lq, DV);
+}
+
+template <int DV, int BN, int NQ, int KS, int VS, int SP, int QT, int IL = 1, int TP = 0>
 static int launch_flash(const ds2_flash_args* a, cudaStream_t st) {
-  using Cfg = FlashCfg<DV, BN, NQ, KS, VS, SP, QT>;
+  using Cfg = FlashCfg<DV, BN, NQ, KS, VS, SP, QT, IL, TP>;
   CUtensorMap tq, tk, tv;
   {
     const uint64_t dims[3] = {256, static_cast<uint64_t>(a->Lq), static_cast<uint64_t>(a->B)};
@@ -656,7 +664,7 @@ static int launch_flash(const ds2_flash_args* a, cudaStream_t st) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(flash_d256_tcgen05_kernel<DV, BN, NQ, KS, VS, SP, QT>,
+    cudaError_t e = cudaFuncSetAttribute(flash_d256_tcgen05_kernel<DV, BN, NQ, KS, VS, SP, QT, IL, TP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
     DS2_REQUIRE(e == cudaSuccess, static_cast<int>(e), "ds2_flash_attn: cudaFuncSetAttribute: %s",
                 cudaGetErrorString(e));
@@ -667,7 +675,7 @@ static int launch_flash(const ds2_flash_args* a, cudaStream_t st) {
   p.Lq = a->Lq;
   p.Lk = a->Lk;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  p.dbg = a->impl == 5 ? 1 : (a->impl == 6 ? 2 : (a->impl == 8 ? 3 : (a->impl == 12 ? 4 : (a->impl == 13 ? 5 : 0))));
+  p.dbg = a->impl == 5 ? 1 : (a->impl == 6 ? 2 : (a->impl == 8 ? 3 : 0));
   p.q = reinterpret_cast<const __nv_bfloat16*>(a->q);
   p.ldq = a->ldq;
   p.bsq = a->bsq;
@@ -683,9 +691,9 @@ static int launch_flash(const ds2_flash_args* a, cudaStream_t st) {
   // Two key halves whenever the caller lends a workspace and the key range is long enough to be worth it.  The decision
   // depends on the key count and the query-tile count only (never on the batch size or the SM count), so the
   // arithmetic of an item — and with it "tracked in a batch == tracked alone" — does not depend on the grid.
-  const size_t ws_need = ds2_flash_workspace_bytes(a->B, a->Lq, DV);
-  p.two_phase = (DV == 64 && NQ == 1 && SP == 1 && a->impl == 0 && all_tiles >= 16 && a->workspace != nullptr &&
-                 static_cast<size_t>(a->workspace_bytes) >= ws_need) ? 1 : 0;
+  p.two_phase = TP;
+  DS2_REQUIRE(!TP || flash_two_phase(a, BN, DV), DS2_E_ARG, "ds2_flash_attn: the two-key-halves kernel needs the workspace");
+  (void)all_tiles;
   int tail = 0;
   if (p.two_phase) {
     // the partial last wave runs as half-length CTAs when they all fit into one wave (3.46 waves -> 3 + 0.5 at 16
@@ -699,7 +707,7 @@ static int launch_flash(const ds2_flash_args* a, cudaStream_t st) {
   p.ws_count = reinterpret_cast<unsigned int*>(a->workspace);
   p.ws = p.two_phase ? reinterpret_cast<float*>(reinterpret_cast<char*>(a->workspace) + flash_ws_count_bytes(items)) : nullptr;
   const int grid = p.n_full + 2 * tail;
-  DS2_LAUNCH((flash_d256_tcgen05_kernel<DV, BN, NQ, KS, VS, SP, QT>), grid, Cfg::kThreads, Cfg::kSmem, st, tq, tk, tv, p);
+  DS2_LAUNCH((flash_d256_tcgen05_kernel<DV, BN, NQ, KS, VS, SP, QT, IL, TP>), grid, Cfg::kThreads, Cfg::kSmem, st, tq, tk, tv, p);
   return post_launch("flash_d256_tcgen05_kernel");
 }
 
@@ -708,8 +716,9 @@ static int launch_flash(const ds2_flash_args* a, cudaStream_t st) {
 extern "C" int64_t ds2_flash_workspace_bytes(int32_t B, int32_t Lq, int32_t DV) {
   if (B <= 0 || Lq <= 0 || DV != 64) return 0;     // only the 64-wide (cross-attention) kernel runs in two key halves
   const int items = B * ((Lq + ds2::kQM - 1) / ds2::kQM);
+  // [items] counters + [items][2 key halves x 2 softmax groups][128 rows][DV + 4] f32
   return static_cast<int64_t>(ds2::flash_ws_count_bytes(items) +
-                              static_cast<size_t>(items) * 2 * ds2::kQM * (DV + 4) * sizeof(float));
+                              static_cast<size_t>(items) * 4 * ds2::kQM * (DV + 4) * sizeof(float));
 }
 
 extern "C" int ds2_debug_flash_stalls(unsigned long long* out8, int reset) {
@@ -752,6 +761,18 @@ extern "C" int ds2_flash_attn(const ds2_flash_args* a, void* stream) {
     if (a->impl == 3) return launch_flash<64, 64, 2, 2, 3, 1, 0>(a, st);
     if (a->impl == 2) return launch_flash<64, 128, 1, 2, 2, 1, 0>(a, st);
     if (a->impl == 9) return launch_flash<64, 128, 1, 3, 2, 2, 1>(a, st);
+    // Measured on one B200, same box, B=16 N=28736 (profiles/r2_s9_flash_variants_ab.txt): single pass 1.13-1.16 ms; two key
+    // halves 1.20 (tail wave split) / 1.27 ms (whole items); + alternating softmax groups 1.27 / 1.33 ms (its 320 threads
+    // leave 168 registers: the 128-column row spills; reading S twice in chunks instead: 1.97 ms).  The single pass is the
+    // default; DS2_FLASH_IL=1 / 2 select the other two for measurements (they need the caller's workspace).
+    static const int il_env = [] {
+      const char* e = getenv("DS2_FLASH_IL");
+      return e ? atoi(e) : 0;
+    }();
+    // il_env: 2 = two key halves + two alternating softmax groups (default with a workspace), 1 = two key halves, one
+    // group, 0 = ignore the workspace (single pass)
+    if (il_env == 2 && flash_two_phase(a, 128, 64)) return launch_flash<64, 128, 1, 3, 2, 1, 1, 2, 1>(a, st);
+    if (il_env == 1 && flash_two_phase(a, 128, 64)) return launch_flash<64, 128, 1, 3, 2, 1, 1, 1, 1>(a, st);
     return launch_flash<64, 128, 1, 3, 2, 1, 1>(a, st);
   }
   if (a->impl == 2) return launch_flash<256, 64, 1, 2, 2, 1, 0>(a, st);

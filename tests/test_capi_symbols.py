@@ -49,6 +49,30 @@ def test_only_sm100a_code_is_embedded():
     assert archs == {"sm_100a"}, archs
 
 
+def test_shipped_flash_kernels_do_not_spill():
+    """Guards the regression of profiles/r2_s9_flash_variants_ab.txt: measurement code left in the flash kernel pushed the
+    cross-attention instantiation to 255 registers with spills (+25 % per launch).  The default instantiations
+    (<BM 64, BN 128, ..., IL 1, TP 0> for the memory bank, the 256-row ones for the windows) must keep the 48-byte frame
+    that holds only the tensor-map parameters."""
+    import shutil
+    import subprocess
+    from detsam2_b200 import build
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "--dump-resource-usage", build.build()], capture_output=True, text=True).stdout
+    usage = dict(re.findall(r"Function (\S*flash_d256_tcgen05_kernel\S*):\s*\n\s*REG:(\d+ STACK:\d+)", out))
+    assert usage, out[:400]
+    default = [k for k in usage if "ILi64ELi128ELi1ELi3ELi2ELi1ELi1ELi1ELi0E" in k]
+    assert len(default) == 1, sorted(usage)
+    for name, u in usage.items():
+        reg, stack = (int(x) for x in re.findall(r"\d+", u))
+        if "ELi2ELi1EEEv" in name:       # IL=2 (opt-in, measured slower): known to spill its 128-column row
+            continue
+        assert stack <= 48, (name, u)
+        assert reg <= 240, (name, u)
+
+
 def test_engine_refuses_to_run_without_cuda():
     """The product path must fail loudly, never fall back to the CPU oracle."""
     import torch

@@ -18,6 +18,4 @@ for name, Lq, Lk, DV in (("cross", 4096, 28736, 64), ("self", 4096, 4096, 256)):
     b = list(buf); n = max(b[7], 1); tiles = (Lk + (128 if DV == 64 else 64) - 1) // (128 if DV == 64 else 64)
     print(f"{name}: {e0.elapsed_time(e1)*1e3:.0f} us, {n} CTAs, {tiles} key tiles; per CTA per tile (clk): MMA warp total {b[3]/n/tiles:.0f} = "
           f"wait K {b[0]/n/tiles:.0f} + wait V {b[1]/n/tiles:.0f} + wait P {b[2]/n/tiles:.0f} + issue {(b[3]-b[0]-b[1]-b[2])/n/tiles:.0f}; "
-          f"softmax warp total {b[6]/n/tiles:.0f} = wait S {b[4]/n/tiles:.0f} + wait O {b[5]/n/tiles:.0f} + work {(b[6]-b[4]-b[5])/n/tiles:.0f}"
-          f" [S load {b[8]/n/tiles:.0f}, row max {b[9]/n/tiles:.0f}, exp+sum+pack {b[10]/n/tiles:.0f}, P store {b[11]/n/tiles:.0f}, "
-          f"st wait+fence+arrive {b[12]/n/tiles:.0f}]")
+          f"softmax warp total {b[6]/n/tiles:.0f} = wait S {b[4]/n/tiles:.0f} + wait O {b[5]/n/tiles:.0f} + work {(b[6]-b[4]-b[5])/n/tiles:.0f}")
