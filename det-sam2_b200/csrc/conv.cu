@@ -126,6 +126,89 @@ __global__ void __launch_bounds__(256) dwconv7_kernel(const float* __restrict__ 
   }
 }
 
+// Shared-memory version (the default).  The register-tiled kernel above is 4096 straight-line instructions (64 KB of
+// code, 220 registers, one CTA per SM): it ran at 1/6 of the FMA rate, stalled on instruction fetch and on the 22 global
+// loads per input row.  Here a CTA stages the (16+6)^2 x 32-channel input patch and the 49 x 32 weights in shared memory
+// with cp.async (zero-filled outside the map), a warp owns two output rows, a lane one channel: the loop over the 8 input
+// rows that feed the two output rows is rolled (~300 instructions), every shared-memory access is 32 consecutive words,
+// and three CTAs fit an SM.  Per output: acc = bias, then taps in (ky, kx) order with fmaf — the same sequence as the
+// register-tiled kernel, so the two are bit-identical.
+constexpr int kDwT = 16, kDwP = kDwT + 6, kDwC = 32;
+constexpr int kDwSmem = (kDwP * kDwP * kDwC + 49 * kDwC) * 4;
+
+__global__ void __launch_bounds__(256, 3) dwconv7_smem_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, float* __restrict__ y,
+                                                              int B, int Hm, int Wm, int C) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
+  extern __shared__ __align__(16) float dsm[];
+  float* patch = dsm;                            // [kDwP][kDwP][32]
+  float* wsm = dsm + kDwP * kDwP * kDwC;         // [49][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.y * kDwC;
+  const int tiles_x = (Wm + kDwT - 1) / kDwT, tiles_y = (Hm + kDwT - 1) / kDwT;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x;
+  t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int x0 = tx * kDwT, y0 = ty * kDwT;
+  for (int i = threadIdx.x; i < 49 * kDwC; i += 256) wsm[i] = __ldg(w + (c0 + (i & 31)) * 49 + (i >> 5));
+  for (int i = threadIdx.x; i < kDwP * kDwP * (kDwC / 4); i += 256) {
+    const int q = i & 7, pix = i >> 3;
+    const int py = pix / kDwP, px = pix - py * kDwP;
+    const int iy = y0 - 3 + py, ix = x0 - 3 + px;
+    float* dst = patch + pix * kDwC + q * 4;
+    if (iy >= 0 && iy < Hm && ix >= 0 && ix < Wm) {
+      const float* src = x + ((static_cast<long long>(b) * Hm + iy) * Wm + ix) * C + c0 + q * 4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))),
+                   "l"(src));
+    } else {
+      *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int r0 = warp * 2;
+  const float bv = bias ? __ldg(bias + c0 + lane) : 0.f;
+  float acc0[kDwT], acc1[kDwT];
+#pragma unroll
+  for (int o = 0; o < kDwT; ++o) acc0[o] = acc1[o] = bv;
+#pragma unroll 1
+  for (int ri = 0; ri < 8; ++ri) {
+    const float* prow = patch + (r0 + ri) * kDwP * kDwC + lane;
+    float row[kDwP];
+#pragma unroll
+    for (int j = 0; j < kDwP; ++j) row[j] = prow[j * kDwC];
+    if (ri < 7) {   // tap row ri of output row r0
+      float wk[7];
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) wk[kx] = wsm[(ri * 7 + kx) * kDwC + lane];
+#pragma unroll
+      for (int o = 0; o < kDwT; ++o)
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) acc0[o] = fmaf(row[o + kx], wk[kx], acc0[o]);
+    }
+    if (ri >= 1) {  // tap row ri - 1 of output row r0 + 1
+      float wk[7];
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) wk[kx] = wsm[((ri - 1) * 7 + kx) * kDwC + lane];
+#pragma unroll
+      for (int o = 0; o < kDwT; ++o)
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) acc1[o] = fmaf(row[o + kx], wk[kx], acc1[o]);
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int oy = y0 + r0 + rr;
+    if (oy >= Hm) continue;
+    float* yp = y + ((static_cast<long long>(b) * Hm + oy) * Wm + x0) * C + c0 + lane;
+#pragma unroll
+    for (int o = 0; o < kDwT; ++o)
+      if (x0 + o < Wm) yp[static_cast<long long>(o) * C] = rr ? acc1[o] : acc0[o];
+  }
+}
+
 // ---- mask down-sampler stage 1 (fused) -----------------------------------------------------------
 // PyTorch bilinear (align_corners=False) source index / weights for scale 1/4.
 __device__ __forceinline__ float hires_mask_value(const float* __restrict__ lr, int Sl, int Y, int X) {
@@ -313,15 +396,24 @@ int ds2_dwconv7(const float* x, const float* w, const float* bias, float* y, int
                 int32_t C, void* stream) {
   using namespace ds2;
   DS2_REQUIRE(x && w && y && B > 0 && Hm > 0 && Wm > 0 && C > 0, DS2_E_ARG, "ds2_dwconv7: bad args");
-  // tile per thread (columns x rows): DS2_DWCONV_TILE = 16x4 (default) | 16x2 | 8x4 | 8x8 — tuning switch
+  // default: the shared-memory kernel; DS2_DWCONV_TILE = 16x4 | 16x2 | 8x4 | 8x8 selects a register-tiled variant (columns x
+  // rows per thread) for measurements
   static const int cfg = [] {
     const char* e = getenv("DS2_DWCONV_TILE");
     if (!e) return 0;
     if (!strcmp(e, "16x2")) return 1;
     if (!strcmp(e, "8x4")) return 2;
     if (!strcmp(e, "8x8")) return 3;
+    if (!strcmp(e, "16x4")) return 4;   // the register-tiled default of round 1
     return 0;
   }();
+  if (cfg == 0 && (C % kDwC) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    static const cudaError_t attr = cudaFuncSetAttribute(dwconv7_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmem);
+    DS2_REQUIRE(attr == cudaSuccess, static_cast<int>(attr), "ds2_dwconv7: cudaFuncSetAttribute: %s", cudaGetErrorString(attr));
+    dim3 grid(static_cast<unsigned>(B) * ((Hm + kDwT - 1) / kDwT) * ((Wm + kDwT - 1) / kDwT), C / kDwC);
+    DS2_LAUNCH((dwconv7_smem_kernel), grid, 256, kDwSmem, as_stream(stream), x, w, bias, y, B, Hm, Wm, C);
+    return post_launch("dwconv7_smem_kernel");
+  }
   const int dwx = (cfg >= 2) ? 8 : 16;
   const int dwy = cfg == 1 ? 2 : (cfg == 3 ? 8 : 4);
   const int threads = C >= 256 ? 256 : ((C + 31) / 32) * 32;

@@ -3,6 +3,8 @@
 // never written to HBM), small batched 3-layer MLP heads, and the mask / token selection epilogue.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.h"
 
 namespace ds2 {
@@ -103,6 +105,7 @@ struct Mlp3Params {
   int sigmoid_out;
   float* y;
   long long ldy;
+  int prefetch;
 };
 // One dense layer of the batched MLP inside a CTA: y[o] = act(sum_k W[k][o] x[k] + b[o]).  W is INPUT-major
 // ([in][out], the transpose of nn.Linear's layout), so the threads of a warp (consecutive outputs o) read
@@ -149,7 +152,27 @@ __device__ __forceinline__ void mlp_layer(const float* __restrict__ W, const flo
   __syncthreads();
 }
 
+// L2 prefetch of a weight matrix, sliced over the `parts` CTAs that share it.
+__device__ __forceinline__ void prefetch_l2_slice(const float* w, long long bytes, int part, int parts) {
+  const char* base = reinterpret_cast<const char*>(w);
+  for (long long off = (static_cast<long long>(threadIdx.x) * parts + part) * 128; off < bytes;
+       off += static_cast<long long>(blockDim.x) * parts * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+}
+
 __global__ void __launch_bounds__(256) mlp3_kernel(const Mlp3Params p) {
+  {
+    // The weights are constants, so they may be touched BEFORE the programmatic-dependent-launch wait: the frame's 1 GB
+    // working set has evicted them from L2 since the last frame, and the three layers are a dependent chain that used to
+    // pay a DRAM round trip per 32-load batch (8 batches per layer, 37 us per launch).  Pull all three matrices into L2
+    // while the preceding kernel drains.
+    const int set = blockIdx.x % p.nmlp, part = blockIdx.x / p.nmlp, parts = (p.rows + p.nmlp - 1) / p.nmlp;
+    if (p.prefetch) {
+      prefetch_l2_slice(p.w1 + static_cast<long long>(set) * p.dh * p.din, 4LL * p.dh * p.din, part, parts);
+      prefetch_l2_slice(p.w2 + static_cast<long long>(set) * p.dh * p.dh, 4LL * p.dh * p.dh, part, parts);
+      prefetch_l2_slice(p.w3 + static_cast<long long>(set) * p.dout * p.dh, 4LL * p.dout * p.dh, part, parts);
+    }
+  }
   pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
   extern __shared__ float sm[];
   float* xin = sm;             // din
@@ -302,6 +325,11 @@ int ds2_mlp3(const ds2_mlp3_args* a, void* stream) {
   p.sigmoid_out = a->sigmoid_out;
   p.y = a->y;
   p.ldy = a->ldy;
+  static const int prefetch = [] {
+    const char* e = getenv("DS2_MLP_PREFETCH");   // A/B switch (tuning only)
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  p.prefetch = prefetch;
   DS2_REQUIRE(a->dh <= 256 && a->dout <= 256, DS2_E_ARG, "ds2_mlp3: hidden / output width must be <= 256 (got %d, %d)",
               a->dh, a->dout);
   const int smem = (a->din + 2 * a->dh + 256 + a->dout) * 4;

@@ -10,7 +10,11 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include "common.h"
+
+namespace cg = cooperative_groups;
 
 namespace ds2 {
 
@@ -308,6 +312,262 @@ __global__ void __launch_bounds__(32 * NW, (DP <= 96 ? (NW == 8 ? 2 : 4) : 1)) m
   }
 }
 
+// ---- the mask decoder's two attention shapes (transformer.py:178-211: 8 heads x 16 dims) ---------------------------
+// (1) token -> image: 8-9 queries against 4096 keys per (object, head).  On the generic kernel one warp of one CTA walked
+//     the 64 key chunks in sequence (33 us, latency).  Here the chunks are dealt round-robin to the 4 warps of the 8 CTAs
+//     of a thread-block cluster; every warp runs the same mma.sync online softmax as above on its chunks, the 32 partial
+//     (max, sum, O) triples are merged by the cluster's rank-0 CTA through distributed shared memory in a fixed order
+//     (no workspace, no atomics, bit-reproducible).
+constexpr int kFqSplit = 8;            // CTAs per cluster = key slices
+constexpr int kFqRow = 18;             // floats per partial row: 16 outputs + running max + running sum
+
+__global__ void __cluster_dims__(1, 1, kFqSplit) __launch_bounds__(128) fewq_attn_kernel(const MhaParams p) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
+  constexpr int DP = 16, QS = DP + 8;
+  __shared__ __align__(16) __nv_bfloat16 Qs[16 * QS];
+  __shared__ __align__(16) __nv_bfloat16 KVs[4][2][64 * QS];   // per warp: K chunk, V chunk
+  __shared__ float red[4][16][kFqRow];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int Lq = p.Lq, Lk = p.Lk;
+  const int Lk_valid = p.Lk_valid > 0 ? p.Lk_valid : Lk;
+  for (int i = tid; i < 16 * 2; i += 128) {
+    const int r = i >> 1, c = i & 1;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (r < Lq) val = *reinterpret_cast<const uint4*>(p.q + b * p.q_bs + static_cast<long long>(r) * p.q_tok + h * DP + c * 8);
+    *reinterpret_cast<uint4*>(Qs + r * QS + c * 8) = val;
+  }
+  __syncthreads();
+  uint32_t qa[4];
+  {
+    const __nv_bfloat16* qrow0 = Qs + g * QS;
+    const __nv_bfloat16* qrow1 = qrow0 + 8 * QS;
+    qa[0] = *reinterpret_cast<const uint32_t*>(qrow0 + 2 * t);
+    qa[1] = *reinterpret_cast<const uint32_t*>(qrow1 + 2 * t);
+    qa[2] = *reinterpret_cast<const uint32_t*>(qrow0 + 8 + 2 * t);
+    qa[3] = *reinterpret_cast<const uint32_t*>(qrow1 + 8 + 2 * t);
+  }
+  float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  __nv_bfloat16* Ks = KVs[warp][0];
+  __nv_bfloat16* Vs = KVs[warp][1];
+  const int n_chunks = (Lk + 63) / 64;
+  for (int j = blockIdx.z * 4 + warp; j < n_chunks; j += 4 * kFqSplit) {
+    const int k0 = j * 64;
+    __syncwarp();   // the previous chunk's ldmatrix reads are done before the buffers are overwritten
+    for (int i = lane; i < 64 * 2; i += 32) {
+      const int r = i >> 1, c = i & 1;
+      const int kr = k0 + r;
+      const bool ok = kr < Lk;
+      const long long tok = ok ? kr : 0;
+      cp_async16(Ks + r * QS + c * 8, p.k + b * p.k_bs + tok * p.k_tok + h * DP + c * 8, ok ? 16 : 0);
+      cp_async16(Vs + r * QS + c * 8, p.v + b * p.v_bs + tok * p.v_tok + h * DP + c * 8, ok ? 16 : 0);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      const __nv_bfloat16* krow = Ks + (nt * 8 + g) * QS;
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + 2 * t);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + 8 + 2 * t);
+      mma_bf16_16816(s[nt], qa, b0, b1);
+    }
+    const int lim = Lk_valid - k0;
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int c0 = nt * 8 + 2 * t;
+      if (c0 >= lim) s[nt][0] = s[nt][2] = -INFINITY;
+      if (c0 + 1 >= lim) s[nt][1] = s[nt][3] = -INFINITY;
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float a0 = (m0 == -INFINITY) ? 0.f : ex2f_fast((m0 - mn0) * p.scale_log2);
+    const float a1 = (m1 == -INFINITY) ? 0.f : ex2f_fast((m1 - mn1) * p.scale_log2);
+    m0 = mn0;
+    m1 = mn1;
+    const float off0 = (mn0 == -INFINITY) ? 0.f : mn0 * p.scale_log2;
+    const float off1 = (mn1 == -INFINITY) ? 0.f : mn1 * p.scale_log2;
+    float sum0 = 0.f, sum1 = 0.f;
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float e0 = ex2f_fast(fmaf(s[nt][0], p.scale_log2, -off0));
+      const float e1 = ex2f_fast(fmaf(s[nt][1], p.scale_log2, -off0));
+      const float e2 = ex2f_fast(fmaf(s[nt][2], p.scale_log2, -off1));
+      const float e3 = ex2f_fast(fmaf(s[nt][3], p.scale_log2, -off1));
+      sum0 += e0 + e1;
+      sum1 += e2 + e3;
+      __nv_bfloat162 p01 = __floats2bfloat162_rn(e0, e1);
+      __nv_bfloat162 p23 = __floats2bfloat162_rn(e2, e3);
+      pa[nt >> 1][(nt & 1) * 2 + 0] = *reinterpret_cast<uint32_t*>(&p01);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&p23);
+    }
+    l0 = l0 * a0 + sum0;
+    l1 = l1 * a1 + sum1;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      o[i][0] *= a0;
+      o[i][1] *= a0;
+      o[i][2] *= a1;
+      o[i][3] *= a1;
+    }
+    const uint32_t vbase = static_cast<uint32_t>(__cvta_generic_to_shared(
+        Vs + ((lane & 7) + ((lane >> 3) & 1) * 8) * QS + (lane >> 4) * 8));
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t b0, b1, b2, b3;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                   : "r"(vbase + static_cast<uint32_t>((kk * 16 * QS) * 2)));
+      mma_bf16_16816(o[0], pa[kk], b0, b1);
+      mma_bf16_16816(o[1], pa[kk], b2, b3);
+    }
+  }
+  // ---- this warp's partial -> shared memory ----
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    red[warp][g][i * 8 + 2 * t] = o[i][0];
+    red[warp][g][i * 8 + 2 * t + 1] = o[i][1];
+    red[warp][g + 8][i * 8 + 2 * t] = o[i][2];
+    red[warp][g + 8][i * 8 + 2 * t + 1] = o[i][3];
+  }
+  if (t == 0) {
+    red[warp][g][16] = m0;
+    red[warp][g][17] = l0;
+    red[warp][g + 8][16] = m1;
+    red[warp][g + 8][17] = l1;
+  }
+  cg::cluster_group cluster = cg::this_cluster();
+  cluster.sync();
+  if (cluster.block_rank() == 0) {
+    // 256 outputs, 2 per thread; partials are merged in (rank, warp) order
+    for (int e = tid; e < 16 * 16; e += 128) {
+      const int r = e >> 4, c = e & 15;
+      if (r >= Lq) continue;
+      float M = -INFINITY;
+      for (int rk = 0; rk < kFqSplit; ++rk) {
+        const float* rr = cluster.map_shared_rank(&red[0][0][0], rk);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) M = fmaxf(M, rr[(w * 16 + r) * kFqRow + 16]);
+      }
+      float L = 0.f, O = 0.f;
+      for (int rk = 0; rk < kFqSplit; ++rk) {
+        const float* rr = cluster.map_shared_rank(&red[0][0][0], rk);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const float* row = rr + (w * 16 + r) * kFqRow;
+          const float mw = row[16];
+          const float sc = (mw == -INFINITY) ? 0.f : ex2f_fast((mw - M) * p.scale_log2);
+          L = fmaf(row[17], sc, L);
+          O = fmaf(row[c], sc, O);
+        }
+      }
+      p.out[b * p.o_bs + static_cast<long long>(r) * p.o_tok + h * DP + c] = __float2bfloat16_rn(O / L);
+    }
+  }
+  cluster.sync();   // the other CTAs' shared memory stays alive until rank 0 has read it
+}
+
+// (2) image -> token: 4096 queries against the 8-9 token keys per (object, head).  One thread = one (query, head):
+//     K / V of the object live in shared memory as f32 (head rows padded 16 -> 20 words: conflict-free float4 reads), the
+//     scores, the softmax and P.V stay in f32 registers; a warp reads / writes 4 whole query rows (256 B each).
+constexpr int kFkMaxKeys = 16;
+__global__ void __launch_bounds__(256) fewk_attn_kernel(const MhaParams p) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
+  constexpr int DP = 16, HS = 20;
+  __shared__ __align__(16) float Ks[kFkMaxKeys][8 * HS];
+  __shared__ __align__(16) float Vs[kFkMaxKeys][8 * HS];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int Lk = p.Lk;
+  const int Lk_valid = p.Lk_valid > 0 ? min(p.Lk_valid, Lk) : Lk;
+  for (int i = tid; i < Lk * 128; i += 256) {
+    const int j = i >> 7, c = i & 127;
+    Ks[j][(c >> 4) * HS + (c & 15)] = __bfloat162float(p.k[b * p.k_bs + static_cast<long long>(j) * p.k_tok + c]);
+    Vs[j][(c >> 4) * HS + (c & 15)] = __bfloat162float(p.v[b * p.v_bs + static_cast<long long>(j) * p.v_tok + c]);
+  }
+  __syncthreads();
+  const int h = tid & 7;
+  const int qi = blockIdx.x * 32 + (tid >> 3);
+  if (qi >= p.Lq) return;
+  float q[DP];
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.q + b * p.q_bs + static_cast<long long>(qi) * p.q_tok + h * DP);
+    const uint4 u0 = __ldg(src), u1 = __ldg(src + 1);
+    const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      q[2 * i] = __uint_as_float(w[i] << 16);
+      q[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  float s[kFkMaxKeys];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kFkMaxKeys; ++j) {
+    s[j] = -INFINITY;
+    if (j < Lk_valid) {
+      const float4* kr = reinterpret_cast<const float4*>(&Ks[j][h * HS]);
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 kv = kr[i];
+        a = fmaf(q[4 * i], kv.x, a);
+        a = fmaf(q[4 * i + 1], kv.y, a);
+        a = fmaf(q[4 * i + 2], kv.z, a);
+        a = fmaf(q[4 * i + 3], kv.w, a);
+      }
+      s[j] = a;
+      mx = fmaxf(mx, a);
+    }
+  }
+  float acc[DP];
+#pragma unroll
+  for (int i = 0; i < DP; ++i) acc[i] = 0.f;
+  float l = 0.f;
+  const float off = mx * p.scale_log2;
+#pragma unroll
+  for (int j = 0; j < kFkMaxKeys; ++j) {
+    if (j < Lk_valid) {
+      const float e = ex2f_fast(fmaf(s[j], p.scale_log2, -off));
+      l += e;
+      const float4* vr = reinterpret_cast<const float4*>(&Vs[j][h * HS]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 vv = vr[i];
+        acc[4 * i] = fmaf(e, vv.x, acc[4 * i]);
+        acc[4 * i + 1] = fmaf(e, vv.y, acc[4 * i + 1]);
+        acc[4 * i + 2] = fmaf(e, vv.z, acc[4 * i + 2]);
+        acc[4 * i + 3] = fmaf(e, vv.w, acc[4 * i + 3]);
+      }
+    }
+  }
+  const float inv = 1.f / l;
+  uint32_t ow[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat162 v2 = __floats2bfloat162_rn(acc[2 * i] * inv, acc[2 * i + 1] * inv);
+    ow[i] = *reinterpret_cast<uint32_t*>(&v2);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(p.out + b * p.o_bs + static_cast<long long>(qi) * p.o_tok + h * DP);
+  dst[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  dst[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+}
+
 template <int DP, int NW>
 static int launch_mha_nw(const MhaParams& p, dim3 grid, cudaStream_t st) {
   const int smem = (16 * NW + 2 * 128) * (DP + 8) * 2;
@@ -406,6 +666,20 @@ extern "C" int ds2_mha(const ds2_mha_args* a, void* stream) {
     }
   }
   const int D = a->D;
+  if (a->window == 0 && D == 16 && a->H == 8 && (a->o_tok_stride % 8) == 0) {   // the mask decoder's two shapes
+    static const bool dec_fast = [] {
+      const char* e = getenv("DS2_DEC_ATTN");   // DS2_DEC_ATTN=0: generic mma.sync kernel (A/B)
+      return !(e && e[0] == '0');
+    }();
+    if (dec_fast && Lq <= 16 && a->Lk >= 256 && a->B <= 65535) {
+      DS2_LAUNCH((fewq_attn_kernel), dim3(a->B, a->H, kFqSplit), 128, 0, st, p);
+      return post_launch("fewq_attn_kernel");
+    }
+    if (dec_fast && a->Lk <= kFkMaxKeys && Lq >= 256 && a->B <= 65535) {
+      DS2_LAUNCH((fewk_attn_kernel), dim3((Lq + 31) / 32, a->B), 256, 0, st, p);
+      return post_launch("fewk_attn_kernel");
+    }
+  }
   if (D <= 16) return launch_mha<16>(p, nseq, a->H, Lq, st);
   if (D <= 32) return launch_mha<32>(p, nseq, a->H, Lq, st);
   if (D <= 64) return launch_mha<64>(p, nseq, a->H, Lq, st);

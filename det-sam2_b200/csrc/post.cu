@@ -145,23 +145,43 @@ __global__ void fill_holes_kernel(float* __restrict__ scores, const int* __restr
 }
 
 // PyTorch upsample_bilinear2d, align_corners=False, antialias=False
-__global__ void resize_bilinear_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int Hi, int Wi,
-                                       int Ho, int Wo, float sh, float sw) {
+// blockIdx.y = output row, blockIdx.z = image; one thread = 4 consecutive output pixels of that row (one 16-byte store
+// when the row pitch allows).  The first version spent its time in three 64-bit divisions per pixel and scalar
+// stores: 100 us for 16 x 1024^2, against 67 MB / HBM rate ~ 12 us.
+template <bool kVec>
+__global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __restrict__ x, float* __restrict__ y, int Hi, int Wi,
+                                                              int Ho, int Wo, float sh, float sw) {
   pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(N) * Ho * Wo;
-  if (i >= total) return;
-  const int ox = static_cast<int>(i % Wo);
-  const int oy = static_cast<int>((i / Wo) % Ho);
-  const int n = static_cast<int>(i / (static_cast<long long>(Wo) * Ho));
+  const int ox0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (ox0 >= Wo) return;
+  const int oy = blockIdx.y;
+  const long long n = blockIdx.z;
   const float sy = fmaxf(sh * (oy + 0.5f) - 0.5f, 0.f);
-  const float sx = fmaxf(sw * (ox + 0.5f) - 0.5f, 0.f);
-  const int y0 = min(static_cast<int>(sy), Hi - 1), x0 = min(static_cast<int>(sx), Wi - 1);
-  const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
-  const float ly = fminf(fmaxf(sy - y0, 0.f), 1.f), lx = fminf(fmaxf(sx - x0, 0.f), 1.f);
-  const float hy = 1.f - ly, hx = 1.f - lx;
-  const float* src = x + static_cast<long long>(n) * Hi * Wi;
-  y[i] = hy * (hx * src[y0 * Wi + x0] + lx * src[y0 * Wi + x1]) + ly * (hx * src[y1 * Wi + x0] + lx * src[y1 * Wi + x1]);
+  const int y0 = min(static_cast<int>(sy), Hi - 1);
+  const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0);
+  const float ly = fminf(fmaxf(sy - y0, 0.f), 1.f);
+  const float hy = 1.f - ly;
+  const float* r0 = x + (n * Hi + y0) * Wi;
+  const float* r1 = x + (n * Hi + y1) * Wi;
+  float v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int ox = min(ox0 + e, Wo - 1);
+    const float sx = fmaxf(sw * (ox + 0.5f) - 0.5f, 0.f);
+    const int x0 = min(static_cast<int>(sx), Wi - 1);
+    const int x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
+    const float lx = fminf(fmaxf(sx - x0, 0.f), 1.f);
+    const float hx = 1.f - lx;
+    v[e] = hy * (hx * __ldg(r0 + x0) + lx * __ldg(r0 + x1)) + ly * (hx * __ldg(r1 + x0) + lx * __ldg(r1 + x1));
+  }
+  float* dst = y + (n * Ho + oy) * Wo + ox0;
+  if (kVec) {
+    __stcs(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));   // streaming: nobody on the device re-reads it
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (ox0 + e < Wo) dst[e] = v[e];
+  }
 }
 
 __global__ void threshold_pack_kernel(const float* __restrict__ x, uint8_t* __restrict__ bits, long long n) {
@@ -290,8 +310,15 @@ int ds2_resize_bilinear(const float* x, float* y, int32_t N, int32_t Hi, int32_t
   using namespace ds2;
   DS2_REQUIRE(x && y && N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, DS2_E_ARG, "ds2_resize_bilinear: bad args");
   const long long total = static_cast<long long>(N) * Ho * Wo;
-  DS2_LAUNCH((resize_bilinear_kernel), nblocks(total, 256), 256, 0, as_stream(stream), 
-      x, y, N, Hi, Wi, Ho, Wo, static_cast<float>(Hi) / Ho, static_cast<float>(Wi) / Wo);
+  DS2_REQUIRE(Ho <= 65535 && N <= 65535, DS2_E_ARG, "ds2_resize_bilinear: Ho %d / N %d above the grid limit", Ho, N);
+  const int tx = Wo >= 1024 ? 256 : (Wo >= 256 ? 64 : 32);
+  const dim3 grid((Wo + 4 * tx - 1) / (4 * tx), Ho, N);
+  const float sh = static_cast<float>(Hi) / Ho, sw = static_cast<float>(Wi) / Wo;
+  if ((Wo & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    DS2_LAUNCH((resize_bilinear_kernel<true>), grid, tx, 0, as_stream(stream), x, y, Hi, Wi, Ho, Wo, sh, sw);
+  } else {
+    DS2_LAUNCH((resize_bilinear_kernel<false>), grid, tx, 0, as_stream(stream), x, y, Hi, Wi, Ho, Wo, sh, sw);
+  }
   return post_launch("resize_bilinear_kernel");
 }
 

@@ -292,6 +292,9 @@ def _mha_ref(q, k, v, scale, Lk_valid=None):
 
 
 @pytest.mark.parametrize("B,H,D,Lq,Lk,Lkv", [(2, 8, 16, 9, 4096, 0), (2, 8, 16, 4096, 16, 9), (3, 8, 32, 8, 16, 8),
+                                              # the mask decoder's shapes on the cluster-split / thread-per-query kernels
+                                              (16, 8, 16, 8, 4096, 0), (3, 8, 16, 16, 300, 290), (1, 8, 16, 1, 257, 0),
+                                              (3, 8, 16, 4096, 9, 0), (2, 8, 16, 1000, 1, 0), (2, 8, 16, 300, 16, 0),
                                               (1, 8, 72, 1024, 1024, 0), (1, 2, 96, 100, 130, 0),
                                               # head_dim in (64, 80], Lq / Lk multiples of 128: tcgen05 flash loop
                                               (2, 4, 72, 256, 384, 0), (1, 2, 80, 128, 128, 0), (1, 8, 72, 4096, 4096, 0)])
@@ -461,7 +464,7 @@ def test_im2col_k3s2_matches_conv(ops):
     assert (out - ref).abs().max().item() < 1e-3
 
 
-@pytest.mark.parametrize("B,Hm,C", [(2, 16, 64), (1, 18, 256), (3, 7, 32)])
+@pytest.mark.parametrize("B,Hm,C", [(2, 16, 64), (1, 18, 256), (3, 7, 32), (2, 64, 256), (1, 9, 48), (1, 33, 96)])
 def test_dwconv7(ops, B, Hm, C):
     torch.manual_seed(14)
     x = torch.randn(B, Hm, Hm, C, device=DEV)
