@@ -5,7 +5,11 @@
 
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include "common.h"
+
+namespace cg = cooperative_groups;
 
 namespace ds2 {
 
@@ -192,6 +196,122 @@ __global__ void __launch_bounds__(256) mlp3_kernel(const Mlp3Params p) {
   for (int o = threadIdx.x; o < p.dout; o += blockDim.x) p.y[static_cast<long long>(item) * p.ldy + o] = yout[o];
 }
 
+// ---- cluster version of the batched 3-layer MLP (the default) -------------------------------------------------------
+// mlp3_kernel above gives every row its own CTA, which then streams all three weight matrices (768 KB) through one SM in
+// three dependent phases: ~30 us per launch, four launches per frame.  Here a cluster of 8 CTAs owns up to 16 rows of one
+// MLP: CTA c computes 1/8 of each layer's outputs for all 16 rows (its 32-column weight slice is 32 KB and is read once),
+// the slices are exchanged through distributed shared memory between layers, and the first thing every CTA does — before
+// the programmatic-dependent-launch wait, the weights being constants — is to prefetch its three slices into L2.
+constexpr int kMcRows = 16, kMcCtas = 8;
+
+// One layer slice: out[r][oo] = act(sum_k W[k][col0 + oo] x[r][k] + bias[col0 + oo]) for this CTA's ncols columns.
+// Threads = P column lanes (ncols padded to a power of two) x G k-slices; the k-slices are summed through `part`.
+__device__ __forceinline__ void mc_layer(const float* __restrict__ W, int ldw, const float* __restrict__ bias, int col0,
+                                         int ncols, const float* xin, int din, float* part, float* out, int act) {
+  int P = 1;
+  while (P < ncols) P <<= 1;
+  const int G = 256 / P;
+  const int o = threadIdx.x % P, g = threadIdx.x / P;
+  const int per = (din + G - 1) / G;
+  const int k0 = g * per, k1 = min(din, k0 + per);
+  float acc[kMcRows];
+#pragma unroll
+  for (int r = 0; r < kMcRows; ++r) acc[r] = 0.f;
+  if (o < ncols) {
+    for (int k = k0; k < k1; k += 16) {
+      float wv[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) wv[i] = (k + i < k1) ? __ldg(W + static_cast<long long>(k + i) * ldw + col0 + o) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (k + i < k1) {
+#pragma unroll
+          for (int r = 0; r < kMcRows; ++r) acc[r] = fmaf(wv[i], xin[r * din + k + i], acc[r]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kMcRows; ++r) part[(g * kMcRows + r) * P + o] = acc[r];
+  __syncthreads();
+  for (int e = threadIdx.x; e < kMcRows * ncols; e += 256) {
+    const int r = e / ncols, oo = e - r * ncols;
+    float a = 0.f;
+    for (int gg = 0; gg < G; ++gg) a += part[(gg * kMcRows + r) * P + oo];
+    a += bias[col0 + oo];
+    if (act == 1) a = fmaxf(a, 0.f);
+    else if (act == 2) a = 1.f / (1.f + expf(-a));
+    out[e] = a;
+  }
+  __syncthreads();
+}
+
+__global__ void __cluster_dims__(kMcCtas, 1, 1) __launch_bounds__(256) mlp3_cluster_kernel(const Mlp3Params p) {
+  extern __shared__ __align__(16) float msm[];
+  const int wmax = p.din > p.dh ? p.din : p.dh;
+  float* full0 = msm;                          // [16][max(din, dh)]  layer input (x, then h2)
+  float* full1 = full0 + kMcRows * wmax;       // [16][dh]            h1
+  float* part = full1 + kMcRows * p.dh;        // [256][16]
+  float* sl0 = part + 256 * kMcRows;           // [16][dh / 8]  this CTA's slice of h1
+  float* sl1 = sl0 + kMcRows * (p.dh / kMcCtas);   // [16][dh / 8]  ... of h2
+  float* sl2 = sl1 + kMcRows * (p.dh / kMcCtas);   // [16][ceil(dout / 8)]
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int set = blockIdx.y;
+  const int rows_per_set = p.rows / p.nmlp;
+  const int row0 = blockIdx.z * kMcRows;
+  const int nh = p.dh / kMcCtas;                       // hidden columns per CTA
+  const int n3 = (p.dout + kMcCtas - 1) / kMcCtas;     // output columns per CTA
+  const int c3 = rank * n3;
+  const int nc3 = max(0, min(n3, p.dout - c3));
+  const float* w1 = p.w1 + static_cast<long long>(set) * p.dh * p.din;
+  const float* w2 = p.w2 + static_cast<long long>(set) * p.dh * p.dh;
+  const float* w3 = p.w3 + static_cast<long long>(set) * p.dout * p.dh;
+  if (p.prefetch) {
+    // weight slices are constants: pull them into L2 while the preceding kernel drains (one 128-byte line per row and slice)
+    for (int k = threadIdx.x; k < p.din; k += 256)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(w1 + static_cast<long long>(k) * p.dh + rank * nh));
+    for (int k = threadIdx.x; k < p.dh; k += 256) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(w2 + static_cast<long long>(k) * p.dh + rank * nh));
+      if (nc3 > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(w3 + static_cast<long long>(k) * p.dout + c3));
+    }
+  }
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
+  for (int e = threadIdx.x; e < kMcRows * p.din; e += 256) {
+    const int r = e / p.din, c = e - r * p.din;
+    float v = 0.f;
+    if (row0 + r < rows_per_set) {
+      const int item = (row0 + r) * p.nmlp + set;
+      const long long src = p.gather ? p.gather[item] : item;
+      v = p.x[src * p.ldx + c];
+    }
+    full0[e] = v;
+  }
+  __syncthreads();
+  auto gather_slices = [&](float* local_slice, float* dst) {
+    cluster.sync();   // every CTA's slice is written
+    for (int e = threadIdx.x; e < kMcRows * p.dh; e += 256) {
+      const int r = e / p.dh, c = e - r * p.dh;
+      const float* remote = cluster.map_shared_rank(local_slice, c / nh);
+      dst[e] = remote[r * nh + (c % nh)];
+    }
+    __syncthreads();
+  };
+  mc_layer(w1, p.dh, p.b1 + set * p.dh, rank * nh, nh, full0, p.din, part, sl0, 1);
+  gather_slices(sl0, full1);
+  mc_layer(w2, p.dh, p.b2 + set * p.dh, rank * nh, nh, full1, p.dh, part, sl1, 1);
+  gather_slices(sl1, full0);
+  mc_layer(w3, p.dout, p.b3 + set * p.dout, c3, nc3, full0, p.dh, part, sl2, p.sigmoid_out ? 2 : 0);
+  for (int e = threadIdx.x; e < kMcRows * nc3; e += 256) {
+    const int r = e / nc3, oo = e - r * nc3;
+    if (row0 + r < rows_per_set) {
+      const int item = (row0 + r) * p.nmlp + set;
+      p.y[static_cast<long long>(item) * p.ldy + c3 + oo] = sl2[e];
+    }
+  }
+  cluster.sync();   // nobody exits while a peer may still read its h2 slice
+}
+
 // mask / token selection: blockIdx.x = object; with multimask output the choice needs no reduction over the mask, so the
 // copy of the chosen 256^2 mask is sliced over gridDim.y CTAs (one CTA per object left 132 SMs idle for 64 us); the
 // stability test of the single-mask path counts over the whole mask and keeps one CTA per object (gridDim.y == 1)
@@ -332,6 +452,24 @@ int ds2_mlp3(const ds2_mlp3_args* a, void* stream) {
   p.prefetch = prefetch;
   DS2_REQUIRE(a->dh <= 256 && a->dout <= 256, DS2_E_ARG, "ds2_mlp3: hidden / output width must be <= 256 (got %d, %d)",
               a->dh, a->dout);
+  static const bool use_cluster = [] {
+    const char* e = getenv("DS2_MLP_CLUSTER");   // DS2_MLP_CLUSTER=0: one CTA per row (A/B)
+    return !(e && e[0] == '0');
+  }();
+  if (use_cluster && (a->dh % kMcCtas) == 0 && (a->rows % a->nmlp) == 0 && a->nmlp <= 65535) {
+    const int wmax = a->din > a->dh ? a->din : a->dh;
+    const int n3 = (a->dout + kMcCtas - 1) / kMcCtas;
+    const int csmem = (kMcRows * wmax + kMcRows * a->dh + 256 * kMcRows + 2 * kMcRows * (a->dh / kMcCtas) + kMcRows * n3) * 4;
+    static int attr_smem = 0;
+    if (csmem > attr_smem) {
+      cudaError_t e = cudaFuncSetAttribute(mlp3_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, csmem);
+      DS2_REQUIRE(e == cudaSuccess, static_cast<int>(e), "ds2_mlp3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      attr_smem = csmem;
+    }
+    const int row_blocks = (a->rows / a->nmlp + kMcRows - 1) / kMcRows;
+    DS2_LAUNCH((mlp3_cluster_kernel), dim3(kMcCtas, a->nmlp, row_blocks), 256, csmem, as_stream(stream), p);
+    return post_launch("mlp3_cluster_kernel");
+  }
   const int smem = (a->din + 2 * a->dh + 256 + a->dout) * 4;
   DS2_LAUNCH((mlp3_kernel), a->rows, 256, smem, as_stream(stream), p);
   return post_launch("mlp3_kernel");

@@ -49,7 +49,7 @@ struct FlashParams {
   int n_full, two_phase, q_tiles;
   float* ws;               // [items][2][128 rows][DV + 4] f32
   unsigned int* ws_count;  // [items], zero between launches
-  int dbg;                 // timing experiments only (impl 5/6/8): 1 = load half of each K tile, 2 = skip the exps, 3 = stall
+  int dbg;                 // timing experiments only (impl 5/6/8/13): 1 = load half of each K tile, 2 = skip the exps, 4 = softmax relays only, 3 = stall
                            // accounting.  (Two more — no TMEM loads of S, softmax warps relaying barriers only — were run
                            // once, profiles/r2_s7_flash_softmax_stage_accounting.txt, and removed: they cost registers.)
   const __nv_bfloat16* q;  // QT kernels read the query rows straight from global memory
@@ -357,6 +357,15 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       timed_wait(bar(o_sfull, 2 * h + (j & 1)), (j >> 1) & 1, prof, w_s);
       tc::tc_fence_after();
       const uint32_t ts = tmem_s(h, j & 1) + lane_off;
+      if (p.dbg == 4) {
+        // timing experiment (impl 13): the softmax warps only relay the barriers, so the launch time is that of the
+        // TMA + MMA pipeline alone (the output is garbage)
+        if (j >= IL) tc::mbar_wait(bar(o_odone, h * IL + g), ((j / IL) - 1) & 1);
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(bar(o_pfull, 2 * h + (j & 1)));
+        continue;
+      }
       float alpha = 1.f;
       bool resc = false;
       bool half1_flag = false;
@@ -675,7 +684,7 @@ static int launch_flash(const ds2_flash_args* a, cudaStream_t st) {
   p.Lq = a->Lq;
   p.Lk = a->Lk;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  p.dbg = a->impl == 5 ? 1 : (a->impl == 6 ? 2 : (a->impl == 8 ? 3 : 0));
+  p.dbg = a->impl == 5 ? 1 : (a->impl == 6 ? 2 : (a->impl == 8 ? 3 : (a->impl == 13 ? 4 : 0)));
   p.q = reinterpret_cast<const __nv_bfloat16*>(a->q);
   p.ldq = a->ldq;
   p.bsq = a->bsq;

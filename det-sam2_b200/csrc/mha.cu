@@ -312,6 +312,213 @@ __global__ void __launch_bounds__(32 * NW, (DP <= 96 ? (NW == 8 ? 2 : 4) : 1)) m
   }
 }
 
+// ---- Hiera windows of 4x4 and 8x8 tokens (stages 1-2, hieradet.py:57-82, backbones/utils.py:16-63) -----------------
+// 16 or 64 tokens per window: far too small for a 128-row tcgen05 tile, and on the generic kernel above a 4x4 window kept
+// one warp of four busy on a quarter-filled key chunk (162 us per stage-2 block of a 4-frame pass, 7x the time its 150 MB
+// of traffic takes).  Here a CTA owns WPC whole windows with ALL heads: a token's [q | k | v] row is contiguous in the
+// fused qkv buffer, so the window is staged with 16-byte cp.async in four (eight) contiguous row segments, one warp runs
+// one (window, head, 16-query tile) on mma.sync m16n8k16 with the whole key range in a single softmax pass, writes its
+// O tile over its own Q tile in shared memory, and the CTA stores whole output rows.  With q_pool the 2x2 max-pooled
+// queries (hieradet.py:65-68) are built in shared memory first.
+template <int W, int DP, int WPC>
+__global__ void __launch_bounds__(512) win_small_attn_kernel(const MhaParams p, int C, int tasks_per_window) {
+  pdl_sync();  // griddepcontrol.wait + launch_dependents (programmatic dependent launch)
+  constexpr int NTOK = W * W;
+  constexpr int NT = NTOK / 8;         // key n-tiles of S
+  constexpr int KP = NTOK / 16;        // k-steps of P.V
+  extern __shared__ __align__(16) uint8_t smem_ws[];
+  const int RS = 3 * C + 8;            // elements per staged token row (16-byte pad: conflict-free fragment reads)
+  const int QPS = C + 8;               // row stride of the pooled-query tile
+  __nv_bfloat16* tok = reinterpret_cast<__nv_bfloat16*>(smem_ws);              // [WPC][NTOK][RS]
+  __nv_bfloat16* qp = tok + WPC * NTOK * RS;                                     // [WPC][16 * ceil(NTOK/64)][QPS] (q_pool only)
+  constexpr int NQP = NTOK / 4;        // pooled queries per window
+  constexpr int QPR = (NQP + 15) / 16 * 16;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int per = p.nwy * p.nwx;
+  const int win0 = blockIdx.x * WPC;   // first window of this CTA (windows of one CTA are neighbours in x)
+  const int b = win0 / per;
+  const int wy = (win0 % per) / p.nwx, wx0 = (win0 % per) % p.nwx;
+  const int D = p.D;
+  const int pieces = 3 * C / 8;
+  // ---- stage the windows ----
+  for (int i = tid; i < WPC * NTOK * pieces; i += nthr) {
+    const int c = i % pieces, r = (i / pieces) % NTOK, wi = i / (pieces * NTOK);
+    const int gy = wy * W + r / W, gx = (wx0 + wi) * W + r % W;
+    const __nv_bfloat16* src = p.q + b * p.q_bs + (static_cast<long long>(gy) * p.Wm + gx) * p.q_tok + c * 8;
+    cp_async16(tok + (wi * NTOK + r) * RS + c * 8, src, 16);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  if (p.q_pool) {
+    for (int i = tid; i < WPC * QPR * (C / 8); i += nthr) {
+      const int c = i % (C / 8), r = (i / (C / 8)) % QPR, wi = i / ((C / 8) * QPR);
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (r < NQP) {
+        const int py = r / (W / 2), px = r % (W / 2);
+        const __nv_bfloat16* t00 = tok + (wi * NTOK + (2 * py) * W + 2 * px) * RS + c * 8;
+        val = bf16x8_max(bf16x8_max(*reinterpret_cast<const uint4*>(t00), *reinterpret_cast<const uint4*>(t00 + RS)),
+                         bf16x8_max(*reinterpret_cast<const uint4*>(t00 + W * RS), *reinterpret_cast<const uint4*>(t00 + (W + 1) * RS)));
+      }
+      *reinterpret_cast<uint4*>(qp + (wi * QPR + r) * QPS + c * 8) = val;
+    }
+    __syncthreads();
+  }
+  // ---- one warp = one (window, head, 16-query tile) ----
+  const int wi = warp / tasks_per_window;
+  const int task = warp % tasks_per_window;
+  const int qtiles = p.q_pool ? QPR / 16 : NTOK / 16;
+  const int h = task / qtiles, qt = task % qtiles;
+  if (wi < WPC && h < p.H) {
+    const __nv_bfloat16* wtok = tok + wi * NTOK * RS;
+    __nv_bfloat16* qbase = p.q_pool ? qp + (wi * QPR + qt * 16) * QPS + h * D : tok + (wi * NTOK + qt * 16) * RS + h * D;
+    const int qs = p.q_pool ? QPS : RS;
+    uint32_t qa[DP / 16][4];
+    {
+      const __nv_bfloat16* qrow0 = qbase + g * qs;
+      const __nv_bfloat16* qrow1 = qrow0 + 8 * qs;
+#pragma unroll
+      for (int kk = 0; kk < DP / 16; ++kk) {
+        qa[kk][0] = *reinterpret_cast<const uint32_t*>(qrow0 + kk * 16 + 2 * t);
+        qa[kk][1] = *reinterpret_cast<const uint32_t*>(qrow1 + kk * 16 + 2 * t);
+        qa[kk][2] = *reinterpret_cast<const uint32_t*>(qrow0 + kk * 16 + 8 + 2 * t);
+        qa[kk][3] = *reinterpret_cast<const uint32_t*>(qrow1 + kk * 16 + 8 + 2 * t);
+      }
+      if (D < DP) qa[DP / 16 - 1][2] = qa[DP / 16 - 1][3] = 0u;   // DP - D == 8: columns >= D belong to the next head
+    }
+    float s[NT][4];
+    const __nv_bfloat16* kb = wtok + C + h * D;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      const __nv_bfloat16* krow = kb + (nt * 8 + g) * RS;
+#pragma unroll
+      for (int kk = 0; kk < DP / 16; ++kk) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + kk * 16 + 2 * t);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + kk * 16 + 8 + 2 * t);
+        mma_bf16_16816(s[nt], qa[kk], b0, b1);
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float off0 = mx0 * p.scale_log2, off1 = mx1 * p.scale_log2;
+    float l0 = 0.f, l1 = 0.f;
+    uint32_t pa[KP][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const float e0 = ex2f_fast(fmaf(s[nt][0], p.scale_log2, -off0));
+      const float e1 = ex2f_fast(fmaf(s[nt][1], p.scale_log2, -off0));
+      const float e2 = ex2f_fast(fmaf(s[nt][2], p.scale_log2, -off1));
+      const float e3 = ex2f_fast(fmaf(s[nt][3], p.scale_log2, -off1));
+      l0 += e0 + e1;
+      l1 += e2 + e3;
+      __nv_bfloat162 p01 = __floats2bfloat162_rn(e0, e1);
+      __nv_bfloat162 p23 = __floats2bfloat162_rn(e2, e3);
+      pa[nt >> 1][(nt & 1) * 2 + 0] = *reinterpret_cast<uint32_t*>(&p01);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&p23);
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    // ---- O = P V; the odd last 8-column tile is computed as half of a pair (its twin reads the 16-byte row pad or the
+    //      next head's columns and is dropped) ----
+    float o[DP / 8][4];
+#pragma unroll
+    for (int i = 0; i < DP / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    const uint32_t vbase = static_cast<uint32_t>(__cvta_generic_to_shared(
+        wtok + 2 * C + h * D + ((lane & 7) + ((lane >> 3) & 1) * 8) * RS + (lane >> 4) * 8));
+#pragma unroll
+    for (int i = 0; i < DP / 8; i += 2) {
+#pragma unroll
+      for (int kk = 0; kk < KP; ++kk) {
+        uint32_t b0, b1, b2, b3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                     : "r"(vbase + static_cast<uint32_t>((kk * 16 * RS + i * 8) * 2)));
+        mma_bf16_16816(o[i], pa[kk], b0, b1);
+        mma_bf16_16816(o[i + 1], pa[kk], b2, b3);
+      }
+    }
+    __syncwarp();   // every lane has read its Q fragments before the tile is overwritten with O
+#pragma unroll
+    for (int i = 0; i < DP / 8; ++i) {
+      const int c = i * 8 + 2 * t;
+      if (c < D) {
+        *reinterpret_cast<__nv_bfloat162*>(qbase + g * qs + c) = __floats2bfloat162_rn(o[i][0] * i0, o[i][1] * i0);
+        *reinterpret_cast<__nv_bfloat162*>(qbase + (g + 8) * qs + c) = __floats2bfloat162_rn(o[i][2] * i1, o[i][3] * i1);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- store whole output rows (C bf16 per token) ----
+  const int nq = p.q_pool ? NQP : NTOK;
+  const int ww = p.q_pool ? W / 2 : W;
+  const int Wo = p.q_pool ? p.Wm / 2 : p.Wm;
+  for (int i = tid; i < WPC * nq * (C / 8); i += nthr) {
+    const int c = i % (C / 8), r = (i / (C / 8)) % nq, wi2 = i / ((C / 8) * nq);
+    const __nv_bfloat16* src = p.q_pool ? qp + (wi2 * QPR + r) * QPS + c * 8 : tok + (wi2 * NTOK + r) * RS + c * 8;
+    const int gy = wy * ww + r / ww, gx = (wx0 + wi2) * ww + r % ww;
+    *reinterpret_cast<uint4*>(p.out + b * p.o_bs + (static_cast<long long>(gy) * Wo + gx) * p.o_tok + c * 8) =
+        *reinterpret_cast<const uint4*>(src);
+  }
+}
+
+template <int W, int DP, int WPC>
+static int launch_win_small(const MhaParams& p, int C, cudaStream_t st) {
+  constexpr int NTOK = W * W;
+  const int qtiles = p.q_pool ? (NTOK / 4 + 15) / 16 : NTOK / 16;
+  const int tpw = p.H * qtiles;
+  // at least 8 warps: with few (pooled) tasks the extra warps only help staging and storing the window
+  const int threads = 32 * WPC * tpw < 256 ? 256 : 32 * WPC * tpw;
+  const int smem = (WPC * NTOK * (3 * C + 8) + WPC * ((NTOK / 4 + 15) / 16 * 16) * (C + 8)) * 2;
+  if (threads > 512 || smem > 200 * 1024) return -1;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(win_small_attn_kernel<W, DP, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    DS2_REQUIRE(e == cudaSuccess, static_cast<int>(e), "ds2_mha: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_smem = smem;
+  }
+  const int windows = p.B * p.nwy * p.nwx;
+  DS2_LAUNCH((win_small_attn_kernel<W, DP, WPC>), windows / WPC, threads, smem, st, p, C, tpw);
+  return post_launch("win_small_attn_kernel");
+}
+
+// 4x4 / 8x8 windows of a fused [q | k | v] buffer without zero-padded windows; -1 = shape not covered (generic kernel)
+static int try_win_small(const ds2_mha_args* a, const MhaParams& p, cudaStream_t st) {
+  const int C = a->H * a->D;
+  if (a->window != 4 && a->window != 8) return -1;
+  if ((a->Hm % a->window) || (a->Wm % a->window) || (C % 8)) return -1;
+  const __nv_bfloat16 *q = p.q, *k = p.k, *v = p.v;
+  if (k != q + C || v != q + 2 * C || a->q_tok_stride != 3 * C || a->k_tok_stride != 3 * C || a->v_tok_stride != 3 * C) return -1;
+  if (a->k_bs != a->q_bs || a->v_bs != a->q_bs || (a->o_tok_stride % 8) || (a->q_bs % 8) || (a->o_bs % 8)) return -1;
+  if ((reinterpret_cast<uintptr_t>(a->q) & 15) || (reinterpret_cast<uintptr_t>(a->out) & 15)) return -1;
+  const int DP = (a->D + 15) / 16 * 16;
+  if (DP - a->D != 0 && DP - a->D != 8) return -1;
+  if (a->window == 4) {
+    if (p.nwx % 2) return -1;
+    if (DP == 64) return launch_win_small<4, 64, 2>(p, C, st);
+    if (DP == 80) return launch_win_small<4, 80, 2>(p, C, st);
+    if (DP == 96) return launch_win_small<4, 96, 2>(p, C, st);
+    return -1;
+  }
+  if (DP == 64) return launch_win_small<8, 64, 1>(p, C, st);
+  if (DP == 80) return launch_win_small<8, 80, 1>(p, C, st);
+  if (DP == 96) return launch_win_small<8, 96, 1>(p, C, st);
+  return -1;
+}
+
 // ---- the mask decoder's two attention shapes (transformer.py:178-211: 8 heads x 16 dims) ---------------------------
 // (1) token -> image: 8-9 queries against 4096 keys per (object, head).  On the generic kernel one warp of one CTA walked
 //     the 64 key chunks in sequence (33 us, latency).  Here the chunks are dealt round-robin to the 4 warps of the 8 CTAs
@@ -662,6 +869,16 @@ extern "C" int ds2_mha(const ds2_mha_args* a, void* stream) {
       int rc = launch_win16_attn_tc(a, st);
       if (rc >= 0) return rc;
       rc = launch_glob_attn_tc(a, st);
+      if (rc >= 0) return rc;
+    }
+  }
+  if (a->window > 0) {
+    static const bool win_small = [] {
+      const char* e = getenv("DS2_WIN_SMALL");   // DS2_WIN_SMALL=0: generic kernel (A/B)
+      return !(e && e[0] == '0');
+    }();
+    if (win_small) {
+      const int rc = try_win_small(a, p, st);
       if (rc >= 0) return rc;
     }
   }

@@ -330,6 +330,9 @@ def _window_unpartition(win, w, pad_hw, hw):
 @pytest.mark.parametrize("Hm,w,heads,D,pool", [(32, 8, 2, 72, 0), (32, 8, 2, 72, 1), (16, 4, 4, 72, 0),
                                                 (16, 4, 2, 72, 1), (32, 16, 4, 72, 0), (32, 14, 2, 56, 0),
                                                 (32, 14, 2, 56, 1), (16, 7, 2, 96, 0),
+                                                # 4x4 / 8x8 windows without padding: the whole-window-per-CTA kernel
+                                                (16, 8, 1, 96, 0), (16, 4, 2, 56, 1), (32, 4, 8, 72, 1), (64, 8, 4, 72, 1),
+                                                (16, 8, 2, 56, 0), (24, 4, 4, 72, 0),
                                                 # 16x16 windows with head_dim in (64, 80]: the tcgen05 kernel
                                                 (64, 16, 8, 72, 0), (32, 16, 3, 80, 0), (16, 16, 1, 72, 0)])
 def test_mha_window(ops, Hm, w, heads, D, pool):
@@ -564,6 +567,14 @@ def test_mlp3(ops):
         ops.mlp3(x, tr(w1[:1]), b1[:1], tr(w2[:1]), b2[:1], tr(w3n), b3n, y3, rows=B * n, nmlp=1)
         hh = torch.relu(torch.relu(x @ w1[0].t() + b1[0]) @ w2[0].t() + b2[0])
         assert (y3 - (hh @ w3n[0].t() + b3n[0])).abs().max().item() < 1e-4
+    # object pointer head: 256 outputs, 16 and 64 rows (one and four row blocks of the cluster kernel)
+    for rows in (16, 64):
+        xr = torch.randn(rows, 256, device=DEV)
+        w3w, b3w = torch.randn(1, 256, 256, device=DEV) / 16, torch.randn(1, 256, device=DEV) * 0.1
+        y4 = torch.empty(rows, 256, device=DEV)
+        ops.mlp3(xr, tr(w1[:1]), b1[:1], tr(w2[:1]), b2[:1], tr(w3w), b3w, y4, rows=rows, nmlp=1)
+        hh = torch.relu(torch.relu(xr @ w1[0].t() + b1[0]) @ w2[0].t() + b2[0])
+        assert (y4 - (hh @ w3w[0].t() + b3w[0])).abs().max().item() < 1e-4
     xg = x[gather.long()]
     h = torch.relu(xg @ w1[0].t() + b1[0])
     h = torch.relu(h @ w2[0].t() + b2[0])

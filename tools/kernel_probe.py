@@ -130,7 +130,8 @@ def main():
     for fl, nm in ((0, "two key halves, tail wave split"), (1, "two key halves, whole items")):
         cases.append((f"flash cross B16 N28736 workspace ({nm})",
                       lambda fl=fl: ops.flash_attn(q, k, v, o, 1 / 16.0, workspace=fws, flags=fl), 2.0 * 16 * 4096 * 28736 * 320, None))
-    for im, nm in ((9, "2 softmax wg"), (2, "Q in smem"), (6, "no exps")):
+    for im, nm in ((9, "2 softmax wg"), (2, "Q in smem"), (6, "no exps"), (5, "half of each K tile loaded"),
+                   (13, "MMA pipeline only, softmax relays")):
         cases.append((f"flash cross B16 N28736 impl{im} ({nm})", lambda im=im: ops.flash_attn(q, k, v, o, 1 / 16.0, impl=im),
                       2.0 * 16 * 4096 * 28736 * 320, None))
     qs = torch.randn(16, 4096, 768, device=dev).to(BF16)
