@@ -139,11 +139,10 @@ def run_ours(args):
     vid = BilliardVideo(num_objects=B, height=S, width=S, num_frames=nfr, seed=rank)
     frames = list(vid.frames())
 
+    from detsam2_b200 import streams
+
     def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        streams.barrier(dev)      # synchronize + (world > 1) host-side barrier + synchronize
 
     def session(offload_video):
         st = predictor.init_state(frames, offload_video_to_cpu=offload_video)
@@ -204,10 +203,7 @@ def run_ours(args):
             timers, eng.kernel_timers = eng.kernel_timers, None
             for tag, a, b, meta in timers:
                 kern.setdefault(tag, []).append((a.elapsed_time(b), meta))
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
+        ms = streams.max_over_ranks(ms)     # the slowest rank's device time
         results[mode] = ms
         results[mode + "_host"] = host_ms
         del st, gen

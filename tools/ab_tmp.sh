@@ -1,2 +1,1 @@
-python tools/dec_attn_trace.py points_api 2>&1 | tail -10
-python -m pytest tests/test_engine_gpu.py tests/test_image_predictor.py tests/test_fullsize_gpu.py -m gpu -q 2>&1 | tail -5
+for il in 0 3 0 3; do echo "IL=$il"; DS2_FLASH_IL=$il python bench.py --only-device --no-cpu-baseline --no-extra-legs 2>/dev/null | cut -c1-120; done
