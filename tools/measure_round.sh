@@ -20,3 +20,7 @@ head -30 $o/${tag}_launch_summary.txt
 cut -c1-1500 $o/${tag}_bench.json
 cut -c1-400 $o/${tag}_bench_stream.json
 cut -c1-600 $o/${tag}_bench_reference.json
+# warm per-seam and per-op times of the same configuration (CUDA events; graphs on for the seams, off for the op trace)
+python tools/seam_times.py > $o/${tag}_seam_times.json 2>/dev/null
+python tools/op_trace.py --prefill 8 --steps 3 --out $o/${tag}_op_trace.txt > /dev/null 2>&1
+tail -1 $o/${tag}_seam_times.json | cut -c1-700
