@@ -398,11 +398,8 @@ __global__ void __launch_bounds__(kGlobThreads, 2) glob_attn_tc_kernel(const Glo
     __syncthreads();
     tc::tc_fence_after();
     GLOB_T(2);
-    if (j + 1 < n_tiles) {  // next tile's rows: in flight during this tile's MMAs and softmax
-      load8(ksrc, p.k_tok, (j + 1) * 128, kreg);
-      load8(vsrc, p.v_tok, (j + 1) * 128, vreg);
-    }
-    GLOB_T(3);
+    // Q K^T goes to the tensor pipe FIRST; only then does anybody issue the next tile's 16 global loads (they used to sit
+    // between the barrier and the MMA issue: 1 600 clk of every 6 500-clk tile on the critical path, DS2_WIN_DBG=1)
     // elect.sync evaluated in place (a cached predicate makes the compiler serialise every tcgen05.mma)
     if (warp == 4 && tc::elect_one()) {
 #pragma unroll
@@ -412,6 +409,14 @@ __global__ void __launch_bounds__(kGlobThreads, 2) glob_attn_tc_kernel(const Glo
                     ks != 0 ? 1u : 0u);
       }
       tc::umma_commit(bar_s);
+    }
+    __syncwarp();
+    if (j + 1 < n_tiles) {  // next tile's rows: in flight during this tile's MMAs and softmax
+      load8(ksrc, p.k_tok, (j + 1) * 128, kreg);
+      load8(vsrc, p.v_tok, (j + 1) * 128, vreg);
+    }
+    GLOB_T(3);
+    if (warp == 4 && tc::elect_one()) {
       tc::mbar_wait(bar_p, j & 1);
       tc::tc_fence_after();
 #pragma unroll
