@@ -154,9 +154,13 @@ def run_ours(args):
     clocks = None
     launches = 0
     kern = {}
+    overlap_default = predictor.encoder_overlap
     # "kernel": a few extra steps of the same workload with the memory-attention seam launched eagerly, so
     # that CUDA events can bracket the dominant kernel (events cannot bracket a node of a replayed graph)
     for mode in (("device",) if args.only_device else ("device", "e2e", "kernel")):
+        # the dominant kernel is timed with the GPU to itself: in the "kernel" leg the encoder passes stay on the tracker's
+        # stream (in the `value` / `e2e` legs they run on the encoder stream and share the SMs with the tracker)
+        predictor.encoder_overlap = overlap_default and mode != "kernel"
         st, gen = session(offload_video=(mode == "e2e"))
         bits = torch.empty((B * S * S) // 8, dtype=torch.uint8, device=dev)
         host_bits = torch.empty((B * S * S) // 8, dtype=torch.uint8).pin_memory()
@@ -215,7 +219,8 @@ def run_ours(args):
     fps = world * K / (results["device"] / 1e3)
     if args.only_device:   # A/B runs of a kernel change: the device-resident leg alone (not a bench line)
         print(json.dumps({"ab_only_device": True, "value": round(fps, 3), "ms_per_step": round(results["device"] / K, 3),
-                          "encoder_batch_frames": predictor.encoder_batch_frames, "clocks": clocks,
+                          "encoder_batch_frames": predictor.encoder_batch_frames, "encoder_overlap": overlap_default,
+                          "clocks": clocks,
                           "host_enqueue_ms_per_step": round(results["device_host"] / K, 3)}), flush=True)
         return
     fps_e2e = world * K / (results["e2e"] / 1e3)
@@ -244,8 +249,9 @@ def run_ours(args):
                 "achieved_reference_formulation": round(fm["cross_alg_per_launch"] / (avg_ms * 1e-3) / 1e12, 1),
                 "share_of_step": round(sum(durs) / results["kernel"], 4),
                 "timing": f"CUDA events around each of the {len(durs)} launches of {K} extra steps of the same workload with "
-                          f"the memory-attention seam launched eagerly ({round(results['kernel'] / K, 3)} ms/step); the "
-                          f"timed `value` steps replay CUDA graphs, whose nodes events cannot bracket"}
+                          f"the memory-attention seam launched eagerly and the encoder passes on the same stream, i.e. the "
+                          f"kernel has the GPU to itself ({round(results['kernel'] / K, 3)} ms/step); the timed `value` "
+                          f"steps replay CUDA graphs, whose nodes events cannot bracket"}
     line = {
         "metric": METRIC, "value": round(fps, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(results["device"] / K, 3), "higher_is_better": True, "scaling": "weak",
@@ -256,6 +262,10 @@ def run_ours(args):
                    "encoder_batching": "the image encoder runs once per frame, several upcoming frames per launch sequence "
                                        "(bit-identical per frame); features encoded ahead during warm-up are dropped "
                                        "before the timed region",
+                   "encoder_overlap": overlap_default,
+                   "encoder_overlap_note": "the pass over the next frames runs on the engine's encoder stream while the "
+                                           "tracker works on the frames of the previous pass (same kernels, same bits); the "
+                                           "first pass of the timed region has nothing to overlap with and is waited for",
                    "weights": "seeded random init (no checkpoints offline)",
                    "l2": "per-step working set (weights 0.45 GB + bank + activations > 1 GB) exceeds the 126 MB L2; no explicit flush",
                    "parallelism": f"{world} independent streams, no collective"},

@@ -194,6 +194,25 @@ class FrameFeats:
         self.pix_proj = None
 
 
+class PendingFeats:
+    """Features of an encoder pass that is still running on the engine's encoder stream (encode_images_async)."""
+    __slots__ = ("feats", "event", "_joined")
+
+    def __init__(self, feats, event):
+        self.feats, self.event, self._joined = feats, event, False
+
+    def wait(self):
+        """Orders the CALLER's current stream after the pass and returns its list of FrameFeats (no host sync)."""
+        if not self._joined:
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self.event)
+            for f in self.feats:
+                for t in (f.vis_f32, f.vis_bf16, f.feat_s0, f.feat_s1):
+                    t.record_stream(cur)   # allocated on the encoder stream, read (and eventually freed) on this one
+            self._joined = True
+        return self.feats
+
+
 class CudaEngine:
     name = "cuda-sm100a"
 
@@ -209,6 +228,10 @@ class CudaEngine:
         # bench.py sets this to a list to collect (tag, start_event, end_event, meta) of the dominant kernel
         # (CUDA events cannot bracket a node inside a replayed graph, so that seam then runs eagerly)
         self.kernel_timers = None
+        # encoder passes launched ahead of their frames run on their own stream (encode_images_async); every encoder
+        # pass, on whichever stream, is ordered after the previous one: they share the encoder's workspaces
+        self._enc_stream = None
+        self._enc_last = None
         with torch.cuda.device(self.device):
             self.graphs = _SeamGraphs(self.device, enabled=(use_graphs and os.environ.get("DS2_GRAPHS", "1") != "0"))
             self._tables = _TableRing(self.device)
@@ -455,9 +478,44 @@ class CudaEngine:
         S = cfg.image_size
         if image_f16.dtype != torch.float16 or tuple(image_f16.shape) != (3, S, S):
             raise Ds2Error(f"encode_image expects an fp16 [3,{S},{S}] frame, got {image_f16.dtype} {tuple(image_f16.shape)}")
+        self._enc_fence()
         vis, vis16, feat_s0, feat_s1 = self.graphs.run(("enc",), {"img": image_f16.contiguous()},
                                                        self._encode_image_body, (True, True, True, True))
+        self._enc_mark()
         return FrameFeats(vis, vis16, feat_s0, feat_s1)
+
+    def _enc_fence(self):
+        """The encoder's workspaces and static graph inputs exist once: a pass waits for the previous pass, which may
+        have been launched on another stream (a no-op event wait when it was this stream)."""
+        if self._enc_last is not None:
+            torch.cuda.current_stream().wait_event(self._enc_last)
+
+    def _enc_mark(self):
+        ev = torch.cuda.Event()
+        ev.record()
+        self._enc_last = ev
+        return ev
+
+    def encode_images_async(self, images_f16):
+        """``encode_images`` on the engine's encoder stream: returns at once with a PendingFeats handle.
+
+        The backbone of the frames a propagate call will reach next does not depend on the tracker, so the predictor
+        launches it while the tracker works on the frames already encoded.  The tracker's step is a chain of ~250
+        dependent launches, many of them far smaller than the GPU (decoder, memory encoder, hole filling) and its
+        largest kernel ends on a partial wave (3.46 waves of 148 CTAs at 16 objects); the encoder's CTAs fill those
+        holes.  Same kernels, same arithmetic, same bits per frame — only the placement in time changes.  The pass
+        starts after everything the calling stream has enqueued so far (the frames it reads are ready by then)."""
+        cur = torch.cuda.current_stream()
+        if self._enc_stream is None:
+            self._enc_stream = torch.cuda.Stream(device=self.device)
+        s = self._enc_stream
+        s.wait_stream(cur)
+        if images_f16.is_cuda:
+            images_f16.record_stream(s)
+        with torch.cuda.stream(s):
+            feats = self.encode_images(images_f16)
+            ev = self._enc_last    # recorded on the encoder stream by encode_images / encode_image
+        return PendingFeats(feats, ev)
 
     def encode_images(self, images_f16):
         """Several frames through ONE pass of the encoder: fp16 [n,3,S,S] -> list of n FrameFeats.
@@ -477,8 +535,10 @@ class CudaEngine:
         if n == 1:
             return [self.encode_image(images_f16[0])]
         body = lambda inp: self._encode_image_body(inp, n)  # noqa: E731
+        self._enc_fence()
         vis, vis16, feat_s0, feat_s1 = self.graphs.run(("enc", n), {"img": images_f16.contiguous()}, body,
                                                        (True, True, True, True))
+        self._enc_mark()
         return [FrameFeats(*(t.view(n, t.shape[0] // n, t.shape[1])[i] for t in (vis, vis16, feat_s0, feat_s1)))
                 for i in range(n)]
 

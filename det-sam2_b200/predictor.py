@@ -47,7 +47,7 @@ class SAM2VideoPredictor:
 
     def __init__(self, engine, fill_hole_area=0, non_overlap_masks=False, clear_non_cond_mem_around_input=False,
                  clear_non_cond_mem_for_multi_obj=False, add_all_frames_to_correct_as_cond=False,
-                 feature_cache_frames=1, encoder_batch_frames=None, verbose=False):
+                 feature_cache_frames=1, encoder_batch_frames=None, encoder_overlap=None, verbose=False):
         self.engine = engine
         self.cfg = engine.cfg
         self.fill_hole_area = fill_hole_area
@@ -65,8 +65,16 @@ class SAM2VideoPredictor:
         if encoder_batch_frames is None:
             encoder_batch_frames = int(os.environ.get("DS2_ENC_BATCH", "4"))
         self.encoder_batch_frames = max(1, int(encoder_batch_frames)) if hasattr(engine, "encode_images") else 1
+        # while the tracker works through the frames of one encoder pass, the pass over the NEXT frames of the processing
+        # order runs on the engine's encoder stream (engine.encode_images_async) and fills the SMs the tracker's small
+        # kernels and partial waves leave idle.  Same kernels and bits; DS2_ENC_OVERLAP=0 (or encoder_overlap=False)
+        # keeps every pass on the caller's stream.
+        if encoder_overlap is None:
+            encoder_overlap = os.environ.get("DS2_ENC_OVERLAP", "1") != "0"
+        self.encoder_overlap = bool(encoder_overlap) and hasattr(engine, "encode_images_async")
         self._upcoming = None      # (id(state), frames the running propagate call will still encode, in order)
         self._prefetched = {}      # frame_idx -> features encoded ahead of their step (same propagate call only)
+        self._pending = None       # (frames, PendingFeats): the pass in flight on the encoder stream, at most one
         self.verbose = verbose
 
     @classmethod
@@ -513,6 +521,7 @@ class SAM2VideoPredictor:
             self._upcoming = (id(st), [f for f in order if f not in cons["cond_frame_outputs"]
                                        and f not in cons["non_cond_frame_outputs"]])
             self._prefetched = {}
+            self._pending = None
         try:
             for frame_idx in order:
                 if frame_idx in cons["cond_frame_outputs"]:
@@ -538,6 +547,7 @@ class SAM2VideoPredictor:
         finally:
             self._upcoming = None
             self._prefetched = {}
+            self._pending = None
 
     def _add_output_per_object(self, st, frame_idx, current_out, storage_key):
         """svp:1027-1058: per-object views sharing storage with the batched output."""
@@ -628,17 +638,20 @@ class SAM2VideoPredictor:
         feats = cache.get(frame_idx, None)
         if feats is not None:
             return feats
-        if self._upcoming is not None and self._upcoming[0] == id(st):
+        E = self.encoder_batch_frames
+        in_order = False
+        if E > 1 and self._upcoming is not None and self._upcoming[0] == id(st):
+            if self._pending is not None and frame_idx in self._pending[0]:
+                self._join_pending()
             feats = self._prefetched.pop(frame_idx, None)
+            todo = self._upcoming[1]
+            in_order = frame_idx in todo
+            if in_order:
+                del todo[:todo.index(frame_idx) + 1]     # everything up to this frame has been handled
         if feats is None:
-            batch = self._encoder_batch(st, frame_idx)
+            batch = [frame_idx] + (self._next_frames(st, E - 1) if in_order else [])
             if len(batch) > 1:
-                rows = sorted((st["images_idx"].index(f), f) for f in batch)
-                r0, r1 = rows[0][0], rows[-1][0]
-                images = st["images"]
-                # neighbouring rows (the usual case, forward or reverse) are a view; anything else is gathered
-                stack = images[r0:r1 + 1] if r1 - r0 + 1 == len(rows) else images[[r for r, _ in rows]]
-                for (_, f), o in zip(rows, self.engine.encode_images(stack)):
+                for f, o in zip(*self._encode_frames(st, batch, False)):
                     if f == frame_idx:
                         feats = o
                     else:
@@ -647,6 +660,11 @@ class SAM2VideoPredictor:
                 row = st["images_idx"].index(frame_idx)
                 image = st["images"][row]
                 feats = self.engine.encode_image(image)
+        if in_order and self.encoder_overlap and self._pending is None:
+            # the pass that holds this frame has just started to be consumed: launch the next one behind it
+            batch = self._next_frames(st, E)
+            if batch:
+                self._pending = self._encode_frames(st, batch, True)
         if self.feature_cache_frames <= 1:
             st["cached_features"] = {frame_idx: feats}
         else:
@@ -655,27 +673,40 @@ class SAM2VideoPredictor:
             cache[frame_idx] = feats
         return feats
 
+    def _encode_frames(self, st, batch, on_encoder_stream):
+        """One encoder pass over the frames of ``batch``: (frames in row order, their features or a PendingFeats)."""
+        rows = sorted((st["images_idx"].index(f), f) for f in batch)
+        r0, r1 = rows[0][0], rows[-1][0]
+        images = st["images"]
+        # neighbouring rows (the usual case, forward or reverse) are a view; anything else is gathered
+        stack = images[r0:r1 + 1] if r1 - r0 + 1 == len(rows) else images[[r for r, _ in rows]]
+        frames = [f for _, f in rows]
+        if on_encoder_stream:
+            return frames, self.engine.encode_images_async(stack)
+        return frames, self.engine.encode_images(stack)
+
+    def _join_pending(self):
+        frames, pend = self._pending
+        self._pending = None
+        for f, o in zip(frames, pend.wait()):
+            self._prefetched[f] = o
+
     def drop_encoded_ahead(self):
         """Forgets features that were encoded ahead of their step (bench.py calls this at the start of its timed region
         so that every frame tracked inside the region is also encoded inside it)."""
         self._prefetched = {}
+        self._pending = None
 
-    def _encoder_batch(self, st, frame_idx):
-        """Frames to encode together with ``frame_idx``: the next ones of the running propagate call that have neither
-        cached nor prefetched features and whose pixels the session still holds."""
-        up = self._upcoming
-        E = self.encoder_batch_frames
-        if E <= 1 or up is None or up[0] != id(st) or frame_idx not in up[1]:
-            return [frame_idx]
-        todo = up[1]
-        pos = todo.index(frame_idx)
-        del todo[:pos + 1]             # everything before this frame has been handled
+    def _next_frames(self, st, n):
+        """Up to ``n`` frames the running propagate call will reach next that have neither cached nor prefetched
+        features, are not in the pass in flight, and whose pixels the session still holds."""
         cache, have = st["cached_features"], set(st["images_idx"])
-        batch = [frame_idx]
-        for f in todo:
-            if len(batch) >= E:
+        flying = self._pending[0] if self._pending is not None else ()
+        batch = []
+        for f in self._upcoming[1]:
+            if len(batch) >= n:
                 break
-            if f not in cache and f not in self._prefetched and f in have:
+            if f not in cache and f not in self._prefetched and f not in flying and f in have:
                 batch.append(f)
         return batch
 

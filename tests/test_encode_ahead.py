@@ -91,6 +91,61 @@ def test_encode_ahead_abandoned_generator_leaves_no_state():
         pred.add_new_points_or_box(st, 5, 0, box=np.asarray(vid.boxes(5)[0], dtype=np.float32))
 
 
+@pytest.mark.parametrize("reverse,chunks,cache", [(False, 1, 1), (False, 2, 1), (True, 3, 1), (True, 3, 16)])
+def test_overlapped_encoder_bookkeeping_on_oracle_engine(reverse, chunks, cache):
+    """The pass over the NEXT frames is launched (engine.encode_images_async) when the current pass starts to be
+    consumed and joined when its first frame is reached: same results, every frame encoded exactly as often as without
+    the overlap, at most one pass in flight, nothing left behind."""
+    from oracle import sam2_oracle as O
+    cfg = get_config("tiny", image_size=256)
+    sd = synthetic_state_dict(cfg, 0)
+    vid = BilliardVideo(num_objects=2, height=96, width=128, num_frames=12, seed=3)
+
+    class AsyncOracle(O.OracleEngine):
+        launched = joined = frames_encoded = 0
+        pred = None
+
+        def encode_image(self, image):
+            self.frames_encoded += 1
+            return super().encode_image(image)
+
+        def encode_images_async(self, images):
+            eng = self
+            assert eng.pred._pending is None    # at most one pass in flight on the encoder stream
+            eng.launched += 1
+            feats = self.encode_images(images)
+
+            class Pending:
+                def wait(self):
+                    eng.joined += 1
+                    return feats
+            return Pending()
+
+    def run(overlap):
+        eng = AsyncOracle(cfg, sd, fill_holes=False)
+        pred = SAM2VideoPredictor(eng, fill_hole_area=0, feature_cache_frames=cache, encoder_batch_frames=4,
+                                  encoder_overlap=overlap)
+        assert pred.encoder_overlap == overlap
+        eng.pred = pred
+        res, st = _track(pred, vid, 12, reverse=reverse, chunks=chunks)
+        assert pred._upcoming is None and pred._prefetched == {} and pred._pending is None
+        return res, eng
+
+    sync, e0 = run(False)
+    over, e1 = run(True)
+    assert e0.launched == 0 and e1.launched > 0
+    assert e1.joined == e1.launched              # a pass is only launched for frames the call will reach
+    assert e1.frames_encoded == e0.frames_encoded
+    _same(sync, over, exact=True)
+
+
+def test_overlap_needs_an_engine_with_an_encoder_stream():
+    from oracle import sam2_oracle as O
+    cfg = get_config("tiny", image_size=256)
+    pred = SAM2VideoPredictor(O.OracleEngine(cfg, synthetic_state_dict(cfg, 0), fill_holes=False), encoder_overlap=True)
+    assert pred.encoder_overlap is False
+
+
 # ------------------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("model,size", [("tiny", 512), ("large", 1024)])
@@ -118,7 +173,37 @@ def test_tracking_is_bit_identical_with_encode_ahead():
     sd = synthetic_state_dict(cfg, 0)
     vid = BilliardVideo(num_objects=3, height=512, width=512, num_frames=12, seed=6)
     res = {}
-    for E in (1, 4):
-        pred = SAM2VideoPredictor(CudaEngine(cfg, sd), fill_hole_area=8, encoder_batch_frames=E)
-        res[E], _ = _track(pred, vid, 12, reverse=True, chunks=3)
-    _same(res[1], res[4], exact=True)
+    for E, overlap in ((1, False), (4, False), (4, True)):
+        pred = SAM2VideoPredictor(CudaEngine(cfg, sd), fill_hole_area=8, encoder_batch_frames=E, encoder_overlap=overlap)
+        assert pred.encoder_overlap == overlap
+        res[E, overlap], _ = _track(pred, vid, 12, reverse=True, chunks=3)
+    _same(res[1, False], res[4, False], exact=True)
+    _same(res[1, False], res[4, True], exact=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("host_frames", [False, True])
+def test_overlapped_encoder_is_bit_identical_on_a_long_forward_run(host_frames):
+    """Encoder passes on the engine's own stream while the tracker runs (engine.encode_images_async): 40 frames, forward,
+    the host never synchronises inside the loop (so the two streams really overlap and the CUDA graphs of both seams are
+    replayed concurrently) — every mask logit equal to the run that keeps the encoder on the tracker's stream."""
+    from detsam2_b200.engine import CudaEngine
+    cfg = get_config("tiny", image_size=512)
+    sd = synthetic_state_dict(cfg, 0)
+    vid = BilliardVideo(num_objects=4, height=512, width=512, num_frames=40, seed=8)
+    frames = [vid.frame(t) for t in range(40)]
+    res = {}
+    for overlap in (False, True):
+        pred = SAM2VideoPredictor(CudaEngine(cfg, sd), fill_hole_area=8, encoder_batch_frames=4, encoder_overlap=overlap)
+        with torch.inference_mode():
+            st = pred.init_state(frames, offload_video_to_cpu=host_frames)
+            for oid, b in vid.boxes(0).items():
+                pred.add_new_points_or_box(st, 0, oid, box=np.asarray(b, dtype=np.float32))
+            out = [(f, m) for f, _, m in pred.propagate_in_video(st)]     # device tensors: no sync until the end
+            torch.cuda.synchronize()
+        res[overlap] = out
+        if overlap:
+            assert pred.engine._enc_stream is not None
+    assert len(res[False]) == len(res[True]) == 40
+    for (fa, ma), (fb, mb) in zip(res[False], res[True]):
+        assert fa == fb and torch.equal(ma, mb), fa
