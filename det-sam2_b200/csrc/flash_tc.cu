@@ -27,6 +27,7 @@
 // traffic per FLOP (K tiles come out of L2, which is the binding bandwidth here).
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.h"
 #include "tc05.cuh"
@@ -54,6 +55,7 @@ struct FlashParams {
                            // once, profiles/r2_s7_flash_softmax_stage_accounting.txt, and removed: they cost registers.)
   const __nv_bfloat16* q;  // QT kernels read the query rows straight from global memory
   long long ldq, bsq;
+  int H, D;                // HD == 80 kernels (Hiera global attention): heads per batch item, head h at column h * D
   __nv_bfloat16* out;
   long long ldo, bso;
 };
@@ -65,21 +67,31 @@ struct FlashParams {
 // for tile j.  The groups' partial results are combined like the two key halves (fixed order, through the workspace).
 // TP = 1: the instantiation that runs every item as two key halves through the workspace (see FlashParams); the plain
 // instantiation (TP = 0) contains none of that code — it costs the single-pass kernel ~120 registers otherwise.
-template <int DV, int BN, int NQ, int KS, int VS, int SP, int QT, int IL = 1, int TP = 0>
+// HD = 80: the multi-head variant for Hiera's global-attention blocks (hieradet.py:57-82 with window_size == 0): head_dim
+// 72 zero-padded to 80 = 5 K-steps, DV = 80, one CTA per (query tile, head, frame).  K and V rows of a head are 144-byte
+// segments of the token-major qkv matrix, so a tile is fetched as TWO 64-column TMA boxes: columns [h*D, h*D+64) and
+// [h*D+64, h*D+128) — the second box carries 8 real dims and, beyond them, the next head's data (or TMA zero fill past the
+// end of the row).  That tail is harmless: Q's columns D..79 are stored as zeros (so it adds nothing to Q.K^T), and the
+// output columns D..79 it produces in P.V are never written out.
+template <int DV, int BN, int NQ, int KS, int VS, int SP, int QT, int IL = 1, int TP = 0, int HD = 256>
 struct FlashCfg {
+  static constexpr int kKBox = (HD + 63) / 64;    // 64-column boxes per K tile
+  static constexpr int kVBox = (DV + 63) / 64;
+  static constexpr int kQCols = HD == 256 ? 128 : 48;   // TMEM columns of a query tile (bf16 pairs; 40 used + 8 zero at HD = 80)
   // IL == 2: three whole warpgroups — warps 0-3 control (TMA producer, MMA issuer, two idle), warps 4-7 / 8-11 the two
   // softmax groups — so that setmaxnreg can move registers from the control warpgroup to the softmax warpgroups
   static constexpr int kSoftmaxWarp0 = IL == 2 ? 4 : 2;
   static constexpr int kThreads = 32 * kSoftmaxWarp0 + 128 * NQ * SP * IL;
   static constexpr int kXchBytes = 2 * SP * NQ * kQM * 2;  // [parity][part][row] bf16 partial maxima
-  static constexpr int kQBytes = QT ? 0 : kQM * kHD * 2;  // 64 KB per query tile when Q is a shared-memory operand
-  static constexpr int kKBytes = BN * kHD * 2;
-  static constexpr int kVBytes = BN * DV * 2;
+  static constexpr int kQBytes = QT ? 0 : kQM * kKBox * 128;  // 64 KB per query tile when Q is a shared-memory operand
+  static constexpr int kKBytes = BN * kKBox * 128;
+  static constexpr int kVBytes = BN * kVBox * 128;
   static constexpr int kSmemData = NQ * kQBytes + KS * kKBytes + VS * kVBytes;
   static constexpr int kBarBytes = 256;
   static constexpr int kSmem = kSmemData + 1024 + kBarBytes + (kXchBytes < 1024 ? 1024 : kXchBytes);
-  static_assert(BN % (32 * SP) == 0 && DV % (32 * SP) == 0, "column split");
-  static constexpr int kTmemCols = 2 * NQ * BN + NQ * IL * DV + (QT ? NQ * (kHD / 2) : 0);
+  static_assert(BN % (32 * SP) == 0 && (DV % (32 * SP) == 0 || DV == 80), "column split");
+  static constexpr int kTmemCols = 2 * NQ * BN + NQ * IL * DV + (QT ? NQ * kQCols : 0);
+  static_assert(HD == 256 || (HD == 80 && DV == 80 && QT == 1 && NQ == 1 && TP == 0 && SP <= 2 && IL == 1), "multi-head variant");
   static_assert(IL == 1 || (IL == 2 && SP == 1 && NQ == 1), "alternating softmax groups: one query tile, unsplit rows");
   static_assert(TP == 0 || (SP == 1 && NQ == 1), "two key halves: one query tile, unsplit rows");
   static_assert(kTmemCols <= 512, "TMEM budget");
@@ -109,12 +121,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int DV, int BN, int NQ, int KS, int VS, int SP, int QT, int IL = 1, int TP = 0>
+template <int DV, int BN, int NQ, int KS, int VS, int SP, int QT, int IL = 1, int TP = 0, int HD = 256>
 __global__ void __launch_bounds__((IL == 2 ? 128 : 64) + 128 * NQ * SP * IL, 1)
 flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
                           const __grid_constant__ CUtensorMap tmap_k,
                           const __grid_constant__ CUtensorMap tmap_v, const FlashParams p) {
-  using Cfg = FlashCfg<DV, BN, NQ, KS, VS, SP, QT, IL, TP>;
+  using Cfg = FlashCfg<DV, BN, NQ, KS, VS, SP, QT, IL, TP, HD>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sq = smem_base;
@@ -144,7 +156,8 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     kv_parts = 2;
   }
   const int q0 = (item % p.q_tiles) * (kQM * NQ);
-  const int b = item / p.q_tiles;
+  const int b = HD == 256 ? item / p.q_tiles : (item / p.q_tiles) / p.H;
+  const int hcol = HD == 256 ? 0 : ((item / p.q_tiles) % p.H) * p.D;   // first column of this CTA's head
   const int all_tiles = (p.Lk + BN - 1) / BN;
   const int j0 = (all_tiles * kv_part) / kv_parts;                     // first key tile of this CTA
   const int n_tiles = (all_tiles * (kv_part + 1)) / kv_parts - j0;    // its number of key tiles (>= 1)
@@ -157,7 +170,7 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     if (!QT) tc::prefetch_tmap(&tmap_q);
     tc::prefetch_tmap(&tmap_k);
     tc::prefetch_tmap(&tmap_v);
-    for (int i = 0; i < NQ; ++i) tc::mbar_init(bar(o_q, i), QT ? 4 * SP : 1);
+    for (int i = 0; i < NQ; ++i) tc::mbar_init(bar(o_q, i), QT ? (HD == 256 ? 4 * SP : 4) : 1);
     for (int i = 0; i < KS; ++i) {
       tc::mbar_init(bar(o_kfull, i), 1);
       tc::mbar_init(bar(o_kempty, i), 1);
@@ -191,7 +204,7 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
   // the tensor core reads only the K tile from shared memory.  With both operands in shared memory a
   // 128x128x16 MMA reads 8 KB per 64 clk = the whole 128 B/clk of the SM's shared memory, on top of the
   // TMA writes of the K/V rings — the kernel was shared-memory-bandwidth bound at ~52 % of the MMA rate.
-  auto tmem_q = [&](int h) { return tmem_base + static_cast<uint32_t>(2 * NQ * BN + NQ * IL * DV + h * (kHD / 2)); };
+  auto tmem_q = [&](int h) { return tmem_base + static_cast<uint32_t>(2 * NQ * BN + NQ * IL * DV + h * Cfg::kQCols); };
 
   // Role gates use elect.sync, not `lane == 0`: tcgen05.mma / TMA take their operands from the uniform
   // datapath, and under a lane-id predicate the compiler wraps EVERY such instruction in an
@@ -205,7 +218,7 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     if (!QT) {
       for (int h = 0; h < NQ; ++h) {
         tc::mbar_expect_tx(bar(o_q, h), Cfg::kQBytes);
-        for (int kk = 0; kk < kHD / 64; ++kk)
+        for (int kk = 0; kk < Cfg::kKBox; ++kk)
           tc::tma_load_3d(sq + h * Cfg::kQBytes + kk * (kQM * 128), &tmap_q, bar(o_q, h), kk * 64,
                           q0 + h * kQM, b);
       }
@@ -214,19 +227,20 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       {
         const int s = j % KS;
         tc::mbar_wait(bar(o_kempty, s), ((j / KS) & 1) ^ 1);
-        const int nkk = (p.dbg == 1) ? kHD / 128 : kHD / 64;
+        const int nkk = (p.dbg == 1) ? Cfg::kKBox / 2 : Cfg::kKBox;   // (timing experiment: half of the boxes)
         tc::mbar_expect_tx(bar(o_kfull, s), nkk * (BN * 128));
         const uint32_t sk = sk0 + s * Cfg::kKBytes;
         for (int kk = 0; kk < nkk; ++kk)
-          tc::tma_load_3d(sk + kk * (BN * 128), &tmap_k, bar(o_kfull, s), kk * 64, (j0 + j) * BN, b);
+          tc::tma_load_3d(sk + kk * (BN * 128), &tmap_k, bar(o_kfull, s), hcol + kk * 64, (j0 + j) * BN, b);
       }
       {
         const int s = j % VS;
         tc::mbar_wait(bar(o_vempty, s), ((j / VS) & 1) ^ 1);
-        tc::mbar_expect_tx(bar(o_vfull, s), Cfg::kVBytes);
+        const int nvb = (HD != 256 && p.dbg == 1) ? 1 : Cfg::kVBox;
+        tc::mbar_expect_tx(bar(o_vfull, s), nvb * (BN * 128));
         const uint32_t sv = sv0 + s * Cfg::kVBytes;
-        for (int nn = 0; nn < DV / 64; ++nn)
-          tc::tma_load_3d(sv + nn * (BN * 128), &tmap_v, bar(o_vfull, s), nn * 64, (j0 + j) * BN, b);
+        for (int nn = 0; nn < nvb; ++nn)
+          tc::tma_load_3d(sv + nn * (BN * 128), &tmap_v, bar(o_vfull, s), hcol + nn * 64, (j0 + j) * BN, b);
       }
     }
   } else if (warp == 1 && tc::elect_one()) {
@@ -246,7 +260,7 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const uint32_t d = tmem_s(h, j & 1);
         const uint32_t sqh = sq + h * Cfg::kQBytes;
 #pragma unroll
-        for (int k = 0; k < kHD / 16; ++k) {
+        for (int k = 0; k < HD / 16; ++k) {
           const uint64_t db = tc::make_desc_sw128(sk + (k >> 2) * (BN * 128) + (k & 3) * 32, 16, 1024);
           if (QT) {
             tc::umma_ts(d, tmem_q(h) + k * 8, db, idesc_qk, k != 0 ? 1u : 0u);
@@ -305,12 +319,50 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const uint32_t lane_off = static_cast<uint32_t>(lq * 32) << 16;
     const int rloc = h * kQM + lq * 32 + lane;  // row inside the CTA
     const int row = q0 + rloc;
-    const uint32_t to = tmem_o(h, g) + lane_off + part * OW;
+    // O columns of a row owned by this thread.  DV % (32 SP) == 0: [part * OW, +OW) as 32-column chunks.  DV == 80 (kOdd):
+    // the chunks at 0 and 32 plus the 16-column chunk at 64 for one thread per row; split over two threads, part 0 owns the
+    // chunks at 0 and 64, part 1 the chunk at 32 (tcgen05.ld / st are warp-wide: `part` is uniform in a warp).
+    constexpr bool kOdd = DV == 80;
+    const uint32_t to = tmem_o(h, g) + lane_off + (kOdd ? (SP == 1 ? 0 : part * 32) : part * OW);
+    constexpr int N32 = kOdd ? (SP == 1 ? 2 : 1) : OW / 32;
+    const bool has16 = kOdd && part == 0;
+    const uint32_t to16 = tmem_o(h, g) + lane_off + 64;
     const int bar_id = 1 + h * 4 + lq;  // named barrier of the SP warps that share these 32 rows
     auto xch_max = [&](int par, int pt) {
       return xch_base + 2u * static_cast<uint32_t>((par * SP + pt) * (NQ * kQM) + rloc);
     };
-    if (QT && g == 0) {
+    if (QT && g == 0 && HD != 256) {
+      // multi-head variant: one thread per row (part 0) moves the D real columns of its query row, zero-padded to 96
+      if (part == 0) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.q + static_cast<long long>(b) * p.bsq +
+                                                          static_cast<long long>(row) * p.ldq + hcol);
+        const int nch = p.D >> 3;
+        uint32_t w0[32], w1[16];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          uint4 t = make_uint4(0u, 0u, 0u, 0u);
+          if (row < p.Lq && i < nch) t = __ldg(src + i);
+          if (i < 8) {
+            w0[4 * i] = t.x;
+            w0[4 * i + 1] = t.y;
+            w0[4 * i + 2] = t.z;
+            w0[4 * i + 3] = t.w;
+          } else {
+            w1[4 * (i - 8)] = t.x;
+            w1[4 * (i - 8) + 1] = t.y;
+            w1[4 * (i - 8) + 2] = t.z;
+            w1[4 * (i - 8) + 3] = t.w;
+          }
+        }
+        const uint32_t tq = tmem_q(h) + lane_off;
+        tc::tmem_st32(tq, w0);
+        tc::tmem_st16(tq + 32, w1);
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(bar(o_q, h));
+      }
+    } else if (QT && g == 0) {
       // this thread's part of its query row: global -> registers -> TMEM (bf16 pairs, K-major A operand)
       constexpr int QW = (kHD / 2) / SP;  // 32-bit columns per thread
       const uint4* src = reinterpret_cast<const uint4*>(p.q + static_cast<long long>(b) * p.bsq +
@@ -468,13 +520,23 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         // O is stable here: P·V of tile j-1 is complete and P·V of tile j is not yet issued
         tc::tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < OW / 32; ++c) {
+        for (int c = 0; c < N32; ++c) {
           uint32_t o[32];
           tc::tmem_ld32(to + c * 32, o);
           tc::tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
           tc::tmem_st32(to + c * 32, o);
+        }
+        if constexpr (kOdd) {
+          if (has16) {
+            uint32_t o[16];
+            tc::tmem_ld16(to16, o);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tc::tmem_st16(to16, o);
+          }
         }
       }
       tc::tmem_st_wait();
@@ -509,7 +571,8 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       tc::mbar_wait(bar(o_odone, h * IL + g), (jl / IL) & 1);
     }
     tc::tc_fence_after();
-    __nv_bfloat16* orow = p.out + static_cast<long long>(b) * p.bso + static_cast<long long>(row) * p.ldo + part * OW;
+    __nv_bfloat16* orow = p.out + static_cast<long long>(b) * p.bso + static_cast<long long>(row) * p.ldo +
+                          (kOdd ? hcol + (SP == 1 ? 0 : part * 32) : part * OW);
     if constexpr (TP) {
       // ---- two key halves: this CTA's (last) half goes to the workspace, then the halves are combined in part
       //      order by this CTA (it ran both) or by the item's CTA that arrives last ----
@@ -627,6 +690,49 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
           }
         }
       }
+    } else if constexpr (kOdd) {
+      // ---- multi-head variant: only the D real columns of the head leave the CTA ----
+      const float inv = 1.0f / l;
+      const int nch = p.D >> 3;                              // 8-column groups of the head (9 at D = 72)
+      const int g0 = SP == 1 ? 0 : part * 4;                 // first group of this thread's 32-column chunks
+#pragma unroll
+      for (int c = 0; c < N32; ++c) {
+        uint32_t o[32];
+        tc::tmem_ld32(to + c * 32, o);
+        tc::tmem_ld_wait();
+        if (row < p.Lq) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (g0 + 4 * c + i < nch) {
+              uint4 t;
+              t.x = tc::pack_bf16(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+              t.y = tc::pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+              t.z = tc::pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+              t.w = tc::pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+              reinterpret_cast<uint4*>(orow + c * 32)[i] = t;
+            }
+          }
+        }
+      }
+      if (has16) {
+        uint32_t o[16];
+        tc::tmem_ld16(to16, o);
+        tc::tmem_ld_wait();
+        if (row < p.Lq) {
+          __nv_bfloat16* o64 = p.out + static_cast<long long>(b) * p.bso + static_cast<long long>(row) * p.ldo + hcol + 64;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            if (8 + i < nch) {
+              uint4 t;
+              t.x = tc::pack_bf16(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+              t.y = tc::pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+              t.z = tc::pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+              t.w = tc::pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+              reinterpret_cast<uint4*>(o64)[i] = t;
+            }
+          }
+        }
+      }
     } else {
     const float inv = 1.0f / l;
 #pragma unroll
@@ -706,27 +812,29 @@ static bool flash_two_phase(const ds2_flash_args* a, int BN, int DV) {
 
 static inline int all_tiles_of(const ds2_flash_args* a, int bn) { return (a->Lk + bn - 1) / bn; }
 
-template <int DV, int BN, int NQ, int KS, int VS, int SP, int QT, int IL = 1, int TP = 0>
-static int launch_flash(const ds2_flash_args* a, cudaStream_t st) {
-  using Cfg = FlashCfg<DV, BN, NQ, KS, VS, SP, QT, IL, TP>;
+template <int DV, int BN, int NQ, int KS, int VS, int SP, int QT, int IL = 1, int TP = 0, int HD = 256>
+static int launch_flash(const ds2_flash_args* a, cudaStream_t st, int H = 1, int D = 0) {
+  using Cfg = FlashCfg<DV, BN, NQ, KS, VS, SP, QT, IL, TP, HD>;
   CUtensorMap tq, tk, tv;
+  // multi-head variant: the maps span the H * D columns of all heads (boxes reaching past them are zero-filled)
+  const uint64_t kcols = HD == 256 ? 256 : static_cast<uint64_t>(H) * D;
+  const uint64_t vcols = HD == 256 ? static_cast<uint64_t>(DV) : static_cast<uint64_t>(H) * D;
   {
-    const uint64_t dims[3] = {256, static_cast<uint64_t>(a->Lq), static_cast<uint64_t>(a->B)};
+    const uint64_t dims[3] = {kcols, static_cast<uint64_t>(a->Lq), static_cast<uint64_t>(a->B)};
     const uint64_t str[2] = {static_cast<uint64_t>(a->ldq) * 2, static_cast<uint64_t>(a->bsq) * 2};
     const uint32_t box[3] = {64, kQM, 1};
     int rc = make_tmap_bf16(&tq, a->q, 3, dims, str, box);
     if (rc) return rc;
   }
   {
-    const uint64_t dims[3] = {256, static_cast<uint64_t>(a->Lk), static_cast<uint64_t>(a->B)};
+    const uint64_t dims[3] = {kcols, static_cast<uint64_t>(a->Lk), static_cast<uint64_t>(a->B)};
     const uint64_t str[2] = {static_cast<uint64_t>(a->ldk) * 2, static_cast<uint64_t>(a->bsk) * 2};
     const uint32_t box[3] = {64, BN, 1};
     int rc = make_tmap_bf16(&tk, a->k, 3, dims, str, box);
     if (rc) return rc;
   }
   {
-    const uint64_t dims[3] = {static_cast<uint64_t>(DV), static_cast<uint64_t>(a->Lk),
-                              static_cast<uint64_t>(a->B)};
+    const uint64_t dims[3] = {vcols, static_cast<uint64_t>(a->Lk), static_cast<uint64_t>(a->B)};
     const uint64_t str[2] = {static_cast<uint64_t>(a->ldv) * 2, static_cast<uint64_t>(a->bsv) * 2};
     const uint32_t box[3] = {64, BN, 1};
     int rc = make_tmap_bf16(&tv, a->v, 3, dims, str, box);
@@ -734,7 +842,7 @@ static int launch_flash(const ds2_flash_args* a, cudaStream_t st) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(flash_d256_tcgen05_kernel<DV, BN, NQ, KS, VS, SP, QT, IL, TP>,
+    cudaError_t e = cudaFuncSetAttribute(flash_d256_tcgen05_kernel<DV, BN, NQ, KS, VS, SP, QT, IL, TP, HD>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
     DS2_REQUIRE(e == cudaSuccess, static_cast<int>(e), "ds2_flash_attn: cudaFuncSetAttribute: %s",
                 cudaGetErrorString(e));
@@ -752,9 +860,11 @@ static int launch_flash(const ds2_flash_args* a, cudaStream_t st) {
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   p.ldo = a->ldo;
   p.bso = a->bso;
+  p.H = H;
+  p.D = D;
   // ---- grid: whole items + (two-phase only) the items of the partial last wave as two half-length CTAs each ----
   p.q_tiles = (a->Lq + kQM * NQ - 1) / (kQM * NQ);
-  const int items = p.q_tiles * a->B;
+  const int items = p.q_tiles * a->B * H;
   const int sms = sm_count();
   DS2_REQUIRE(sms > 0, DS2_E_NODEVICE, "ds2_flash_attn: no CUDA device");
   const int all_tiles = (a->Lk + BN - 1) / BN;
@@ -777,8 +887,46 @@ static int launch_flash(const ds2_flash_args* a, cudaStream_t st) {
   p.ws_count = reinterpret_cast<unsigned int*>(a->workspace);
   p.ws = p.two_phase ? reinterpret_cast<float*>(reinterpret_cast<char*>(a->workspace) + flash_ws_count_bytes(items)) : nullptr;
   const int grid = p.n_full + 2 * tail;
-  DS2_LAUNCH((flash_d256_tcgen05_kernel<DV, BN, NQ, KS, VS, SP, QT, IL, TP>), grid, Cfg::kThreads, Cfg::kSmem, st, tq, tk, tv, p);
+  DS2_LAUNCH((flash_d256_tcgen05_kernel<DV, BN, NQ, KS, VS, SP, QT, IL, TP, HD>), grid, Cfg::kThreads, Cfg::kSmem, st, tq, tk, tv, p);
   return post_launch("flash_d256_tcgen05_kernel");
+}
+
+// Hiera global attention (window_size == 0 blocks, hieradet.py:57-82) on the flash kernel: head_dim in (64, 80], H heads side
+// by side in the token-major qkv matrix.  Returns -1 for shapes it does not cover (ds2_mha then takes the next kernel).
+int launch_glob_flash(const ds2_mha_args* a, cudaStream_t st, int sp) {
+  if (a->window != 0 || a->q_pool) return -1;
+  if (a->D <= 64 || a->D > 80 || (a->D % 8) != 0) return -1;
+  if (a->Lq < 128 || (a->Lq % 128) != 0 || a->Lk < 128 || (a->Lk % 128) != 0) return -1;
+  if (a->Lk_valid != 0 && a->Lk_valid != a->Lk) return -1;
+  if ((a->q_tok_stride % 8) || (a->k_tok_stride % 8) || (a->v_tok_stride % 8) || (a->o_tok_stride % 8)) return -1;
+  if ((a->q_bs % 8) || (a->k_bs % 8) || (a->v_bs % 8) || (a->o_bs % 8)) return -1;
+  if ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) | reinterpret_cast<uintptr_t>(a->v) |
+       reinterpret_cast<uintptr_t>(a->out)) & 15)
+    return -1;
+  // a head's columns must lie inside a token's row of every operand (the TMA maps are H * D columns wide)
+  if (a->k_tok_stride < static_cast<int64_t>(a->H) * a->D || a->v_tok_stride < static_cast<int64_t>(a->H) * a->D) return -1;
+  ds2_flash_args f;
+  memset(&f, 0, sizeof(f));
+  f.B = a->B;
+  f.Lq = a->Lq;
+  f.Lk = a->Lk;
+  f.DV = 80;
+  f.q = a->q;
+  f.k = a->k;
+  f.v = a->v;
+  f.out = a->out;
+  f.ldq = a->q_tok_stride;
+  f.ldk = a->k_tok_stride;
+  f.ldv = a->v_tok_stride;
+  f.ldo = a->o_tok_stride;
+  f.bsq = a->q_bs;
+  f.bsk = a->k_bs;
+  f.bsv = a->v_bs;
+  f.bso = a->o_bs;
+  f.scale = a->scale;
+  if (const char* e = getenv("DS2_GLOB_DBG")) f.impl = atoi(e);   // timing experiments (5 = first box of every tile only)
+  if (sp == 2) return launch_flash<80, 128, 1, 3, 2, 2, 1, 1, 0, 80>(&f, st, a->H, a->D);
+  return launch_flash<80, 128, 1, 3, 2, 1, 1, 1, 0, 80>(&f, st, a->H, a->D);
 }
 
 }  // namespace ds2

@@ -799,6 +799,7 @@ static int launch_mha(const MhaParams& p, int nseq, int H, int Lq, cudaStream_t 
 
 int launch_win16_attn_tc(const ds2_mha_args* a, cudaStream_t st);  // win_attn_tc.cu (tcgen05)
 int launch_glob_attn_tc(const ds2_mha_args* a, cudaStream_t st);   // win_attn_tc.cu (tcgen05)
+int launch_glob_flash(const ds2_mha_args* a, cudaStream_t st, int sp);  // flash_tc.cu (tcgen05, TMA ring, Q in TMEM)
 
 }  // namespace ds2
 
@@ -868,6 +869,18 @@ extern "C" int ds2_mha(const ds2_mha_args* a, void* stream) {
     if (win_tc) {
       int rc = launch_win16_attn_tc(a, st);
       if (rc >= 0) return rc;
+      // Global blocks: the flash kernel's multi-head variant (TMA ring, Q in TMEM, S double-buffered): 281 us against 496 us
+      // for the 4-frame launch of the large model.  Measured on the same box (profiles/r2_s17_glob_flash_ab.txt): one or two
+      // softmax threads per row 281 / 281 us, two alternating softmax groups 269 us, half of the TMA boxes 278 us — the
+      // softmax warps are busy ~1 900 of the ~2 100 clk per key tile however the row is split (16 384 exponentials per tile
+      // = 1 024 clk of MUFU per SM, plus the TMEM round trips).  DS2_GLOB_FLASH=0: the serial-chain kernel of
+      // win_attn_tc.cu (A/B), 2: two softmax threads per row.  (read per call: the tests switch it)
+      const char* gf = getenv("DS2_GLOB_FLASH");
+      const int glob_flash = gf ? atoi(gf) : 1;
+      if (glob_flash > 0) {
+        rc = launch_glob_flash(a, st, glob_flash);
+        if (rc >= 0) return rc;
+      }
       rc = launch_glob_attn_tc(a, st);
       if (rc >= 0) return rc;
     }

@@ -310,6 +310,29 @@ def test_mha_dense(ops, B, H, D, Lq, Lk, Lkv):
     assert (o.float() - ref).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("B,H,D,T", [(2, 8, 72, 512), (1, 8, 72, 4096), (3, 2, 80, 256), (1, 5, 72, 128)])
+def test_mha_global_hiera_layout(ops, monkeypatch, mode, B, H, D, T):
+    """Hiera's global-attention blocks (hieradet.py:57-82, window_size 0) in the engine's layout: q, k, v are column
+    sections of one token-major qkv matrix.  DS2_GLOB_FLASH = 1 (default) / 2: the flash kernel's multi-head variant (TMA boxes of
+    64 columns that run past the head — and, for the last head, past the section — into data that must not matter) with
+    one / two softmax threads per row; 0: the serial-chain kernel.  All against fp32 softmax attention; the two flash
+    variants must also agree with each other to bf16 rounding."""
+    monkeypatch.setenv("DS2_GLOB_FLASH", str(mode))
+    torch.manual_seed(11)
+    do = H * D
+    qkv = bf(torch.randn(B * T, 3 * do, device=DEV))
+    # poison everything a careless box could pick up beyond the q / k / v sections of interest
+    out = torch.full((B * T, do), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.mha(qkv, qkv[:, do:], qkv[:, 2 * do:], out, heads=H, head_dim=D, scale=D ** -0.5, B=B, Lq=T, Lk=T,
+            strides=(3 * do, 3 * do, 3 * do, do, T * 3 * do, T * 3 * do, T * 3 * do, T * do))
+    q, k, v = (qkv[:, i * do:(i + 1) * do].reshape(B, T, H, D) for i in range(3))
+    ref = _mha_ref(q, k, v, D ** -0.5)
+    got = out.view(B, T, H, D).float()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() < 2e-2
+
+
 def _window_partition(x, w):
     B, H, W, C = x.shape
     ph, pw = (w - H % w) % w, (w - W % w) % w

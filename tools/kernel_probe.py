@@ -82,23 +82,32 @@ def main():
     gemm_case("ma.out   65536x256x256 +res", 65536, 256, 256, out="f32", res=True)
     gemm_case("big      8192x8192x8192", 8192, 8192, 8192)
 
-    def mha_case(name, T, do, heads, window, Hm, pool=0):
-        qkv = torch.randn(T, 3 * do, device=dev).to(BF16)
+    def mha_case(name, T, do, heads, window, Hm, pool=0, B=1, env=None):
+        qkv = torch.randn(B * T, 3 * do, device=dev).to(BF16)
         Tq = T // 4 if pool else T
-        att = torch.zeros(Tq, do, device=dev, dtype=BF16)
+        att = torch.zeros(B * Tq, do, device=dev, dtype=BF16)
         hd = do // heads
         Lk = window * window if window else T
         Lq = (Lk // 4 if pool else Lk) if window else Tq
         nseq = (Hm // window) ** 2 if window else 1
-        fl = 4.0 * nseq * heads * Lq * Lk * hd
-        cases.append((name, lambda: ops.mha(qkv, qkv[:, do:], qkv[:, 2 * do:], att, heads=heads, head_dim=hd,
-                                            scale=1.0 / math.sqrt(hd), B=1, Lq=Tq if window == 0 else 0,
-                                            Lk=T if window == 0 else 0,
-                                            strides=(3 * do, 3 * do, 3 * do, do, T * 3 * do, T * 3 * do, T * 3 * do, Tq * do),
-                                            window=window, Hm=Hm, Wm=Hm, q_pool=pool), fl, None))
+        fl = 4.0 * B * nseq * heads * Lq * Lk * hd
+
+        def run():
+            if env:
+                os.environ.update(env)      # kernel selection switches that the library reads per call
+            ops.mha(qkv, qkv[:, do:], qkv[:, 2 * do:], att, heads=heads, head_dim=hd,
+                    scale=1.0 / math.sqrt(hd), B=B, Lq=Tq if window == 0 else 0,
+                    Lk=T if window == 0 else 0,
+                    strides=(3 * do, 3 * do, 3 * do, do, T * 3 * do, T * 3 * do, T * 3 * do, Tq * do),
+                    window=window, Hm=Hm, Wm=Hm, q_pool=pool)
+        cases.append((name, run, fl, None))
 
     mha_case("mha s3 win16 8h", 4096, 576, 8, 16, 64)
     mha_case("mha s3 global 8h", 4096, 576, 8, 0, 64)
+    for mode, nm in ((0, "serial-chain kernel"), (1, "flash variant, 1 softmax thread/row"), (2, "flash variant, 2 softmax threads/row")):
+        mha_case(f"mha s3 global 8h x4 frames ({nm})", 4096, 576, 8, 0, 64, B=4, env={"DS2_GLOB_FLASH": str(mode), "DS2_GLOB_DBG": "0"})
+    mha_case("mha s3 global 8h x4 frames (flash variant, first TMA box only: wrong results)", 4096, 576, 8, 0, 64, B=4,
+             env={"DS2_GLOB_FLASH": "2", "DS2_GLOB_DBG": "5"})
     mha_case("mha s2 win4 4h", 16384, 288, 4, 4, 128)
     mha_case("mha s1 win8 2h", 65536, 144, 2, 8, 256)
 
