@@ -56,6 +56,9 @@ struct FlashParams {
   const __nv_bfloat16* q;  // QT kernels read the query rows straight from global memory
   long long ldq, bsq;
   int H, D;                // HD == 80 kernels (Hiera global attention): heads per batch item, head h at column h * D
+  // HD == 80, window mode (win_nwin > 0): an item is one 128-row half of a 16 x 16 window of the [Hm, Wm] token raster
+  // (Lq = Lk = 256); K / V tiles are boxes {64 columns, 16 x, 8 y} of a rank-4 map {columns, x, y, batch}
+  int win_nwin, win_nwx, Wm;
   __nv_bfloat16* out;
   long long ldo, bso;
 };
@@ -156,8 +159,20 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     kv_parts = 2;
   }
   const int q0 = (item % p.q_tiles) * (kQM * NQ);
-  const int b = HD == 256 ? item / p.q_tiles : (item / p.q_tiles) / p.H;
   const int hcol = HD == 256 ? 0 : ((item / p.q_tiles) % p.H) * p.D;   // first column of this CTA's head
+  const bool win = HD != 256 && p.win_nwin > 0;
+  int b = HD == 256 ? item / p.q_tiles : (item / p.q_tiles) / p.H;
+  int wx16 = 0, wy16 = 0;               // first raster column / row of the window
+  if (win) {
+    const int w = b % p.win_nwin;
+    b /= p.win_nwin;
+    wy16 = (w / p.win_nwx) * 16;
+    wx16 = (w % p.win_nwx) * 16;
+  }
+  // token (row of the q / out matrices inside batch item b) of query row `r` of this item's sequence
+  auto tok_of = [&](int r) -> long long {
+    return win ? static_cast<long long>(wy16 + (r >> 4)) * p.Wm + wx16 + (r & 15) : static_cast<long long>(r);
+  };
   const int all_tiles = (p.Lk + BN - 1) / BN;
   const int j0 = (all_tiles * kv_part) / kv_parts;                     // first key tile of this CTA
   const int n_tiles = (all_tiles * (kv_part + 1)) / kv_parts - j0;    // its number of key tiles (>= 1)
@@ -230,8 +245,10 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const int nkk = (p.dbg == 1) ? Cfg::kKBox / 2 : Cfg::kKBox;   // (timing experiment: half of the boxes)
         tc::mbar_expect_tx(bar(o_kfull, s), nkk * (BN * 128));
         const uint32_t sk = sk0 + s * Cfg::kKBytes;
-        for (int kk = 0; kk < nkk; ++kk)
-          tc::tma_load_3d(sk + kk * (BN * 128), &tmap_k, bar(o_kfull, s), hcol + kk * 64, (j0 + j) * BN, b);
+        for (int kk = 0; kk < nkk; ++kk) {
+          if (win) tc::tma_load_4d(sk + kk * (BN * 128), &tmap_k, bar(o_kfull, s), hcol + kk * 64, wx16, wy16 + (j0 + j) * (BN / 16), b);
+          else tc::tma_load_3d(sk + kk * (BN * 128), &tmap_k, bar(o_kfull, s), hcol + kk * 64, (j0 + j) * BN, b);
+        }
       }
       {
         const int s = j % VS;
@@ -239,8 +256,10 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const int nvb = (HD != 256 && p.dbg == 1) ? 1 : Cfg::kVBox;
         tc::mbar_expect_tx(bar(o_vfull, s), nvb * (BN * 128));
         const uint32_t sv = sv0 + s * Cfg::kVBytes;
-        for (int nn = 0; nn < nvb; ++nn)
-          tc::tma_load_3d(sv + nn * (BN * 128), &tmap_v, bar(o_vfull, s), hcol + nn * 64, (j0 + j) * BN, b);
+        for (int nn = 0; nn < nvb; ++nn) {
+          if (win) tc::tma_load_4d(sv + nn * (BN * 128), &tmap_v, bar(o_vfull, s), hcol + nn * 64, wx16, wy16 + (j0 + j) * (BN / 16), b);
+          else tc::tma_load_3d(sv + nn * (BN * 128), &tmap_v, bar(o_vfull, s), hcol + nn * 64, (j0 + j) * BN, b);
+        }
       }
     }
   } else if (warp == 1 && tc::elect_one()) {
@@ -334,8 +353,7 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
     if (QT && g == 0 && HD != 256) {
       // multi-head variant: one thread per row (part 0) moves the D real columns of its query row, zero-padded to 96
       if (part == 0) {
-        const uint4* src = reinterpret_cast<const uint4*>(p.q + static_cast<long long>(b) * p.bsq +
-                                                          static_cast<long long>(row) * p.ldq + hcol);
+        const uint4* src = reinterpret_cast<const uint4*>(p.q + static_cast<long long>(b) * p.bsq + tok_of(row) * p.ldq + hcol);
         const int nch = p.D >> 3;
         uint32_t w0[32], w1[16];
 #pragma unroll
@@ -571,7 +589,7 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
       tc::mbar_wait(bar(o_odone, h * IL + g), (jl / IL) & 1);
     }
     tc::tc_fence_after();
-    __nv_bfloat16* orow = p.out + static_cast<long long>(b) * p.bso + static_cast<long long>(row) * p.ldo +
+    __nv_bfloat16* orow = p.out + static_cast<long long>(b) * p.bso + (kOdd ? tok_of(row) : static_cast<long long>(row)) * p.ldo +
                           (kOdd ? hcol + (SP == 1 ? 0 : part * 32) : part * OW);
     if constexpr (TP) {
       // ---- two key halves: this CTA's (last) half goes to the workspace, then the halves are combined in part
@@ -719,7 +737,7 @@ flash_d256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tc::tmem_ld16(to16, o);
         tc::tmem_ld_wait();
         if (row < p.Lq) {
-          __nv_bfloat16* o64 = p.out + static_cast<long long>(b) * p.bso + static_cast<long long>(row) * p.ldo + hcol + 64;
+          __nv_bfloat16* o64 = p.out + static_cast<long long>(b) * p.bso + tok_of(row) * p.ldo + hcol + 64;
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             if (8 + i < nch) {
@@ -813,7 +831,7 @@ static bool flash_two_phase(const ds2_flash_args* a, int BN, int DV) {
 static inline int all_tiles_of(const ds2_flash_args* a, int bn) { return (a->Lk + bn - 1) / bn; }
 
 template <int DV, int BN, int NQ, int KS, int VS, int SP, int QT, int IL = 1, int TP = 0, int HD = 256>
-static int launch_flash(const ds2_flash_args* a, cudaStream_t st, int H = 1, int D = 0) {
+static int launch_flash(const ds2_flash_args* a, cudaStream_t st, int H = 1, int D = 0, int win_Hm = 0, int win_Wm = 0) {
   using Cfg = FlashCfg<DV, BN, NQ, KS, VS, SP, QT, IL, TP, HD>;
   CUtensorMap tq, tk, tv;
   // multi-head variant: the maps span the H * D columns of all heads (boxes reaching past them are zero-filled)
@@ -826,6 +844,17 @@ static int launch_flash(const ds2_flash_args* a, cudaStream_t st, int H = 1, int
     int rc = make_tmap_bf16(&tq, a->q, 3, dims, str, box);
     if (rc) return rc;
   }
+  if (win_Wm > 0) {
+    // window mode: {columns, x, y, batch}; a key tile is 8 raster rows of the 16-token-wide window
+    for (int m = 0; m < 2; ++m) {
+      const int64_t ld = m == 0 ? a->ldk : a->ldv, bs = m == 0 ? a->bsk : a->bsv;
+      const uint64_t dims[4] = {kcols, static_cast<uint64_t>(win_Wm), static_cast<uint64_t>(win_Hm), static_cast<uint64_t>(a->B)};
+      const uint64_t str[3] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * win_Wm, static_cast<uint64_t>(bs) * 2};
+      const uint32_t box[4] = {64, 16, BN / 16, 1};
+      int rc = make_tmap_bf16(m == 0 ? &tk : &tv, m == 0 ? a->k : a->v, 4, dims, str, box);
+      if (rc) return rc;
+    }
+  } else {
   {
     const uint64_t dims[3] = {kcols, static_cast<uint64_t>(a->Lk), static_cast<uint64_t>(a->B)};
     const uint64_t str[2] = {static_cast<uint64_t>(a->ldk) * 2, static_cast<uint64_t>(a->bsk) * 2};
@@ -839,6 +868,7 @@ static int launch_flash(const ds2_flash_args* a, cudaStream_t st, int H = 1, int
     const uint32_t box[3] = {64, BN, 1};
     int rc = make_tmap_bf16(&tv, a->v, 3, dims, str, box);
     if (rc) return rc;
+  }
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -862,9 +892,12 @@ static int launch_flash(const ds2_flash_args* a, cudaStream_t st, int H = 1, int
   p.bso = a->bso;
   p.H = H;
   p.D = D;
+  p.Wm = win_Wm;
+  p.win_nwx = win_Wm / 16;
+  p.win_nwin = (win_Hm / 16) * (win_Wm / 16);
   // ---- grid: whole items + (two-phase only) the items of the partial last wave as two half-length CTAs each ----
   p.q_tiles = (a->Lq + kQM * NQ - 1) / (kQM * NQ);
-  const int items = p.q_tiles * a->B * H;
+  const int items = p.q_tiles * a->B * H * (win_Wm > 0 ? p.win_nwin : 1);
   const int sms = sm_count();
   DS2_REQUIRE(sms > 0, DS2_E_NODEVICE, "ds2_flash_attn: no CUDA device");
   const int all_tiles = (a->Lk + BN - 1) / BN;
@@ -894,10 +927,15 @@ static int launch_flash(const ds2_flash_args* a, cudaStream_t st, int H = 1, int
 // Hiera global attention (window_size == 0 blocks, hieradet.py:57-82) on the flash kernel: head_dim in (64, 80], H heads side
 // by side in the token-major qkv matrix.  Returns -1 for shapes it does not cover (ds2_mha then takes the next kernel).
 int launch_glob_flash(const ds2_mha_args* a, cudaStream_t st, int sp) {
-  if (a->window != 0 || a->q_pool) return -1;
+  const bool win = a->window == 16;     // 16 x 16 windows: 256 queries x 256 keys per (window, head)
+  if ((a->window != 0 && !win) || a->q_pool) return -1;
   if (a->D <= 64 || a->D > 80 || (a->D % 8) != 0) return -1;
-  if (a->Lq < 128 || (a->Lq % 128) != 0 || a->Lk < 128 || (a->Lk % 128) != 0) return -1;
-  if (a->Lk_valid != 0 && a->Lk_valid != a->Lk) return -1;
+  if (win) {
+    if ((a->Hm % 16) != 0 || (a->Wm % 16) != 0 || a->Hm <= 0 || a->Wm <= 0) return -1;
+  } else {
+    if (a->Lq < 128 || (a->Lq % 128) != 0 || a->Lk < 128 || (a->Lk % 128) != 0) return -1;
+    if (a->Lk_valid != 0 && a->Lk_valid != a->Lk) return -1;
+  }
   if ((a->q_tok_stride % 8) || (a->k_tok_stride % 8) || (a->v_tok_stride % 8) || (a->o_tok_stride % 8)) return -1;
   if ((a->q_bs % 8) || (a->k_bs % 8) || (a->v_bs % 8) || (a->o_bs % 8)) return -1;
   if ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) | reinterpret_cast<uintptr_t>(a->v) |
@@ -908,8 +946,8 @@ int launch_glob_flash(const ds2_mha_args* a, cudaStream_t st, int sp) {
   ds2_flash_args f;
   memset(&f, 0, sizeof(f));
   f.B = a->B;
-  f.Lq = a->Lq;
-  f.Lk = a->Lk;
+  f.Lq = win ? 256 : a->Lq;
+  f.Lk = win ? 256 : a->Lk;
   f.DV = 80;
   f.q = a->q;
   f.k = a->k;
@@ -925,8 +963,9 @@ int launch_glob_flash(const ds2_mha_args* a, cudaStream_t st, int sp) {
   f.bso = a->o_bs;
   f.scale = a->scale;
   if (const char* e = getenv("DS2_GLOB_DBG")) f.impl = atoi(e);   // timing experiments (5 = first box of every tile only)
-  if (sp == 2) return launch_flash<80, 128, 1, 3, 2, 2, 1, 1, 0, 80>(&f, st, a->H, a->D);
-  return launch_flash<80, 128, 1, 3, 2, 1, 1, 1, 0, 80>(&f, st, a->H, a->D);
+  const int Hm = win ? a->Hm : 0, Wm = win ? a->Wm : 0;
+  if (sp == 2) return launch_flash<80, 128, 1, 3, 2, 2, 1, 1, 0, 80>(&f, st, a->H, a->D, Hm, Wm);
+  return launch_flash<80, 128, 1, 3, 2, 1, 1, 1, 0, 80>(&f, st, a->H, a->D, Hm, Wm);
 }
 
 }  // namespace ds2

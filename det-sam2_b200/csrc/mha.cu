@@ -867,7 +867,14 @@ extern "C" int ds2_mha(const ds2_mha_args* a, void* stream) {
       return !(e && e[0] == '0');
     }();
     if (win_tc) {
-      int rc = launch_win16_attn_tc(a, st);
+      int rc = -1;
+      // DS2_WIN_FLASH=1: 16 x 16 windows through the flash kernel's multi-head variant (two 128-row items per window)
+      const char* wf = getenv("DS2_WIN_FLASH");
+      if (wf && atoi(wf) > 0 && a->window == 16) {
+        rc = launch_glob_flash(a, st, atoi(wf));
+        if (rc >= 0) return rc;
+      }
+      rc = launch_win16_attn_tc(a, st);
       if (rc >= 0) return rc;
       // Global blocks: the flash kernel's multi-head variant (TMA ring, Q in TMEM, S double-buffered): 281 us against 496 us
       // for the 4-frame launch of the large model.  Measured on the same box (profiles/r2_s17_glob_flash_ab.txt): one or two
@@ -877,7 +884,7 @@ extern "C" int ds2_mha(const ds2_mha_args* a, void* stream) {
       // win_attn_tc.cu (A/B), 2: two softmax threads per row.  (read per call: the tests switch it)
       const char* gf = getenv("DS2_GLOB_FLASH");
       const int glob_flash = gf ? atoi(gf) : 1;
-      if (glob_flash > 0) {
+      if (glob_flash > 0 && a->window == 0) {
         rc = launch_glob_flash(a, st, glob_flash);
         if (rc >= 0) return rc;
       }

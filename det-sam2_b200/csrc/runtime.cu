@@ -41,13 +41,13 @@ static EncodeTiledFn get_encode() {
 }
 
 struct TmapKey {
-  uint64_t v[12];
+  uint64_t v[16];
   bool operator==(const TmapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
 };
 struct TmapKeyHash {
   size_t operator()(const TmapKey& k) const {
     uint64_t h = 1469598103934665603ull;
-    for (int i = 0; i < 12; ++i) {
+    for (int i = 0; i < 16; ++i) {
       h ^= k.v[i];
       h *= 1099511628211ull;
     }
@@ -69,7 +69,7 @@ int make_tmap(CUtensorMap* out, const void* base, int elt_bytes, int swizzle_byt
   DS2_REQUIRE(swizzle_bytes == 64 || swizzle_bytes == 128, DS2_E_ARG, "tensor map swizzle %d unsupported",
               swizzle_bytes);
   DS2_REQUIRE(enc != nullptr, DS2_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
-  DS2_REQUIRE(rank >= 2 && rank <= 3, DS2_E_ARG, "tensor map rank %d unsupported", rank);
+  DS2_REQUIRE(rank >= 2 && rank <= 4, DS2_E_ARG, "tensor map rank %d unsupported", rank);
   DS2_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, DS2_E_ALIGN,
               "TMA base pointer %p not 16-byte aligned", base);
   TmapKey key;
@@ -79,9 +79,9 @@ int make_tmap(CUtensorMap* out, const void* base, int elt_bytes, int swizzle_byt
              (static_cast<uint64_t>(swizzle_bytes) << 16);
   for (int i = 0; i < rank; ++i) {
     key.v[2 + i] = dims[i];
-    key.v[5 + i] = box[i];
+    key.v[6 + i] = box[i];
     if (i > 0) {
-      key.v[8 + i] = strides_bytes[i - 1];
+      key.v[10 + i] = strides_bytes[i - 1];
       DS2_REQUIRE((strides_bytes[i - 1] & 15) == 0, DS2_E_ALIGN,
                   "TMA stride %llu bytes not a multiple of 16",
                   static_cast<unsigned long long>(strides_bytes[i - 1]));
@@ -95,10 +95,10 @@ int make_tmap(CUtensorMap* out, const void* base, int elt_bytes, int swizzle_byt
       return DS2_OK;
     }
   }
-  cuuint64_t gdim[3];
-  cuuint64_t gstr[2];
-  cuuint32_t bx[3];
-  cuuint32_t estr[3] = {1, 1, 1};
+  cuuint64_t gdim[4];
+  cuuint64_t gstr[3];
+  cuuint32_t bx[4];
+  cuuint32_t estr[4] = {1, 1, 1, 1};
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];

@@ -359,6 +359,19 @@ def _window_unpartition(win, w, pad_hw, hw):
                                                 # 16x16 windows with head_dim in (64, 80]: the tcgen05 kernel
                                                 (64, 16, 8, 72, 0), (32, 16, 3, 80, 0), (16, 16, 1, 72, 0)])
 def test_mha_window(ops, Hm, w, heads, D, pool):
+    _mha_window_case(ops, Hm, w, heads, D, pool)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("Hm,heads,D", [(64, 8, 72), (32, 3, 80), (16, 1, 72), (48, 4, 72)])
+def test_mha_window16_on_flash_variant(ops, monkeypatch, mode, Hm, heads, D):
+    """DS2_WIN_FLASH: the 16 x 16 windows as two 128-row items each of the flash kernel's multi-head variant (key tiles are
+    TMA boxes {64 columns, 16 x, 8 y} of the token raster) — same reference as the window kernel."""
+    monkeypatch.setenv("DS2_WIN_FLASH", str(mode))
+    _mha_window_case(ops, Hm, 16, heads, D, 0)
+
+
+def _mha_window_case(ops, Hm, w, heads, D, pool):
     """qkv token-major [B, Hm*Wm, 3*heads*D] exactly as MultiScaleAttention consumes it
     (hieradet.py:57-82), including zero-pad windows whose pad tokens carry the qkv bias."""
     torch.manual_seed(8)

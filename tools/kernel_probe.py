@@ -104,6 +104,8 @@ def main():
 
     mha_case("mha s3 win16 8h", 4096, 576, 8, 16, 64)
     mha_case("mha s3 global 8h", 4096, 576, 8, 0, 64)
+    for mode, nm in ((0, "window kernel"), (1, "flash variant, 1 softmax thread/row"), (2, "flash variant, 2 softmax threads/row")):
+        mha_case(f"mha s3 win16 8h x4 frames ({nm})", 4096, 576, 8, 16, 64, B=4, env={"DS2_WIN_FLASH": str(mode)})
     for mode, nm in ((0, "serial-chain kernel"), (1, "flash variant, 1 softmax thread/row"), (2, "flash variant, 2 softmax threads/row")):
         mha_case(f"mha s3 global 8h x4 frames ({nm})", 4096, 576, 8, 0, 64, B=4, env={"DS2_GLOB_FLASH": str(mode), "DS2_GLOB_DBG": "0"})
     mha_case("mha s3 global 8h x4 frames (flash variant, first TMA box only: wrong results)", 4096, 576, 8, 0, 64, B=4,
