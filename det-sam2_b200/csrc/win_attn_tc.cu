@@ -147,6 +147,29 @@ __global__ void __launch_bounds__(kWinThreads, 1) win16_attn_tc_kernel(const Win
     __syncthreads();
     tc::tc_fence_after();
     if (threadIdx.x == 0) WIN_T(3);
+    // Q K^T goes to the tensor pipe BEFORE the MMA warp stores its share of V (it used to sit behind those stores and the
+    // V loads they wait for: ~1 500 clk of the CTA's ~16 000, DS2_WIN_DBG=1)
+    uint32_t tb;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tb) : "r"(tmem_slot));
+    if (warp == 8 && tc::elect_one()) {
+      const uint32_t idesc_qk = tc::make_idesc_bf16(128, 256, 0, 0);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t d = tb + 256u * h;
+        const uint32_t sqh = sq + h * (128 * 128);
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks) {
+          // K-steps 0..3: dims 16ks..16ks+15 of block 0; K-step 4: dims 64..79 = first 32 bytes of block 1
+          const uint32_t off = ks < 4 ? ks * 32 : kBlkBytes;
+          const uint64_t da = tc::make_desc_sw128(sqh + off, 16, 1024);
+          const uint64_t db = tc::make_desc_sw128(sk + off, 16, 1024);
+          tc::umma_ss(d, da, db, idesc_qk, ks != 0 ? 1u : 0u);
+        }
+        tc::umma_commit(bar_s(h));
+      }
+      WIN_T(9);
+    }
+    __syncwarp();
     store(2, val[0]);
     tc::fence_proxy_async_smem();
     tc::mbar_arrive(bar_v);
@@ -155,24 +178,8 @@ __global__ void __launch_bounds__(kWinThreads, 1) win16_attn_tc_kernel(const Win
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 8 && tc::elect_one()) {
-    // ------------------------------ MMA issuer ------------------------------
-    const uint32_t idesc_qk = tc::make_idesc_bf16(128, 256, 0, 0);
+    // ------------------------------ MMA issuer (P V) ------------------------------
     const uint32_t idesc_pv = tc::make_idesc_bf16(128, 80, 0, 1);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const uint32_t d = tmem_base + 256u * h;
-      const uint32_t sqh = sq + h * (128 * 128);
-#pragma unroll
-      for (int ks = 0; ks < 5; ++ks) {
-        // K-steps 0..3: dims 16ks..16ks+15 of block 0; K-step 4: dims 64..79 = first 32 bytes of block 1
-        const uint32_t off = ks < 4 ? ks * 32 : kBlkBytes;
-        const uint64_t da = tc::make_desc_sw128(sqh + off, 16, 1024);
-        const uint64_t db = tc::make_desc_sw128(sk + off, 16, 1024);
-        tc::umma_ss(d, da, db, idesc_qk, ks != 0 ? 1u : 0u);
-      }
-      tc::umma_commit(bar_s(h));
-    }
-    WIN_T(9);
     tc::mbar_wait(bar_v, 0);
     WIN_T(10);
 #pragma unroll
