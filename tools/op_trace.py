@@ -53,6 +53,7 @@ def main():
     yaml = {"tiny": "t", "small": "s", "base_plus": "b+", "large": "l"}[args.model]
     dev = torch.device("cuda", 0)
     pred = build_sam2_video_predictor(f"configs/sam2.1/sam2.1_hiera_{yaml}.yaml", device=dev, seed=0, feature_cache_frames=1)
+    pred.encoder_overlap = False     # per-op times: one stream, nothing running beside the op being timed
     S = pred.cfg.image_size
     vid = BilliardVideo(num_objects=args.objects, height=S, width=S, num_frames=2 + args.prefill + args.steps, seed=0)
     st = pred.init_state(list(vid.frames()), offload_video_to_cpu=False)
