@@ -383,10 +383,15 @@ __global__ void __launch_bounds__(512) win_small_attn_kernel(const MhaParams p, 
       for (int kk = 0; kk < DP / 16; ++kk) {
         qa[kk][0] = *reinterpret_cast<const uint32_t*>(qrow0 + kk * 16 + 2 * t);
         qa[kk][1] = *reinterpret_cast<const uint32_t*>(qrow1 + kk * 16 + 2 * t);
-        qa[kk][2] = *reinterpret_cast<const uint32_t*>(qrow0 + kk * 16 + 8 + 2 * t);
-        qa[kk][3] = *reinterpret_cast<const uint32_t*>(qrow1 + kk * 16 + 8 + 2 * t);
+        if (D < DP && kk == DP / 16 - 1) {
+          // DP - D == 8: columns >= D belong to the next head — whose warp may already be writing its O over its own
+          // query columns (compute-sanitizer racecheck flagged the discarded read); they are never read
+          qa[kk][2] = qa[kk][3] = 0u;
+        } else {
+          qa[kk][2] = *reinterpret_cast<const uint32_t*>(qrow0 + kk * 16 + 8 + 2 * t);
+          qa[kk][3] = *reinterpret_cast<const uint32_t*>(qrow1 + kk * 16 + 8 + 2 * t);
+        }
       }
-      if (D < DP) qa[DP / 16 - 1][2] = qa[DP / 16 - 1][3] = 0u;   // DP - D == 8: columns >= D belong to the next head
     }
     float s[NT][4];
     const __nv_bfloat16* kb = wtok + C + h * D;
