@@ -537,7 +537,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="large", choices=list(_YAML))
     ap.add_argument("--objects", type=int, default=16)
-    ap.add_argument("--prefill", type=int, default=16, help="tracked frames before warm-up so the bank is at steady state")
+    ap.add_argument("--prefill", type=int, default=24, help="tracked frames before warm-up: the bank is at steady state after 16, the rest lets the steady-state graphs replay a few times before anything is timed")
     ap.add_argument("--mode", default="offline", choices=["offline", "stream"],
                     help="offline = BASELINE configs[1] mode A (the bench line); stream = Det-SAM2's VideoProcessor drive (mode B)")
     ap.add_argument("--frames", type=int, default=300, help="--mode stream: length of the stream")
