@@ -25,6 +25,8 @@
 // DV = 64 is the cross-attention case: the 64->256 value projection is applied AFTER P·V by the
 // caller (softmax rows sum to one), which cuts P·V work and V traffic 4x; NQ = 2 halves the K
 // traffic per FLOP (K tiles come out of L2, which is the binding bandwidth here).
+// HD = 80 (the kernel keeps its name) is the multi-head variant for Hiera's global-attention blocks: head_dim 72
+// padded to 80, H heads side by side in the token-major qkv matrix, optional 16 x 16 window addressing — see FlashCfg.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
