@@ -50,6 +50,17 @@ def _peaks():
             "source": "fallback (B200_PROFILING.md)"}
 
 
+def _energy_mj(index):
+    """Board energy counter (mJ since driver load) through NVML, or None.  Its update period is tens of milliseconds, so
+    a difference over the 0.25 s default timed region is good to a few percent only; use --steps 150 for a precise one."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        return pynvml.nvmlDeviceGetTotalEnergyConsumption(pynvml.nvmlDeviceGetHandleByIndex(index))
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -159,6 +170,7 @@ def run_ours(args):
     clocks = None
     launches = 0
     kern = {}
+    energy_j = None
     overlap_default = predictor.encoder_overlap
     # "kernel": a few extra steps of the same workload with the memory-attention seam launched eagerly, so
     # that CUDA events can bracket the dominant kernel (events cannot bracket a node of a replayed graph)
@@ -194,6 +206,7 @@ def run_ours(args):
         prof = args.cuda_profiler and mode == "device"
         if prof:
             torch.cuda.profiler.start()  # ncu --profile-from-start off: only the timed device steps
+        mj0 = _energy_mj(local_rank) if mode == "device" else None
         e0.record()
         h0 = time.perf_counter()
         for _ in range(K):
@@ -201,11 +214,16 @@ def run_ours(args):
         host_ms = (time.perf_counter() - h0) * 1e3   # CPU time to ENQUEUE the K steps (no sync inside)
         e1.record()
         barrier()
+        if mj0 is not None:
+            mj1 = _energy_mj(local_rank)
+            energy_j = (mj1 - mj0) / 1e3 / K if mj1 is not None else None
         if prof:
             torch.cuda.profiler.stop()
         ms = e0.elapsed_time(e1)
         if mode == "device":
             clocks = sampler.stop()
+            if energy_j is not None:
+                clocks["energy_j_per_step"] = round(energy_j, 2)   # NVML energy counter over the timed region / K
             launches = eng.launches_executed() - l0
             graph_replays = eng.graphs.replays
         if mode == "kernel":
