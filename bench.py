@@ -50,14 +50,22 @@ def _peaks():
             "source": "fallback (B200_PROFILING.md)"}
 
 
+_NVML = {}
+
+
 def _energy_mj(index):
     """Board energy counter (mJ since driver load) through NVML, or None.  Its update period is tens of milliseconds, so
-    a difference over the 0.25 s default timed region is good to a few percent only; use --steps 150 for a precise one."""
+    a difference over the 0.25 s default timed region is good to a few percent only; use --steps 150 for a precise one.
+    NVML is initialised on the first call (made long before the timed region); later calls are one driver query."""
     try:
-        import pynvml
-        pynvml.nvmlInit()
-        return pynvml.nvmlDeviceGetTotalEnergyConsumption(pynvml.nvmlDeviceGetHandleByIndex(index))
+        if index not in _NVML:
+            import pynvml
+            pynvml.nvmlInit()
+            _NVML[index] = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(index))
+        nv, h = _NVML[index]
+        return nv.nvmlDeviceGetTotalEnergyConsumption(h) if nv is not None else None
     except Exception:
+        _NVML[index] = (None, None)
         return None
 
 
@@ -69,6 +77,16 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    # nvidia-smi is started well BEFORE the timed region (its start-up holds driver locks for a few hundred milliseconds
+    # and stalled this process's launches when it fell inside a 0.25 s region: one run read 22.5 ms per step, host-bound);
+    # only the samples that arrive between begin() and end() are used
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def start(self):
         try:
@@ -82,7 +100,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -95,7 +113,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = (self.t1 if self.t1 is not None else time.perf_counter()) + 0.12   # a sample covers the ~100 ms before it
+        for ts, r in self.rows:
+            if ts < t0 or ts > t1:
+                continue
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -113,7 +135,10 @@ class ClockSampler:
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm),
-                "power_w": round(statistics.median(pw), 1) if pw else None}   # board power under load (the frame runs at the cap)
+                # board power: nvidia-smi reports a ~1 s moving average and the NVML energy counter lags by tens of
+                # milliseconds, so both read low over the default 0.25 s region; --steps 150 gives 975-986 W / 12.4-12.8 J
+                "power_w": round(statistics.median(pw), 1) if pw else None,
+                "power_note": "moving average; meaningful for timed regions of a second or more (--steps 150)"}
 
 
 def _dist_env():
@@ -189,12 +214,13 @@ def run_ours(args):
                 host_bits.copy_(bits, non_blocking=True)
             return m
 
-        for _ in range(1 + prefill + W):
-            step()
-        barrier()
         if mode == "device":
             sampler = ClockSampler(local_rank)
             sampler.start()
+            _energy_mj(local_rank)      # NVML initialised here, not next to the timed region
+        for _ in range(1 + prefill + W):
+            step()
+        barrier()
         if mode == "kernel":
             eng.kernel_timers = []
         # frames are encoded a few at a time ahead of their step (predictor.encoder_batch_frames): drop what the
@@ -207,6 +233,8 @@ def run_ours(args):
         if prof:
             torch.cuda.profiler.start()  # ncu --profile-from-start off: only the timed device steps
         mj0 = _energy_mj(local_rank) if mode == "device" else None
+        if mode == "device":
+            sampler.begin()
         e0.record()
         h0 = time.perf_counter()
         for _ in range(K):
@@ -214,6 +242,8 @@ def run_ours(args):
         host_ms = (time.perf_counter() - h0) * 1e3   # CPU time to ENQUEUE the K steps (no sync inside)
         e1.record()
         barrier()
+        if mode == "device":
+            sampler.end()
         if mj0 is not None:
             mj1 = _energy_mj(local_rank)
             energy_j = (mj1 - mj0) / 1e3 / K if mj1 is not None else None
