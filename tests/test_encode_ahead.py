@@ -207,3 +207,32 @@ def test_overlapped_encoder_is_bit_identical_on_a_long_forward_run(host_frames):
     assert len(res[False]) == len(res[True]) == 40
     for (fa, ma), (fb, mb) in zip(res[False], res[True]):
         assert fa == fb and torch.equal(ma, mb), fa
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("frames_on_device", [True, False])
+def test_overlapped_encoder_is_bit_identical_in_stream_mode(frames_on_device):
+    """Det-SAM2's own drive mode (VideoProcessor: chunks, detection every few frames, reverse re-tracking over a window,
+    release of old frames, feature cache) with the encoder passes on the engine's stream and without: every handed-out mask
+    identical.  Long enough (40 frames, K = 8, M = 16) that reverse windows span several encoder passes."""
+    from detsam2_b200.engine import CudaEngine
+    from detsam2_b200.synthetic import GroundTruthDetector
+    from detsam2_b200.video_processor import VideoProcessor
+    cfg = get_config("tiny", image_size=512)
+    sd = synthetic_state_dict(cfg, 0)
+    vid = BilliardVideo(num_objects=3, height=240, width=320, num_frames=40, seed=9)
+    res = {}
+    for overlap in (False, True):
+        pred = SAM2VideoPredictor(CudaEngine(cfg, sd), fill_hole_area=8, encoder_batch_frames=4, encoder_overlap=overlap,
+                                  feature_cache_frames=20)
+        vp = VideoProcessor(predictor=pred, detector=GroundTruthDetector(vid, detect_interval=8), frame_buffer_size=8,
+                            detect_interval=8, max_frame_num_to_track=16, max_inference_state_frames=16, skip_classes=set(),
+                            frames_on_device=frames_on_device)
+        with torch.inference_mode():
+            res[overlap] = vp.run(frames=(vid.frame(t) for t in range(40)))
+        assert pred.encoder_overlap == overlap and pred._pending is None
+    assert sorted(res[False]) == sorted(res[True]) == list(range(40))
+    for t in range(40):
+        assert sorted(res[False][t]) == sorted(res[True][t])
+        for oid, m in res[False][t].items():
+            assert np.array_equal(m, res[True][t][oid]), (t, oid)
