@@ -225,7 +225,8 @@ def run_ours(args):
             eng.kernel_timers = []
         # frames are encoded a few at a time ahead of their step (predictor.encoder_batch_frames): drop what the
         # warm-up steps encoded ahead, so that every frame tracked in the timed region is also encoded inside it
-        predictor.drop_encoded_ahead()
+        if not args.keep_encoded_ahead:
+            predictor.drop_encoded_ahead()
         l0 = eng.launches_executed()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -595,6 +596,9 @@ def main():
     ap.add_argument("--no-extra-legs", action="store_true", help="skip the stream_mode and gpu_library_baseline legs")
     ap.add_argument("--only-device", action="store_true", help="A/B helper: time the device-resident leg only")
     ap.add_argument("--cuda-profiler", action="store_true", help="bracket the timed device steps with cudaProfilerStart/Stop")
+    ap.add_argument("--keep-encoded-ahead", action="store_true",
+                    help="profiling helper (with --only-device): keep the features the warm-up encoded ahead, so that the bracketed "
+                         "steps hold the tracker's kernels only; never a bench line")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--cpu-budget-ref", type=float, default=150.0)
     args = ap.parse_args()
